@@ -1,0 +1,133 @@
+"""Shared definition of the parity cases.
+
+The same table drives (i) ``oracle/ref_harness/run_reference.py`` — which builds the REFERENCE's
+controllers from it inside the development container and writes ``tests/golden/*.npz`` — and
+(ii) the parity tests, which build this repo's controllers from it.  Pure data: no imports from
+either implementation.
+
+Controller parameterisations follow the reference's examples:
+  * config 1  /root/reference/examples/PyGame/force_osc_xy.py:20-34
+  * config 3  /root/reference/examples/timing_plots.py:37 + examples/CoppeliaSim/force_osc_xyzabg.py:16-26
+  * config 5  /root/reference/examples/CoppeliaSim/force_osc_xyz_avoid_obstacle.py:17-28,40,74
+"""
+import numpy as np
+
+N_GOLDEN = 32  # states per golden file (kept small: fixtures are committed)
+XOFF = [0.11, -0.07, 0.05]  # non-zero offset inside a frame, exercises the general-x functions
+
+ARMS = {
+    "ur5": dict(n=6, has_C=True, mid="link3"),
+    "jaco2": dict(n=6, has_C=False, mid="link4"),  # C oracle un-generatable
+    "threejoint": dict(n=3, has_C=True, mid="link2"),
+    "twojoint": dict(n=2, has_C=True, mid="link1"),
+}
+
+
+def frames(n):
+    return [f"link{i}" for i in range(n + 1)] + [f"joint{i}" for i in range(n)] + ["EE"]
+
+
+def states(arm, count=N_GOLDEN):
+    """Seeded synthetic joint states: q~U(0,2pi), dq~U(-5,5), target~U(-1,1) (cf. timing_plots.py:18-20)."""
+    n = ARMS[arm]["n"]
+    rng = np.random.default_rng(abs(hash_name(arm)))
+    q = rng.uniform(0, 2 * np.pi, (count, n))
+    dq = rng.uniform(-5, 5, (count, n))
+    target = rng.uniform(-1, 1, (count, 6))
+    target_velocity = rng.uniform(-0.5, 0.5, (count, 6))
+    return q, dq, target, target_velocity
+
+
+def hash_name(s):
+    h = 0
+    for ch in s:
+        h = (h * 131 + ord(ch)) % 1000003
+    return h
+
+
+T, F = True, False
+PI = float(np.pi)
+
+# name -> dict(arm, osc=<OSC kwargs>, null=[(kind, kwargs)...], tv=<use target_velocity>,
+#              ref_frame, xyz_offset)
+OSC_CASES = {
+    # --- UR5 -----------------------------------------------------------------------------------
+    "ur5_xyz": dict(arm="ur5", osc=dict(kp=10)),
+    "ur5_6dof": dict(arm="ur5", osc=dict(kp=30, ko=20, ctrlr_dof=[T] * 6)),
+    "ur5_6dof_C_damp": dict(
+        arm="ur5", osc=dict(kp=50, ctrlr_dof=[T] * 6, use_C=True), null=[("Damping", dict(kv=10))]
+    ),
+    "ur5_6dof_alg1": dict(arm="ur5", osc=dict(kp=25, kv=9, ctrlr_dof=[T] * 6, orientation_algorithm=1)),
+    "ur5_vmax": dict(arm="ur5", osc=dict(kp=10, ko=8, kv=4, ctrlr_dof=[T] * 6, vmax=[0.5, 1.0])),
+    "ur5_tv_offset": dict(
+        arm="ur5",
+        osc=dict(kp=20, ctrlr_dof=[T, T, T, F, T, F]),
+        tv=True,
+        ref_frame="link4",
+        xyz_offset=XOFF,
+    ),
+    "ur5_nog_xz": dict(arm="ur5", osc=dict(kp=5, kv=3, ctrlr_dof=[T, F, T, F, F, F], use_g=False)),
+    "ur5_rest": dict(
+        arm="ur5",
+        osc=dict(kp=40),
+        null=[("RestingConfig", dict(kp=30, kv=6, rest_angles=[None, PI / 4, -PI / 2, PI / 4, None, None]))],
+    ),
+    # --- Jaco2 ---------------------------------------------------------------------------------
+    "jaco2_cfg3": dict(
+        arm="jaco2", osc=dict(kp=200, ctrlr_dof=[T] * 5 + [F]), null=[("Damping", dict(kv=10))]
+    ),
+    "jaco2_cfg5": dict(
+        arm="jaco2",
+        osc=dict(kp=200, vmax=[0.5, 0], ctrlr_dof=[T, T, T, F, F, F]),
+        null=[
+            ("AvoidObstacles", dict(obstacles=[[0.09596, -0.2661, 0.64204, 0.05]], threshold=0.2)),
+            ("Damping", dict(kv=10)),
+        ],
+    ),
+    "jaco2_obst2": dict(
+        arm="jaco2",
+        osc=dict(kp=100, ctrlr_dof=[T, T, T, F, F, F]),
+        null=[
+            (
+                "AvoidObstacles",
+                dict(
+                    obstacles=[[0.1, -0.2, 0.5, 0.08], [-0.15, 0.1, 0.6, 0.1]],
+                    threshold=0.5,
+                    gain=2.0,
+                    maximum=40.0,
+                ),
+            )
+        ],
+    ),
+    "jaco2_alg1_tv": dict(
+        arm="jaco2", osc=dict(kp=60, ko=40, kv=12, ctrlr_dof=[T] * 6, orientation_algorithm=1), tv=True
+    ),
+    # --- threejoint (config 1) and twojoint (the arm the reference's unit tests pin) ----------------
+    "threejoint_cfg1": dict(
+        arm="threejoint",
+        osc=dict(kp=20, use_C=True, ctrlr_dof=[T, T, F, F, F, F]),
+        null=[
+            ("Damping", dict(kv=10)),
+            ("RestingConfig", dict(kp=50, kv=float(np.sqrt(50)), rest_angles=[PI / 4, PI, None])),
+        ],
+    ),
+    "twojoint_xy": dict(arm="twojoint", osc=dict(kp=15, use_C=True, ctrlr_dof=[T, T, F, F, F, F])),
+}
+
+# standalone secondary controllers
+NULL_CASES = {
+    "ur5_damping": dict(arm="ur5", ctrl=("Damping", dict(kv=10))),
+    "ur5_resting": dict(
+        arm="ur5", ctrl=("RestingConfig", dict(kp=30, kv=6, rest_angles=[None, PI / 4, -PI / 2, PI / 4, None, None]))
+    ),
+    "jaco2_avoid": dict(
+        arm="jaco2",
+        ctrl=("AvoidObstacles", dict(obstacles=[[0.1, -0.2, 0.5, 0.08], [-0.15, 0.1, 0.6, 0.1]], threshold=0.5)),
+    ),
+    "ur5_avoid": dict(
+        arm="ur5", ctrl=("AvoidObstacles", dict(obstacles=[[0.2, 0.1, 0.4, 0.05]], threshold=0.6, gain=1.5, maximum=30.0))
+    ),
+    "threejoint_resting": dict(
+        arm="threejoint", ctrl=("RestingConfig", dict(kp=50, kv=float(np.sqrt(50)), rest_angles=[PI / 4, PI, None]))
+    ),
+}
