@@ -1,0 +1,650 @@
+// abrb_math.cuh — per-state arithmetic of the batched arm engine (one joint state per thread).
+//
+// Everything here is a template over the scalar type T (float / double), the joint count N and
+// ORTHO (all constant frames orthonormal -> joint-axis operators reduce to cross products).
+// The functions are __host__ __device__ so the very same code can be instantiated by g++ for the
+// CPU-side unit tests in tests/hostsim (test infrastructure only: the shipped library launches them
+// exclusively from CUDA kernels, see kernels.cu).
+//
+// Formulation.  The reference differentiates symbolic products of 4x4 factors
+// (/root/reference/abr_control/arms/base_config.py:559-563, :504-507, :706-714).  Here the same exact
+// derivatives are obtained from per-joint operators.  For joint k let R_k, t_k be the rotation block and
+// origin of frame "joint k" (before its own rotation) and
+//        Omega_k = R_k E R_k^-1,   E = [[0,-1,0],[1,0,0],[0,0,0]]
+// (for an orthonormal R_k, Omega_k v = z_k x v).  For any point p rigidly attached downstream of joint k:
+//        dp/dq_k          = Omega_k (p - t_k)
+//        d2p/dq_i dq_k    = Omega_min(i,k) dp/dq_max(i,k)
+//        dz_a/dq_i        = Omega_i z_a   (i < a),  0 otherwise
+// which holds for non-orthonormal constant frames too (Jaco2) because Omega_k commutes
+// with the joint's own rotation.  M, g, C then follow the reference's definitions
+// (base_config.py:625-632, :448-455, :706-714) with the diagonal link inertias left un-rotated.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define ABRB_HD __host__ __device__ __forceinline__
+#define ABRB_HD_NOINLINE __host__ __device__ __noinline__
+#define ABRB_UNROLL _Pragma("unroll")
+#else
+#define ABRB_HD inline
+#define ABRB_HD_NOINLINE __attribute__((noinline))
+#define ABRB_UNROLL
+#endif
+
+namespace abrb {
+
+constexpr int kMaxJoints = 7;
+constexpr int kMaxNull = 4;
+constexpr int kMaxObstacles = 16;
+
+ABRB_HD void sincos_t(double x, double *s, double *c) { ::sincos(x, s, c); }
+ABRB_HD void sincos_t(float x, float *s, float *c) { ::sincosf(x, s, c); }
+ABRB_HD double sqrt_t(double x) { return ::sqrt(x); }
+ABRB_HD float sqrt_t(float x) { return ::sqrtf(x); }
+ABRB_HD double abs_t(double x) { return ::fabs(x); }
+ABRB_HD float abs_t(float x) { return ::fabsf(x); }
+ABRB_HD double fmod_t(double x, double y) { return ::fmod(x, y); }
+ABRB_HD float fmod_t(float x, float y) { return ::fmodf(x, y); }
+ABRB_HD double pow_t(double x, double y) { return ::pow(x, y); }
+ABRB_HD float pow_t(float x, float y) { return ::powf(x, y); }
+
+// ------------------------------------------------------------------------------------------------
+// Chain constants in compute precision; passed to the kernels BY VALUE (kernel-parameter constant bank:
+// every lane reads the same constant at the same time, so the constant cache broadcast is the right
+// staging level — no shared-memory copy is needed for a one-state-per-thread mapping).
+// Affine blocks are 3x4 row-major [R|t].
+template <typename T, int N>
+struct ChainK {
+  T G0[12];          // world -> joint0 frame            (L0 . A_0)
+  T L0[12];          // world -> link0 frame
+  T Bf[N][12];       // rotated joint-i frame -> link(i+1) COM frame          (B_i)
+  T BA[N][12];       // rotated joint-i frame -> joint(i+1) frame (B_i . A_{i+1}); BA[N-1] = B_{N-1} . E -> EE
+  T Wp[N + 1][3];    // translational part of diag link inertia l
+  T Wos[N][3];       // Wos[k] = sum_{l>k} rotational diag inertia of link l
+  T gp[N + 1][3];    // Wp[l][c] * gravity[c]
+  T gos[N][3];       // sum_{l>k} Wo[l][c] * gravity[3+c]
+};
+
+// frame ids: link l -> l (0..N), joint j -> N+1+j, EE -> 2N+1
+template <int N>
+ABRB_HD int frame_dep(int frame) {  // number of joints the frame moves with == reference `end_point`
+  return frame <= N ? frame : (frame <= 2 * N ? frame - (N + 1) : N);
+}
+
+template <typename T, int N, bool ORTHO>
+struct Kin {
+  T t[N][3];                   // joint origins
+  T z[N][3];                   // joint axes (third column of R_k)
+  T r0[ORTHO ? 1 : N][3];      // non-orthonormal chains only: columns 0,1 of R_k and rows 0,1 of R_k^-1
+  T r1[ORTHO ? 1 : N][3];
+  T s0[ORTHO ? 1 : N][3];
+  T s1[ORTHO ? 1 : N][3];
+  T pl[N][3];                  // COM of link i+1
+  T F[12];                     // the requested frame
+};
+
+template <typename T>
+ABRB_HD void cross3(const T *a, const T *b, T *o) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+template <typename T>
+ABRB_HD T dot3(const T *a, const T *b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+
+// out = X . C for two affine 3x4 blocks
+template <typename T>
+ABRB_HD void aff_mul(const T *X, const T *C, T *o) {
+  ABRB_UNROLL
+  for (int r = 0; r < 3; ++r) {
+    ABRB_UNROLL
+    for (int c = 0; c < 3; ++c)
+      o[r * 4 + c] = X[r * 4 + 0] * C[c] + X[r * 4 + 1] * C[4 + c] + X[r * 4 + 2] * C[8 + c];
+    o[r * 4 + 3] = X[r * 4 + 0] * C[3] + X[r * 4 + 1] * C[7] + X[r * 4 + 2] * C[11] + X[r * 4 + 3];
+  }
+}
+
+// Omega_k v
+template <typename T, int N, bool ORTHO>
+ABRB_HD void omega_apply(const Kin<T, N, ORTHO> &K, int k, const T *v, T *o) {
+  if (ORTHO) {
+    cross3(K.z[k], v, o);
+  } else {
+    const T a = dot3(K.s0[k], v), b = dot3(K.s1[k], v);
+    ABRB_UNROLL
+    for (int c = 0; c < 3; ++c) o[c] = K.r1[k][c] * a - K.r0[k][c] * b;
+  }
+}
+
+// Running sum  W_j = sum_{i<j} dq_i Omega_i  (angular-velocity operator seen by joint j)
+template <typename T, bool ORTHO>
+struct Spin {
+  T w[ORTHO ? 3 : 9];
+  ABRB_HD void clear() {
+    ABRB_UNROLL
+    for (int i = 0; i < (ORTHO ? 3 : 9); ++i) w[i] = T(0);
+  }
+  template <int N>
+  ABRB_HD void add(const Kin<T, N, ORTHO> &K, int k, T dqk) {
+    if (ORTHO) {
+      ABRB_UNROLL
+      for (int c = 0; c < 3; ++c) w[c] += dqk * K.z[k][c];
+    } else {
+      ABRB_UNROLL
+      for (int r = 0; r < 3; ++r)
+        ABRB_UNROLL
+      for (int c = 0; c < 3; ++c)
+        w[r * 3 + c] += dqk * (K.r1[k][r] * K.s0[k][c] - K.r0[k][r] * K.s1[k][c]);
+    }
+  }
+  ABRB_HD void apply(const T *v, T *o) const {
+    if (ORTHO) {
+      cross3(w, v, o);
+    } else {
+      ABRB_UNROLL
+      for (int r = 0; r < 3; ++r) o[r] = w[r * 3] * v[0] + w[r * 3 + 1] * v[1] + w[r * 3 + 2] * v[2];
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Forward walk along the chain: fills joint origins/axes, link COMs and the
+// full transform of `frame`.
+template <typename T, int N, bool ORTHO>
+ABRB_HD void walk(const ChainK<T, N> &P, const T *q, int frame, Kin<T, N, ORTHO> &K,
+                  T (*link_frames)[12] = nullptr) {  // optional: all link(i+1) frames (rare paths only)
+  T X[12];
+  ABRB_UNROLL
+  for (int i = 0; i < 12; ++i) X[i] = P.G0[i];
+  if (frame == 0) {
+    ABRB_UNROLL
+    for (int i = 0; i < 12; ++i) K.F[i] = P.L0[i];
+  }
+  ABRB_UNROLL
+  for (int i = 0; i < N; ++i) {
+    ABRB_UNROLL
+    for (int r = 0; r < 3; ++r) {
+      K.t[i][r] = X[r * 4 + 3];
+      K.z[i][r] = X[r * 4 + 2];
+    }
+    if (!ORTHO) {
+      T c0[3], c1[3], c2[3], c12[3], c20[3];
+      ABRB_UNROLL
+      for (int r = 0; r < 3; ++r) {
+        c0[r] = X[r * 4 + 0];
+        c1[r] = X[r * 4 + 1];
+        c2[r] = X[r * 4 + 2];
+      }
+      cross3(c1, c2, c12);
+      cross3(c2, c0, c20);
+      const T inv = T(1) / dot3(c0, c12);
+      ABRB_UNROLL
+      for (int r = 0; r < 3; ++r) {
+        K.r0[ORTHO ? 0 : i][r] = c0[r];
+        K.r1[ORTHO ? 0 : i][r] = c1[r];
+        K.s0[ORTHO ? 0 : i][r] = c12[r] * inv;
+        K.s1[ORTHO ? 0 : i][r] = c20[r] * inv;
+      }
+    }
+    if (frame == N + 1 + i) {
+      ABRB_UNROLL
+      for (int j = 0; j < 12; ++j) K.F[j] = X[j];
+    }
+    T s, c;
+    sincos_t(q[i], &s, &c);
+    ABRB_UNROLL
+    for (int r = 0; r < 3; ++r) {
+      const T a = X[r * 4 + 0], b = X[r * 4 + 1];
+      X[r * 4 + 0] = c * a + s * b;
+      X[r * 4 + 1] = c * b - s * a;
+    }
+    ABRB_UNROLL
+    for (int r = 0; r < 3; ++r)
+      K.pl[i][r] = X[r * 4 + 0] * P.Bf[i][3] + X[r * 4 + 1] * P.Bf[i][7] + X[r * 4 + 2] * P.Bf[i][11] + X[r * 4 + 3];
+    if (frame == i + 1) aff_mul(X, P.Bf[i], K.F);
+    if (link_frames != nullptr) aff_mul(X, P.Bf[i], link_frames[i]);
+    T Y[12];
+    aff_mul(X, P.BA[i], Y);
+    ABRB_UNROLL
+    for (int j = 0; j < 12; ++j) X[j] = Y[j];
+  }
+  if (frame == 2 * N + 1) {
+    ABRB_UNROLL
+    for (int j = 0; j < 12; ++j) K.F[j] = X[j];
+  }
+}
+
+// point `x` of the requested frame in world coordinates  (reference Tx, base_config.py:371-392)
+template <typename T>
+ABRB_HD void frame_point(const T *F, const T *x, T *p) {
+  ABRB_UNROLL
+  for (int r = 0; r < 3; ++r) p[r] = F[r * 4 + 0] * x[0] + F[r * 4 + 1] * x[1] + F[r * 4 + 2] * x[2] + F[r * 4 + 3];
+}
+
+// J[6][N] of world point p attached to a frame that moves with the first `dep` joints
+// (reference J, base_config.py:522-592: rows 0-2 dTx/dq_k, rows 3-5 J_orientation[k] for k < end_point)
+template <typename T, int N, bool ORTHO>
+ABRB_HD void jacobian(const Kin<T, N, ORTHO> &K, const T *p, int dep, T (*J)[N]) {
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) {
+    T d[3], v[3];
+    ABRB_UNROLL
+    for (int c = 0; c < 3; ++c) d[c] = p[c] - K.t[k][c];
+    omega_apply(K, k, d, v);
+    const bool on = k < dep;
+    ABRB_UNROLL
+    for (int c = 0; c < 3; ++c) {
+      J[c][k] = on ? v[c] : T(0);
+      J[3 + c][k] = on ? K.z[k][c] : T(0);
+    }
+  }
+}
+
+// dJ/dt = sum_i dJ/dq_i dq_i (reference dJ, base_config.py:470-520) given J's position rows
+template <typename T, int N, bool ORTHO>
+ABRB_HD void jacobian_dot(const Kin<T, N, ORTHO> &K, const T (*J)[N], const T *dq, int dep, T (*dJ)[N]) {
+  // suffix sums s_k = sum_{k<=i<dep} dq_i v_i
+  T suf[N][3];
+  T run[3] = {T(0), T(0), T(0)};
+  ABRB_UNROLL
+  for (int k = N - 1; k >= 0; --k) {
+    if (k < dep) {
+      ABRB_UNROLL
+      for (int c = 0; c < 3; ++c) run[c] += dq[k] * J[c][k];
+    }
+    ABRB_UNROLL
+    for (int c = 0; c < 3; ++c) suf[k][c] = run[c];
+  }
+  Spin<T, ORTHO> W;
+  W.clear();
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) {
+    T v[3] = {J[0][k], J[1][k], J[2][k]};
+    T a[3], b[3], zd[3];
+    W.apply(v, a);
+    omega_apply(K, k, suf[k], b);
+    W.apply(K.z[k], zd);
+    const bool on = k < dep;
+    ABRB_UNROLL
+    for (int c = 0; c < 3; ++c) {
+      dJ[c][k] = on ? a[c] + b[c] : T(0);
+      dJ[3 + c][k] = on ? zd[c] : T(0);
+    }
+    W.template add<N>(K, k, dq[k]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Joint-space dynamics.  M (upper triangle a<=b filled, mirrored by the caller), g, and optionally
+// the Coriolis matrix C (CMAT) or only the product C.dq (CDQ).
+//   M = sum_l J_l^T W_l J_l            base_config.py:625-632
+//   g = sum_l J_l^T W_l gravity        base_config.py:448-455
+//   C[k][j] = sum_i 1/2 (d_i M_kj + d_j M_ki - d_k M_ij) dq_i     base_config.py:706-714
+// Translational part of C:  sum_l (W_l v_lk) . (d/dt v_lj)   — the symmetric second-derivative terms of
+// the Christoffel sum cancel exactly; rotational part: explicit Christoffel sum.
+template <typename T, int N, bool ORTHO, bool CMAT, bool CDQ>
+ABRB_HD void dynamics(const ChainK<T, N> &P, const Kin<T, N, ORTHO> &K, const T *dq, T (*M)[N], T *g,
+                      T (*C)[N], T *cdq) {
+  ABRB_UNROLL
+  for (int a = 0; a < N; ++a) {
+    g[a] = T(0);
+    if (CDQ) cdq[a] = T(0);
+    ABRB_UNROLL
+    for (int b = 0; b < N; ++b) {
+      M[a][b] = T(0);
+      if (CMAT) C[a][b] = T(0);
+    }
+  }
+  // ---- translational part, link by link (link l = 1..N has COM K.pl[l-1] and moves with joints < l)
+  ABRB_UNROLL
+  for (int l = 1; l <= N; ++l) {
+    T v[N][3], wv[N][3];
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) {
+      if (k < l) {
+        T d[3];
+        ABRB_UNROLL
+        for (int c = 0; c < 3; ++c) d[c] = K.pl[l - 1][c] - K.t[k][c];
+        omega_apply(K, k, d, v[k]);
+        ABRB_UNROLL
+        for (int c = 0; c < 3; ++c) wv[k][c] = P.Wp[l][c] * v[k][c];
+        g[k] += dot3(v[k], P.gp[l]);
+      }
+    }
+    ABRB_UNROLL
+    for (int a = 0; a < N; ++a)
+      ABRB_UNROLL
+    for (int b = a; b < N; ++b)
+      if (b < l) M[a][b] += dot3(wv[a], v[b]);
+    if (CMAT || CDQ) {
+      T suf[N][3];
+      T run[3] = {T(0), T(0), T(0)};
+      ABRB_UNROLL
+      for (int k = N - 1; k >= 0; --k) {
+        if (k < l) {
+          ABRB_UNROLL
+          for (int c = 0; c < 3; ++c) {
+            run[c] += dq[k] * v[k][c];
+            suf[k][c] = run[c];
+          }
+        }
+      }
+      Spin<T, ORTHO> W;
+      W.clear();
+      T acc[3] = {T(0), T(0), T(0)};
+      ABRB_UNROLL
+      for (int j = 0; j < N; ++j) {
+        if (j < l) {
+          T a1[3], a2[3], aj[3];
+          W.apply(v[j], a1);
+          omega_apply(K, j, suf[j], a2);
+          ABRB_UNROLL
+          for (int c = 0; c < 3; ++c) aj[c] = a1[c] + a2[c];
+          if (CMAT) {
+            ABRB_UNROLL
+            for (int k = 0; k < N; ++k)
+              if (k < l) C[k][j] += dot3(wv[k], aj);
+          }
+          if (CDQ) {
+            ABRB_UNROLL
+            for (int c = 0; c < 3; ++c) acc[c] += dq[j] * aj[c];
+          }
+          W.template add<N>(K, j, dq[j]);
+        }
+      }
+      if (CDQ) {
+        ABRB_UNROLL
+        for (int k = 0; k < N; ++k)
+          if (k < l) cdq[k] += dot3(wv[k], acc);
+      }
+    }
+  }
+  // ---- rotational part: M_ab += sum_c z_a[c] Wos[max(a,b)][c] z_b[c]
+  ABRB_UNROLL
+  for (int a = 0; a < N; ++a) {
+    g[a] += dot3(K.z[a], P.gos[a]);
+    ABRB_UNROLL
+    for (int b = a; b < N; ++b)
+      M[a][b] += K.z[a][0] * P.Wos[b][0] * K.z[b][0] + K.z[a][1] * P.Wos[b][1] * K.z[b][1] +
+                 K.z[a][2] * P.Wos[b][2] * K.z[b][2];
+  }
+  if (CMAT) {
+    // dz[i][a] = Omega_i z_a (i<a);  dMo(i;a,b) = sum_c Wos[max(a,b)][c] (dz[i][a][c] z_b[c] + z_a[c] dz[i][b][c])
+    T dz[N][N][3];
+    ABRB_UNROLL
+    for (int i = 0; i < N; ++i)
+      ABRB_UNROLL
+    for (int a = 0; a < N; ++a) {
+      if (i < a) {
+        omega_apply(K, i, K.z[a], dz[i][a]);
+      } else {
+        dz[i][a][0] = dz[i][a][1] = dz[i][a][2] = T(0);
+      }
+    }
+    auto dMo = [&](int i, int a, int b) -> T {
+      const int m = a > b ? a : b;
+      T s = T(0);
+      ABRB_UNROLL
+      for (int c = 0; c < 3; ++c) s += P.Wos[m][c] * (dz[i][a][c] * K.z[b][c] + K.z[a][c] * dz[i][b][c]);
+      return s;
+    };
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k)
+      ABRB_UNROLL
+    for (int j = 0; j < N; ++j) {
+      T s = T(0);
+      ABRB_UNROLL
+      for (int i = 0; i < N; ++i) s += (dMo(i, k, j) + dMo(j, k, i) - dMo(k, i, j)) * dq[i];
+      C[k][j] += T(0.5) * s;
+    }
+  }
+  if (CDQ) {
+    // (C dq)_k = (dM/dt dq)_k - 1/2 d/dq_k (dq^T M dq), rotational part
+    T zd[N][3], h[N][3];
+    Spin<T, ORTHO> W;
+    W.clear();
+    ABRB_UNROLL
+    for (int a = 0; a < N; ++a) {
+      W.apply(K.z[a], zd[a]);
+      W.template add<N>(K, a, dq[a]);
+    }
+    ABRB_UNROLL
+    for (int i = 0; i < N; ++i) {
+      h[i][0] = h[i][1] = h[i][2] = T(0);
+      ABRB_UNROLL
+      for (int j = 0; j < N; ++j) {
+        const int m = i > j ? i : j;
+        ABRB_UNROLL
+        for (int c = 0; c < 3; ++c) h[i][c] += dq[j] * P.Wos[m][c] * K.z[j][c];
+      }
+    }
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) {
+      T s = T(0);
+      ABRB_UNROLL
+      for (int j = 0; j < N; ++j) {
+        const int m = k > j ? k : j;
+        T e = T(0);
+        ABRB_UNROLL
+        for (int c = 0; c < 3; ++c) e += P.Wos[m][c] * (zd[k][c] * K.z[j][c] + K.z[k][c] * zd[j][c]);
+        s += dq[j] * e;
+      }
+      ABRB_UNROLL
+      for (int i = 0; i < N; ++i) {
+        if (i > k) {
+          T oz[3];
+          omega_apply(K, k, K.z[i], oz);
+          s -= dq[i] * dot3(oz, h[i]);
+        }
+      }
+      cdq[k] += s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Unit quaternion (w,x,y,z), w >= 0, of a (nearly) rotation matrix R[9] row-major.
+// Reference: utils/transformations.py:1192-1271 (isprecise=False): eigenvector of the largest eigenvalue
+// of the symmetric 4x4 matrix K/3.  For a rotation, K/3 + I/3 = (4/3) q q^T, so the dominant eigenvector is
+// reached by power iteration on K/3 + I/3 from its column with the largest diagonal; the other
+// eigenvalues are O(|R^T R - I|), i.e. each iteration gains >= 3 digits for the arms' measured frames.
+template <typename T>
+ABRB_HD void quat_from_R(const T *m, T *qo) {
+  const T third = T(1) / T(3);
+  T Kp[4][4];
+  Kp[0][0] = (m[0] - m[4] - m[8]) * third + third;
+  Kp[1][1] = (m[4] - m[0] - m[8]) * third + third;
+  Kp[2][2] = (m[8] - m[0] - m[4]) * third + third;
+  Kp[3][3] = (m[0] + m[4] + m[8]) * third + third;
+  Kp[0][1] = Kp[1][0] = (m[1] + m[3]) * third;
+  Kp[0][2] = Kp[2][0] = (m[2] + m[6]) * third;
+  Kp[1][2] = Kp[2][1] = (m[5] + m[7]) * third;
+  Kp[0][3] = Kp[3][0] = (m[7] - m[5]) * third;
+  Kp[1][3] = Kp[3][1] = (m[2] - m[6]) * third;
+  Kp[2][3] = Kp[3][2] = (m[3] - m[1]) * third;
+  // start from the column with the largest diagonal entry (branch-free select)
+  T v[4] = {Kp[0][0], Kp[1][0], Kp[2][0], Kp[3][0]};
+  T best = Kp[0][0];
+  ABRB_UNROLL
+  for (int j = 1; j < 4; ++j) {
+    const bool take = Kp[j][j] > best;
+    best = take ? Kp[j][j] : best;
+    ABRB_UNROLL
+    for (int r = 0; r < 4; ++r) v[r] = take ? Kp[r][j] : v[r];
+  }
+  ABRB_UNROLL
+  for (int it = 0; it < 5; ++it) {
+    T w[4];
+    ABRB_UNROLL
+    for (int r = 0; r < 4; ++r) w[r] = Kp[r][0] * v[0] + Kp[r][1] * v[1] + Kp[r][2] * v[2] + Kp[r][3] * v[3];
+    const T inv = T(1) / sqrt_t(w[0] * w[0] + w[1] * w[1] + w[2] * w[2] + w[3] * w[3]);
+    ABRB_UNROLL
+    for (int r = 0; r < 4; ++r) v[r] = w[r] * inv;
+  }
+  const T sgn = v[3] < T(0) ? T(-1) : T(1);  // reference: flip so that q[0] (w) >= 0
+  qo[0] = sgn * v[3];
+  qo[1] = sgn * v[0];
+  qo[2] = sgn * v[1];
+  qo[3] = sgn * v[2];
+}
+
+// quaternion_from_euler(a, b, g, axes="rxyz")  (utils/transformations.py:1096-1147, _AXES2TUPLE['rxyz']=(2,1,0,1))
+template <typename T>
+ABRB_HD void quat_from_euler_rxyz(T al, T be, T ga, T *qo) {
+  T si, ci, sj, cj, sk, ck;
+  sincos_t(ga * T(0.5), &si, &ci);   // frame=1 swaps first/last angle
+  sincos_t(-be * T(0.5), &sj, &cj);  // parity=1 negates the middle angle
+  sincos_t(al * T(0.5), &sk, &ck);
+  const T cc = ci * ck, cs = ci * sk, sc = si * ck, ss = si * sk;
+  qo[0] = cj * cc + sj * ss;
+  qo[3] = cj * sc - sj * cs;     // i = 3
+  qo[2] = -(cj * ss + sj * cc);  // j = 2, parity flips its sign
+  qo[1] = cj * cs - sj * sc;     // k = 1
+}
+
+// euler_matrix(a, b, g, axes="rxyz")[:3,:3]  (utils/transformations.py:973-1035), row-major R[9]
+template <typename T>
+ABRB_HD void R_from_euler_rxyz(T al, T be, T ga, T *R) {
+  T si, ci, sj, cj, sk, ck;
+  sincos_t(-ga, &si, &ci);
+  sincos_t(-be, &sj, &cj);
+  sincos_t(-al, &sk, &ck);
+  const T cc = ci * ck, cs = ci * sk, sc = si * ck, ss = si * sk;
+  // (i, j, k) = (2, 1, 0)
+  R[2 * 3 + 2] = cj * ck;
+  R[2 * 3 + 1] = sj * sc - cs;
+  R[2 * 3 + 0] = sj * cc + ss;
+  R[1 * 3 + 2] = cj * sk;
+  R[1 * 3 + 1] = sj * ss + cc;
+  R[1 * 3 + 0] = sj * cs - sc;
+  R[0 * 3 + 2] = -sj;
+  R[0 * 3 + 1] = cj * si;
+  R[0 * 3 + 0] = cj * ci;
+}
+
+template <typename T>
+ABRB_HD void quat_mul(const T *q1, const T *q0, T *o) {  // utils/transformations.py:1274-1290
+  o[0] = -q1[1] * q0[1] - q1[2] * q0[2] - q1[3] * q0[3] + q1[0] * q0[0];
+  o[1] = q1[1] * q0[0] + q1[2] * q0[3] - q1[3] * q0[2] + q1[0] * q0[1];
+  o[2] = -q1[1] * q0[3] + q1[2] * q0[0] + q1[3] * q0[1] + q1[0] * q0[2];
+  o[3] = q1[1] * q0[2] - q1[2] * q0[1] + q1[3] * q0[0] + q1[0] * q0[3];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small dense linear algebra on register-resident matrices (static indices only).
+// In-place lower Cholesky of the symmetric S (reads the upper OR lower triangle consistently: we use
+// S[i][j], j<=i).  Returns false if a pivot is not positive.
+template <typename T, int S_>
+ABRB_HD bool chol(T (*A)[S_]) {
+  bool ok = true;
+  ABRB_UNROLL
+  for (int j = 0; j < S_; ++j) {
+    T d = A[j][j];
+    ABRB_UNROLL
+    for (int k = 0; k < S_; ++k)
+      if (k < j) d -= A[j][k] * A[j][k];
+    ok = ok && (d > T(0));
+    const T ljj = sqrt_t(d > T(0) ? d : T(1));
+    A[j][j] = ljj;
+    const T inv = T(1) / ljj;
+    ABRB_UNROLL
+    for (int i = 0; i < S_; ++i) {
+      if (i > j) {
+        T s = A[i][j];
+        ABRB_UNROLL
+        for (int k = 0; k < S_; ++k)
+          if (k < j) s -= A[i][k] * A[j][k];
+        A[i][j] = s * inv;
+      }
+    }
+  }
+  return ok;
+}
+template <typename T, int S_>
+ABRB_HD void fwd_solve(const T (*L)[S_], T *b) {  // L y = b
+  ABRB_UNROLL
+  for (int i = 0; i < S_; ++i) {
+    T s = b[i];
+    ABRB_UNROLL
+    for (int k = 0; k < S_; ++k)
+      if (k < i) s -= L[i][k] * b[k];
+    b[i] = s / L[i][i];
+  }
+}
+template <typename T, int S_>
+ABRB_HD void bwd_solve(const T (*L)[S_], T *b) {  // L^T x = b
+  ABRB_UNROLL
+  for (int i = S_ - 1; i >= 0; --i) {
+    T s = b[i];
+    ABRB_UNROLL
+    for (int k = 0; k < S_; ++k)
+      if (k > i) s -= L[k][i] * b[k];
+    b[i] = s / L[i][i];
+  }
+}
+
+// x = pinv(S, rcond) y for a symmetric positive semi-definite S (numpy.linalg.pinv semantics: singular
+// values <= rcond * largest are dropped; for symmetric PSD they are the eigenvalues).  Cyclic Jacobi.
+// `active` marks the rows that belong to the problem (others are identity rows and are ignored when
+// looking for the largest eigenvalue).  Deliberately NOT inlined: this is the rare, divergent path and
+// works on a private copy so the hot path keeps its registers.
+template <typename T, int S_>
+ABRB_HD_NOINLINE void pinv_apply_sym(const T *Sin, unsigned active, T rcond, const T *y, T *x) {
+  T A[S_][S_], V[S_][S_];
+  for (int i = 0; i < S_; ++i)
+    for (int j = 0; j < S_; ++j) {
+      A[i][j] = Sin[i * S_ + j];
+      V[i][j] = i == j ? T(1) : T(0);
+    }
+  const T eps = sizeof(T) == 8 ? T(1e-30) : T(1e-18);
+  for (int sweep = 0; sweep < 24; ++sweep) {
+    T off = T(0), diag = T(0);
+    for (int i = 0; i < S_; ++i) {
+      diag += A[i][i] * A[i][i];
+      for (int j = i + 1; j < S_; ++j) off += A[i][j] * A[i][j];
+    }
+    if (off <= eps * diag) break;
+    for (int p = 0; p < S_ - 1; ++p)
+      for (int q = p + 1; q < S_; ++q) {
+        const T apq = A[p][q];
+        if (apq == T(0)) continue;
+        const T theta = (A[q][q] - A[p][p]) / (T(2) * apq);
+        const T t = (theta >= T(0) ? T(1) : T(-1)) / (abs_t(theta) + sqrt_t(theta * theta + T(1)));
+        const T c = T(1) / sqrt_t(t * t + T(1)), s = t * c;
+        for (int k = 0; k < S_; ++k) {
+          const T akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - s * akq;
+          A[k][q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < S_; ++k) {
+          const T apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - s * aqk;
+          A[q][k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < S_; ++k) {
+          const T vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq;
+          V[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  T lmax = T(0);
+  for (int i = 0; i < S_; ++i)
+    if ((active >> i) & 1u) lmax = abs_t(A[i][i]) > lmax ? abs_t(A[i][i]) : lmax;
+  for (int i = 0; i < S_; ++i) x[i] = T(0);
+  for (int e = 0; e < S_; ++e) {
+    // an eigenpair belongs to the active block iff its eigenvector lives there; identity rows have
+    // eigenvalue exactly 1 and never couple to y (y is zero on them)
+    const T lam = A[e][e];
+    if (!(abs_t(lam) > rcond * lmax)) continue;
+    T proj = T(0);
+    for (int k = 0; k < S_; ++k) proj += V[k][e] * y[k];
+    proj /= lam;
+    for (int k = 0; k < S_; ++k) x[k] += V[k][e] * proj;
+  }
+}
+
+}  // namespace abrb

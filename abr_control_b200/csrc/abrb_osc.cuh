@@ -1,0 +1,451 @@
+// abrb_osc.cuh — one state of OSC.generate (and the secondary controllers), fully fused:
+// chain walk -> J, M, g, (C dq) -> Cholesky(M) -> task-space inertia -> task PD -> joint torques ->
+// null-space filtered secondary torques.  Reference: /root/reference/abr_control/controllers/osc.py:217-320,
+// damping.py:21-32, resting_config.py:25-42 + joint.py:104-131, avoid_obstacles.py:38-120.
+#pragma once
+#include "abrb_math.cuh"
+
+namespace abrb {
+
+enum { kNullDamping = 1, kNullResting = 2, kNullAvoid = 3 };
+
+template <typename T, int N>
+struct NullK {
+  int kind;
+  int n_obs;
+  unsigned rest_mask;
+  int pad_;
+  T kp, kv;
+  T rest[N];
+  T threshold, gain, maximum;
+  T obs[kMaxObstacles][4];
+};
+
+template <typename T, int N>
+struct OscK {
+  T kp, ko, kv;
+  T lim_xyz, lim_abg;  // vmax[0]/kp*kv, vmax[1]/ko*kv   (osc.py:109-115)
+  T thr;               // |det| threshold of _Mx (osc.py:120,138)
+  T xoff[3];
+  unsigned dof_mask;   // bit r = ctrlr_dof[r]
+  int use_vmax, use_g, use_C, alg, n_null, frame;
+  NullK<T, N> nul[kMaxNull];
+};
+
+// AvoidObstacles.generate — the rare, data-dependent secondary controller; not inlined and self-contained
+// (re-walks the chain) so that the main path's register allocation is unaffected.
+// Lm: Cholesky factor of M (row-major N x N, lower).
+template <typename T, int N, bool ORTHO>
+ABRB_HD_NOINLINE void avoid_generate(const ChainK<T, N> &P, const NullK<T, N> &A, const T *q, const T *Lm,
+                                     T *u_out) {
+  Kin<T, N, ORTHO> K;
+  T LFs[N][12];
+  walk<T, N, ORTHO>(P, q, 2 * N + 1, K, LFs);  // K.F = EE frame, LFs[i] = link(i+1) frame
+  T up[N];
+  for (int k = 0; k < N; ++k) up[k] = T(0);
+  const T thr = A.threshold;
+  for (int seg = 0; seg < N; ++seg) {
+    const T *LF = LFs[seg];
+    T p1[3], p2[3];
+    for (int r = 0; r < 3; ++r) {
+      p1[r] = K.t[seg][r];
+      p2[r] = seg == N - 1 ? K.F[r * 4 + 3] : K.t[seg + 1 < N ? seg + 1 : N - 1][r];
+    }
+    for (int ob = 0; ob < A.n_obs; ++ob) {
+      const T *O = A.obs[ob];
+      T line[3], obl[3];
+      for (int r = 0; r < 3; ++r) {
+        line[r] = p2[r] - p1[r];
+        obl[r] = O[r] - p1[r];
+      }
+      const T proj = dot3(obl, line) / dot3(line, line);
+      T cl[3];
+      for (int r = 0; r < 3; ++r) cl[r] = proj < T(0) ? p1[r] : (proj > T(1) ? p2[r] : p1[r] + proj * line[r]);
+      T d[3] = {O[0] - cl[0], O[1] - cl[1], O[2] - cl[2]};
+      const T dist = sqrt_t(dot3(d, d));
+      T rho = dist - O[3];
+      const T floor_ = thr / T(50);
+      rho = rho > floor_ ? rho : floor_;
+      if (!(rho < thr)) continue;
+      const T mag = T(0.02) * (T(1) / rho - T(1) / thr) * T(1) / (rho * sqrt_t(rho));
+      T F[3];
+      for (int r = 0; r < 3; ++r) F[r] = mag * (d[r] / rho);
+      // m = T_inv(link) [closest;1] with the reference's TRANSPOSE inverse (base_config.py:820-824)
+      T dl[3] = {cl[0] - LF[3], cl[1] - LF[7], cl[2] - LF[11]};
+      T m[3], pw[3];
+      for (int cc = 0; cc < 3; ++cc) m[cc] = LF[0 * 4 + cc] * dl[0] + LF[1 * 4 + cc] * dl[1] + LF[2 * 4 + cc] * dl[2];
+      frame_point(LF, m, pw);
+      // Jp (3 x N) of that point, W = L^-1 Jp^T (N x 3)
+      T Jp[3][N], Wc[3][N];
+      for (int k = 0; k < N; ++k) {
+        T dd[3] = {pw[0] - K.t[k][0], pw[1] - K.t[k][1], pw[2] - K.t[k][2]};
+        T v[3];
+        omega_apply(K, k, dd, v);
+        for (int r = 0; r < 3; ++r) Jp[r][k] = k < seg + 1 ? v[r] : T(0);
+      }
+      for (int r = 0; r < 3; ++r) {
+        for (int i = 0; i < N; ++i) {
+          T sacc = Jp[r][i];
+          for (int k = 0; k < i; ++k) sacc -= Lm[i * N + k] * Wc[r][k];
+          Wc[r][i] = sacc / Lm[i * N + i];
+        }
+      }
+      T S3[9];
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+          T sacc = T(0);
+          for (int k = 0; k < N; ++k) sacc += Wc[a][k] * Wc[b][k];
+          S3[a * 3 + b] = sacc;
+        }
+      T x3[3];
+      pinv_apply_sym<T, 3>(S3, 7u, T(0.01), F, x3);
+      for (int k = 0; k < N; ++k) up[k] -= Jp[0][k] * x3[0] + Jp[1][k] * x3[1] + Jp[2][k] * x3[2];
+    }
+  }
+  for (int k = 0; k < N; ++k) {
+    T v = up[k] * A.gain;
+    v = v > A.maximum ? A.maximum : v;
+    v = v < -A.maximum ? -A.maximum : v;
+    u_out[k] = v;
+  }
+}
+
+// python-style (x mod 2pi) in [0, 2pi)
+template <typename T>
+ABRB_HD T wrap_pm_pi(T d) {
+  const T two_pi = T(6.283185307179586476925286766559);
+  const T pi = T(3.14159265358979323846264338327950288);
+  T r = fmod_t(d + pi, two_pi);
+  r = r < T(0) ? r + two_pi : r;
+  return r - pi;
+}
+
+// One OSC evaluation.  KD = 3: only (a subset of) x,y,z controlled; KD = 6: any mask.
+// PLANT: also return ddq = M^-1 (u + g - C dq) for the rollout kernel.
+template <typename T, int N, bool ORTHO, int KD, bool PLANT>
+ABRB_HD void osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, const T *dq, const T *target,
+                       const T *tv, T *u, T *train, T *ddq) {
+  Kin<T, N, ORTHO> K;
+  walk<T, N, ORTHO>(P, q, O.frame, K);
+  const int dep = frame_dep<N>(O.frame);
+  T pF[3];
+  frame_point(K.F, O.xoff, pF);
+
+  // ---- joint-space dynamics
+  T M[N][N], g[N], cdq[N];
+  if (PLANT || O.use_C)
+    dynamics<T, N, ORTHO, false, true>(P, K, dq, M, g, nullptr, cdq);
+  else
+    dynamics<T, N, ORTHO, false, false>(P, K, dq, M, g, nullptr, nullptr);
+  ABRB_UNROLL
+  for (int a = 0; a < N; ++a)
+    ABRB_UNROLL
+  for (int b = 0; b < N; ++b)
+    if (b < a) M[a][b] = M[b][a];
+
+  // secondary controllers that are M.(something): accumulate the something
+  T wn[N];
+  bool any_null = false, any_avoid = false;
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) wn[k] = T(0);
+  for (int i = 0; i < O.n_null; ++i) {
+    const NullK<T, N> &Z = O.nul[i];
+    any_null = true;
+    if (Z.kind == kNullDamping) {
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) wn[k] -= Z.kv * dq[k];
+    } else if (Z.kind == kNullResting) {
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) {
+        const T qt = ((Z.rest_mask >> k) & 1u) ? wrap_pm_pi(Z.rest[k] - q[k]) : T(0);
+        wn[k] += Z.kp * qt - Z.kv * dq[k];
+      }
+    } else {
+      any_avoid = true;
+    }
+  }
+  T Mdq[N], un[N];
+  ABRB_UNROLL
+  for (int a = 0; a < N; ++a) {
+    T s1 = T(0), s2 = T(0);
+    ABRB_UNROLL
+    for (int b = 0; b < N; ++b) {
+      s1 += M[a][b] * dq[b];
+      s2 += M[a][b] * wn[b];
+    }
+    Mdq[a] = s1;
+    un[a] = s2;
+  }
+
+  // ---- Jacobian rows of the controlled DOF (uncontrolled rows are zeroed; osc.py:242-244)
+  T A[KD][N];  // first J[KD][N], then (L^-1 J^T)^T
+  T xdot[KD];
+  {
+    T J[6][N];
+    jacobian<T, N, ORTHO>(K, pF, dep, J);
+    ABRB_UNROLL
+    for (int r = 0; r < KD; ++r) {
+      const bool on = (O.dof_mask >> r) & 1u;
+      T s = T(0);
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) {
+        A[r][k] = on ? J[r][k] : T(0);
+        s += A[r][k] * dq[k];
+      }
+      xdot[r] = s;
+    }
+  }
+
+  // ---- task-space error (osc.py:250-272)
+  T err[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  if (O.dof_mask & 7u) {
+    ABRB_UNROLL
+    for (int c = 0; c < 3; ++c) err[c] = pF[c] - target[c];
+  }
+  if (KD == 6 && (O.dof_mask & 56u)) {
+    T R[9];
+    ABRB_UNROLL
+    for (int r = 0; r < 3; ++r)
+      ABRB_UNROLL
+    for (int c = 0; c < 3; ++c) R[r * 3 + c] = K.F[r * 4 + c];
+    if (O.alg == 0) {
+      T qd[4], qe[4], qr[4];
+      quat_from_euler_rxyz(target[3], target[4], target[5], qd);
+      const T nd = T(1) / sqrt_t(qd[0] * qd[0] + qd[1] * qd[1] + qd[2] * qd[2] + qd[3] * qd[3]);
+      ABRB_UNROLL
+      for (int i = 0; i < 4; ++i) qd[i] *= nd;
+      quat_from_R(R, qe);
+      qe[1] = -qe[1];
+      qe[2] = -qe[2];
+      qe[3] = -qe[3];
+      quat_mul(qd, qe, qr);
+      const T sg = qr[0] > T(0) ? T(1) : (qr[0] < T(0) ? T(-1) : T(0));  // numpy.sign
+      ABRB_UNROLL
+      for (int c = 0; c < 3; ++c) err[3 + c] = -qr[1 + c] * sg;
+    } else {
+      T Rd[9], Red[9], qed[4];
+      R_from_euler_rxyz(target[3], target[4], target[5], Rd);
+      ABRB_UNROLL
+      for (int r = 0; r < 3; ++r)
+        ABRB_UNROLL
+      for (int c = 0; c < 3; ++c) Red[r * 3 + c] = R[0 * 3 + r] * Rd[0 * 3 + c] + R[1 * 3 + r] * Rd[1 * 3 + c] + R[2 * 3 + r] * Rd[2 * 3 + c];
+      quat_from_R(Red, qed);
+      ABRB_UNROLL
+      for (int r = 0; r < 3; ++r) err[3 + r] = -(R[r * 3 + 0] * qed[1] + R[r * 3 + 1] * qed[2] + R[r * 3 + 2] * qed[3]);
+    }
+  }
+  if (O.use_vmax) {  // osc.py:198-215
+    const T nx = sqrt_t(err[0] * err[0] + err[1] * err[1] + err[2] * err[2]);
+    const T na = sqrt_t(err[3] * err[3] + err[4] * err[4] + err[5] * err[5]);
+    const T sx = nx > O.lim_xyz ? O.lim_xyz / nx : T(1);
+    const T sa = na > O.lim_abg ? O.lim_abg / na : T(1);
+    ABRB_UNROLL
+    for (int c = 0; c < 3; ++c) {
+      err[c] = O.kv * sx * (O.kp / O.kv) * err[c];
+      err[3 + c] = O.kv * sa * (O.ko / O.kv) * err[3 + c];
+    }
+  } else {
+    ABRB_UNROLL
+    for (int c = 0; c < 3; ++c) {
+      err[c] *= O.kp;
+      err[3 + c] *= O.ko;
+    }
+  }
+  // velocity compensation (osc.py:275-282): joint space if the target velocity is all zero
+  bool tv_zero = true;
+  if (tv != nullptr) {
+    ABRB_UNROLL
+    for (int c = 0; c < 6; ++c) tv_zero = tv_zero && (tv[c] == T(0));
+  }
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) u[k] = tv_zero ? -O.kv * Mdq[k] : T(0);
+  if (!tv_zero) {
+    ABRB_UNROLL
+    for (int r = 0; r < KD; ++r) err[r] += O.kv * (xdot[r] - tv[r]);
+  }
+  T y[KD];
+  ABRB_UNROLL
+  for (int r = 0; r < KD; ++r) y[r] = ((O.dof_mask >> r) & 1u) ? err[r] : T(0);
+
+  // ---- M = L L^T ;  A <- rows of (L^-1 J^T)^T ;  S = J M^-1 J^T = A A^T   (osc.py:136-137)
+  chol<T, N>(M);
+  ABRB_UNROLL
+  for (int r = 0; r < KD; ++r) fwd_solve<T, N>(M, A[r]);
+  T S[KD][KD];
+  ABRB_UNROLL
+  for (int a = 0; a < KD; ++a)
+    ABRB_UNROLL
+  for (int b = 0; b < KD; ++b) {
+    if (b <= a) {
+      T s = T(0);
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) s += A[a][k] * A[b][k];
+      const bool on = ((O.dof_mask >> a) & 1u) && ((O.dof_mask >> b) & 1u);
+      S[a][b] = on ? s : (a == b ? T(1) : T(0));
+      S[b][a] = S[a][b];
+    }
+  }
+  // ---- Mx: inverse if |det| >= threshold else pinv(rcond = threshold*0.1)   (osc.py:138-145)
+  T Sc[KD][KD];
+  ABRB_UNROLL
+  for (int a = 0; a < KD; ++a)
+    ABRB_UNROLL
+  for (int b = 0; b < KD; ++b) Sc[a][b] = S[a][b];
+  const bool pd = chol<T, KD>(Sc);
+  T det = T(1);
+  ABRB_UNROLL
+  for (int a = 0; a < KD; ++a) det *= Sc[a][a] * Sc[a][a];
+  bool fast = pd && (det >= O.thr);
+  const T rcond = O.thr * T(0.1);
+  if (pd && !fast) {
+    // pinv == inv whenever no eigenvalue is truncated; certify that cheaply:
+    // lambda_max <= trace(S_active), 1/lambda_min <= ||S^-1||_F  =>  no truncation if 1/||S^-1||_F > rcond*trace
+    T tr = T(0), fro = T(0);
+    ABRB_UNROLL
+    for (int a = 0; a < KD; ++a) {
+      if ((O.dof_mask >> a) & 1u) {
+        tr += S[a][a];
+        T e[KD];
+        ABRB_UNROLL
+        for (int b = 0; b < KD; ++b) e[b] = b == a ? T(1) : T(0);
+        fwd_solve<T, KD>(Sc, e);
+        bwd_solve<T, KD>(Sc, e);
+        ABRB_UNROLL
+        for (int b = 0; b < KD; ++b) fro += e[b] * e[b];
+      }
+    }
+    fast = rcond * tr * sqrt_t(fro) < T(1);
+  }
+  auto mx_apply = [&](T *v) {  // v <- Mx v
+    if (fast) {
+      fwd_solve<T, KD>(Sc, v);
+      bwd_solve<T, KD>(Sc, v);
+    } else {
+      T Sf[KD * KD], yi[KD], xo[KD];
+      for (int a = 0; a < KD; ++a) {
+        yi[a] = v[a];
+        for (int b = 0; b < KD; ++b) Sf[a * KD + b] = S[a][b];
+      }
+      pinv_apply_sym<T, KD>(Sf, O.dof_mask & ((1u << KD) - 1u), rcond, yi, xo);
+      for (int a = 0; a < KD; ++a) v[a] = xo[a];
+    }
+  };
+  // u -= J^T Mx y ;  J^T x = L (A^T x)   (osc.py:285-288)
+  auto JT_apply = [&](const T *x, T *out) {
+    T w[N];
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) {
+      T s = T(0);
+      ABRB_UNROLL
+      for (int r = 0; r < KD; ++r) s += A[r][k] * x[r];
+      w[k] = s;
+    }
+    ABRB_UNROLL
+    for (int i = 0; i < N; ++i) {
+      T s = T(0);
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k)
+        if (k <= i) s += M[i][k] * w[k];
+      out[i] = s;
+    }
+  };
+  mx_apply(y);
+  {
+    T jt[N];
+    JT_apply(y, jt);
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) u[k] -= jt[k];
+  }
+  if (O.use_C) {
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) u[k] -= cdq[k];
+  }
+  if (train != nullptr) {
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) train[k] = u[k];  // osc.py:297
+  }
+  if (O.use_g) {
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) u[k] -= g[k];
+  }
+  // ---- secondary controllers through the null-space filter  I - J^T Mx J M^-1   (osc.py:310-318)
+  if (any_null) {
+    if (any_avoid) {
+      T Lf[N * N];
+      for (int a = 0; a < N; ++a)
+        for (int b = 0; b < N; ++b) Lf[a * N + b] = M[a][b];
+      for (int i = 0; i < O.n_null; ++i) {
+        if (O.nul[i].kind == kNullAvoid) {
+          T ua[N];
+          avoid_generate<T, N, ORTHO>(P, O.nul[i], q, Lf, ua);
+          for (int k = 0; k < N; ++k) un[k] += ua[k];
+        }
+      }
+    }
+    T w[N], z[KD], jt[N];
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) w[k] = un[k];
+    fwd_solve<T, N>(M, w);  // L^-1 u_null
+    ABRB_UNROLL
+    for (int r = 0; r < KD; ++r) {
+      T s = T(0);
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) s += A[r][k] * w[k];
+      z[r] = ((O.dof_mask >> r) & 1u) ? s : T(0);
+    }
+    mx_apply(z);
+    JT_apply(z, jt);
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) u[k] += un[k] - jt[k];
+  }
+  if (PLANT) {
+    T rhs[N];
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) rhs[k] = u[k] + g[k] - cdq[k];
+    fwd_solve<T, N>(M, rhs);
+    bwd_solve<T, N>(M, rhs);
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) ddq[k] = rhs[k];
+  }
+}
+
+// Standalone secondary controller (`Damping/RestingConfig/AvoidObstacles.generate`)
+template <typename T, int N, bool ORTHO>
+ABRB_HD void null_state(const ChainK<T, N> &P, const NullK<T, N> &Z, const T *q, const T *dq, T *u) {
+  Kin<T, N, ORTHO> K;
+  walk<T, N, ORTHO>(P, q, 0, K);
+  T M[N][N], g[N];
+  dynamics<T, N, ORTHO, false, false>(P, K, dq, M, g, nullptr, nullptr);
+  ABRB_UNROLL
+  for (int a = 0; a < N; ++a)
+    ABRB_UNROLL
+  for (int b = 0; b < N; ++b)
+    if (b < a) M[a][b] = M[b][a];
+  if (Z.kind == kNullAvoid) {
+    chol<T, N>(M);
+    T Lf[N * N];
+    for (int a = 0; a < N; ++a)
+      for (int b = 0; b < N; ++b) Lf[a * N + b] = M[a][b];
+    avoid_generate<T, N, ORTHO>(P, Z, q, Lf, u);
+    return;
+  }
+  T w[N];
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) {
+    if (Z.kind == kNullDamping) {
+      w[k] = -Z.kv * dq[k];
+    } else {
+      const T qt = ((Z.rest_mask >> k) & 1u) ? wrap_pm_pi(Z.rest[k] - q[k]) : T(0);
+      w[k] = Z.kp * qt - Z.kv * dq[k];
+    }
+  }
+  ABRB_UNROLL
+  for (int a = 0; a < N; ++a) {
+    T s = T(0);
+    ABRB_UNROLL
+    for (int b = 0; b < N; ++b) s += M[a][b] * w[b];
+    u[a] = s;
+  }
+}
+
+}  // namespace abrb

@@ -1,0 +1,156 @@
+// TEST INFRASTRUCTURE ONLY — never loaded by the abr_control_b200 package.
+// Instantiates the __host__ __device__ per-state functions of abr_control_b200/csrc with g++ so that
+// the kernel arithmetic can be unit-tested against the oracle on a machine without a GPU
+// (`pytest -m "not gpu"`).  The shipped library (libabrb.so) reaches the same functions only through
+// CUDA kernels.
+#include <vector>
+
+#include "../../abr_control_b200/csrc/abrb_host.hpp"
+#include "../../abr_control_b200/csrc/abrb_rbd.cuh"
+
+using namespace abrb;
+
+namespace {
+
+template <typename T, int N, bool ORTHO>
+void rbd_loop(const ChainHost &h, int frame, const double *xoff, const double *q, const double *dq, int64_t B,
+              unsigned want, double *Tx, double *Tm, double *R, double *Tinv, double *quat, double *J, double *dJ,
+              double *M, double *g, double *C) {
+  ChainK<T, N> P;
+  fill_chain<T, N>(h, P);
+  T xo[3] = {T(xoff ? xoff[0] : 0), T(xoff ? xoff[1] : 0), T(xoff ? xoff[2] : 0)};
+  for (int64_t b = 0; b < B; ++b) {
+    T qq[N], dd[N];
+    for (int k = 0; k < N; ++k) {
+      qq[k] = T(q[b * N + k]);
+      dd[k] = dq ? T(dq[b * N + k]) : T(0);
+    }
+    RbdOut<T, N> o;
+    rbd_state<T, N, ORTHO, true, true>(P, qq, dd, frame, xo, want, o);
+    auto put = [&](double *dst, const T *src, int len) {
+      if (dst)
+        for (int i = 0; i < len; ++i) dst[b * len + i] = double(src[i]);
+    };
+    put(Tx, o.Tx, 3);
+    put(Tm, o.Tm, 16);
+    put(R, o.R, 9);
+    put(Tinv, o.Tinv, 16);
+    put(quat, o.quat, 4);
+    put(J, &o.J[0][0], 6 * N);
+    put(dJ, &o.dJ[0][0], 6 * N);
+    put(M, &o.M[0][0], N * N);
+    put(g, o.g, N);
+    put(C, &o.C[0][0], N * N);
+  }
+}
+
+template <typename T, int N, bool ORTHO>
+void osc_loop(const ChainHost &h, const abrb_osc_params &p, int frame, const double *xoff, const double *q,
+              const double *dq, const double *target, int tstride, const double *tv, int tvstride, int64_t B,
+              double *u, double *train, double *ddq) {
+  ChainK<T, N> P;
+  fill_chain<T, N>(h, P);
+  OscK<T, N> O;
+  fill_osc<T, N>(p, frame, xoff, O);
+  const bool kd6 = (O.dof_mask & 56u) != 0;
+  for (int64_t b = 0; b < B; ++b) {
+    T qq[N], dd[N], tg[6], tvv[6], uu[N], tr[N], acc[N];
+    for (int k = 0; k < N; ++k) {
+      qq[k] = T(q[b * N + k]);
+      dd[k] = T(dq[b * N + k]);
+    }
+    for (int c = 0; c < 6; ++c) {
+      tg[c] = T(target[b * tstride + c]);
+      tvv[c] = tv ? T(tv[b * tvstride + c]) : T(0);
+    }
+    if (kd6)
+      osc_state<T, N, ORTHO, 6, true>(P, O, qq, dd, tg, tv ? tvv : nullptr, uu, tr, acc);
+    else
+      osc_state<T, N, ORTHO, 3, true>(P, O, qq, dd, tg, tv ? tvv : nullptr, uu, tr, acc);
+    for (int k = 0; k < N; ++k) {
+      u[b * N + k] = double(uu[k]);
+      if (train) train[b * N + k] = double(tr[k]);
+      if (ddq) ddq[b * N + k] = double(acc[k]);
+    }
+  }
+}
+
+template <typename T, int N, bool ORTHO>
+void null_loop(const ChainHost &h, const abrb_null_params &z, const double *q, const double *dq, int64_t B, double *u) {
+  ChainK<T, N> P;
+  fill_chain<T, N>(h, P);
+  NullK<T, N> Z;
+  fill_null<T, N>(z, Z);
+  for (int64_t b = 0; b < B; ++b) {
+    T qq[N], dd[N], uu[N];
+    for (int k = 0; k < N; ++k) {
+      qq[k] = T(q[b * N + k]);
+      dd[k] = T(dq[b * N + k]);
+    }
+    null_state<T, N, ORTHO>(P, Z, qq, dd, uu);
+    for (int k = 0; k < N; ++k) u[b * N + k] = double(uu[k]);
+  }
+}
+
+}  // namespace
+
+#define DISPATCH_N(FN, ...)                                       \
+  switch (h.n) {                                                  \
+    case 2: DISPATCH_T(FN, 2, __VA_ARGS__); break;                \
+    case 3: DISPATCH_T(FN, 3, __VA_ARGS__); break;                \
+    case 6: DISPATCH_T(FN, 6, __VA_ARGS__); break;                \
+    default: return ABRB_ESHAPE;                                  \
+  }
+#define DISPATCH_T(FN, N, ...)                                    \
+  if (f32) {                                                      \
+    if (ortho) FN<float, N, true>(__VA_ARGS__); else FN<float, N, false>(__VA_ARGS__);   \
+  } else {                                                        \
+    if (ortho) FN<double, N, true>(__VA_ARGS__); else FN<double, N, false>(__VA_ARGS__); \
+  }
+
+extern "C" {
+
+// force_general != 0 runs the non-orthonormal code path even for orthonormal chains
+int hs_rbd(const abrb_chain_desc *d, int f32, int force_general, int frame, const double *xoff, const double *q,
+           const double *dq, int64_t B, double *Tx, double *Tm, double *R, double *Tinv, double *quat, double *J,
+           double *dJ, double *M, double *g, double *C) {
+  ChainHost h;
+  if (!chain_from_desc(*d, h).empty()) return ABRB_EINVAL;
+  const bool ortho = h.ortho && !force_general;
+  unsigned want = 0;
+  if (Tx) want |= kWantTx;
+  if (Tm) want |= kWantT;
+  if (R) want |= kWantR;
+  if (Tinv) want |= kWantTinv;
+  if (quat) want |= kWantQuat;
+  if (J) want |= kWantJ;
+  if (dJ) want |= kWantdJ | kWantJ;
+  if (M) want |= kWantM;
+  if (g) want |= kWantg;
+  if (C) want |= kWantC;
+  DISPATCH_N(rbd_loop, h, frame, xoff, q, dq, B, want, Tx, Tm, R, Tinv, quat, J, dJ, M, g, C);
+  return 0;
+}
+
+int hs_osc(const abrb_chain_desc *d, const abrb_osc_params *p, int f32, int force_general, int frame,
+           const double *xoff, const double *q, const double *dq, const double *target, int tstride, const double *tv,
+           int tvstride, int64_t B, double *u, double *train, double *ddq) {
+  ChainHost h;
+  if (!chain_from_desc(*d, h).empty()) return ABRB_EINVAL;
+  if (!check_osc(h.n, *p).empty()) return ABRB_EUNSUP;
+  const bool ortho = h.ortho && !force_general;
+  DISPATCH_N(osc_loop, h, *p, frame, xoff, q, dq, target, tstride, tv, tvstride, B, u, train, ddq);
+  return 0;
+}
+
+int hs_null(const abrb_chain_desc *d, const abrb_null_params *z, int f32, int force_general, const double *q,
+            const double *dq, int64_t B, double *u) {
+  ChainHost h;
+  if (!chain_from_desc(*d, h).empty()) return ABRB_EINVAL;
+  const bool ortho = h.ortho && !force_general;
+  DISPATCH_N(null_loop, h, *z, q, dq, B, u);
+  return 0;
+}
+
+int hs_frame_id(int n, const char *name) { return parse_frame(n, name); }
+}
