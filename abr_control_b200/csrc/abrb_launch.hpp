@@ -1,0 +1,60 @@
+// abrb_launch.hpp — host-side launch interface between api.cu and the per-joint-count kernel TUs.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "abrb_host.hpp"
+
+namespace abrb {
+
+struct RbdCall {
+  int frame;
+  const double *xoff;  // host, 3 values or nullptr
+  const void *q, *dq;  // device
+  int64_t B;
+  abrb_rbd_out out;    // device pointers
+  bool f32;
+  cudaStream_t stream;
+};
+
+struct OscCall {
+  int frame;
+  const double *xoff;
+  const void *q, *dq, *target, *tv;  // device
+  int target_stride, tv_stride;
+  void *u, *train;
+  int64_t B;
+  bool f32;
+  cudaStream_t stream;
+};
+
+struct RolloutCall {
+  int frame;
+  const double *xoff;
+  void *q, *dq;  // device, in/out
+  const void *target;
+  int target_stride;
+  int steps;
+  double dt;
+  void *q_traj, *dq_traj, *u_traj;
+  int64_t B;
+  bool f32;
+  cudaStream_t stream;
+};
+
+struct NullCall {
+  const void *q, *dq;
+  void *u;
+  int64_t B;
+  bool f32;
+  cudaStream_t stream;
+};
+
+// Each returns a cudaError_t (0 = success).  Defined once per joint count in kernels.cu (-DABRB_N=<n>).
+template <int N> int launch_rbd(const ChainHost &h, const RbdCall &c);
+template <int N> int launch_osc(const ChainHost &h, const abrb_osc_params &p, const OscCall &c);
+template <int N> int launch_rollout(const ChainHost &h, const abrb_osc_params &p, const RolloutCall &c);
+template <int N> int launch_null(const ChainHost &h, const abrb_null_params &z, const NullCall &c);
+
+void count_launch();
+
+}  // namespace abrb

@@ -1,0 +1,389 @@
+// api.cu — the C ABI of libabrb.so (include/abrb.h): handle management, argument checking, dispatch on the
+// joint count to the per-N kernel translation units, host-pointer convenience variants.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "abrb_launch.hpp"
+
+using namespace abrb;
+
+struct abrb_model {
+  abrb_chain_desc desc;
+  ChainHost host;
+};
+
+struct abrb_osc {
+  const abrb_model *model;
+  abrb_osc_params params;
+};
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+int cuda_fail(int e, const char *where) {
+  return fail(ABRB_ECUDA, std::string(where) + ": " + cudaGetErrorString((cudaError_t)e));
+}
+
+#ifndef ABRB_N_LIST
+#define ABRB_N_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
+#endif
+
+bool n_supported(int n) {
+#define X(k) if (n == k) return true;
+  ABRB_N_LIST(X)
+#undef X
+  return false;
+}
+
+int ensure_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(ABRB_ECUDA, "no CUDA device available (libabrb has no CPU fallback)");
+  }
+  return ABRB_OK;
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// grow-only device workspace for the *_host entry points (one per host thread)
+struct Workspace {
+  void *ptr = nullptr;
+  size_t cap = 0;
+  cudaStream_t stream = nullptr;
+  int ensure(size_t bytes) {
+    if (stream == nullptr) {
+      cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+      if (e != cudaSuccess) return (int)e;
+    }
+    if (bytes <= cap) return 0;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&ptr, bytes);
+    if (e != cudaSuccess) return (int)e;
+    cap = bytes;
+    return 0;
+  }
+};
+thread_local Workspace g_ws;
+
+size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+}  // namespace
+
+namespace abrb {
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace abrb
+
+extern "C" {
+
+int abrb_version(void) { return ABRB_VERSION; }
+const char *abrb_last_error(void) { return g_err.c_str(); }
+int64_t abrb_launch_count(void) { return g_launches.load(); }
+
+int abrb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ABRB_ECUDA, "cudaGetDeviceCount failed");
+  }
+  return n;
+}
+
+int abrb_model_create(const abrb_chain_desc *desc, abrb_model **out) {
+  if (!desc || !out) return fail(ABRB_EINVAL, "abrb_model_create: NULL argument");
+  *out = nullptr;
+  if (desc->n_joints < 1 || desc->n_joints > ABRB_MAX_JOINTS || !n_supported(desc->n_joints))
+    return fail(ABRB_ESHAPE, "abrb_model_create: n_joints not supported by this build");
+  abrb_model *m = new (std::nothrow) abrb_model;
+  if (!m) return fail(ABRB_ENOMEM, "abrb_model_create: out of memory");
+  m->desc = *desc;
+  std::string e = chain_from_desc(*desc, m->host);
+  if (!e.empty()) {
+    delete m;
+    return fail(ABRB_ESHAPE, "abrb_model_create: " + e);
+  }
+  *out = m;
+  return ABRB_OK;
+}
+
+int abrb_model_destroy(abrb_model *m) {
+  delete m;
+  return ABRB_OK;
+}
+
+int abrb_model_n_joints(const abrb_model *m) { return m ? m->host.n : fail(ABRB_EINVAL, "NULL model"); }
+int abrb_model_is_orthonormal(const abrb_model *m) { return m ? (m->host.ortho ? 1 : 0) : fail(ABRB_EINVAL, "NULL model"); }
+
+int abrb_frame_id(const abrb_model *m, const char *name) {
+  if (!m) return fail(ABRB_EINVAL, "NULL model");
+  int id = parse_frame(m->host.n, name);
+  if (id < 0) return fail(ABRB_EFRAME, std::string("Invalid transformation name: ") + (name ? name : "(null)"));
+  return id;
+}
+
+// ------------------------------------------------------------------------------------------------ rbd
+static int rbd_eval(const abrb_model *m, int frame_id, const double *x_off, const void *q, const void *dq,
+                    int64_t B, const abrb_rbd_out *out, void *stream, bool f32) {
+  if (!m || !out) return fail(ABRB_EINVAL, "abrb_rbd_eval: NULL model/out");
+  if (B < 0) return fail(ABRB_EINVAL, "abrb_rbd_eval: B < 0");
+  const int n = m->host.n;
+  if (frame_id < 0 || frame_id > 2 * n + 1) return fail(ABRB_EFRAME, "abrb_rbd_eval: invalid frame id");
+  if ((out->dJ || out->C) && !dq) return fail(ABRB_EINVAL, "abrb_rbd_eval: dJ / C need dq");
+  if (B == 0) return ABRB_OK;
+  if (!q) return fail(ABRB_EINVAL, "abrb_rbd_eval: NULL q");
+  const void *ptrs[] = {q, dq, out->Tx, out->T, out->R, out->T_inv, out->quat, out->J, out->dJ, out->M, out->g, out->C};
+  for (const void *p : ptrs)
+    if (p && !aligned16(p)) return fail(ABRB_EINVAL, "abrb_rbd_eval: pointers must be 16-byte aligned");
+  int rc = ensure_device();
+  if (rc) return rc;
+  RbdCall c{frame_id, x_off, q, dq, B, *out, f32, (cudaStream_t)stream};
+  int e = cudaErrorInvalidValue;
+  switch (n) {
+#define X(k) case k: e = launch_rbd<k>(m->host, c); break;
+    ABRB_N_LIST(X)
+#undef X
+  }
+  return e ? cuda_fail(e, "abrb_rbd_eval") : ABRB_OK;
+}
+
+int abrb_rbd_eval_f64(const abrb_model *m, int frame_id, const double *x_off, const double *q, const double *dq,
+                      int64_t B, const abrb_rbd_out *out, void *stream) {
+  return rbd_eval(m, frame_id, x_off, q, dq, B, out, stream, false);
+}
+int abrb_rbd_eval_f32(const abrb_model *m, int frame_id, const double *x_off, const float *q, const float *dq,
+                      int64_t B, const abrb_rbd_out *out, void *stream) {
+  return rbd_eval(m, frame_id, x_off, q, dq, B, out, stream, true);
+}
+
+static int rbd_eval_host(const abrb_model *m, int frame_id, const double *x_off, const void *q, const void *dq,
+                         int64_t B, const abrb_rbd_out *out, bool f32) {
+  if (!m || !out) return fail(ABRB_EINVAL, "abrb_rbd_eval_host: NULL model/out");
+  if (B < 0) return fail(ABRB_EINVAL, "abrb_rbd_eval_host: B < 0");
+  if (B == 0) return ABRB_OK;
+  if (!q) return fail(ABRB_EINVAL, "abrb_rbd_eval_host: NULL q");
+  int rc = ensure_device();
+  if (rc) return rc;
+  const size_t es = f32 ? 4 : 8, n = (size_t)m->host.n;
+  const size_t len[10] = {3, 16, 9, 16, 4, 6 * n, 6 * n, n * n, n, n * n};
+  void *const host_out[10] = {out->Tx, out->T, out->R, out->T_inv, out->quat, out->J, out->dJ, out->M, out->g, out->C};
+  size_t total = 2 * align_up((size_t)B * n * es);
+  for (int i = 0; i < 10; ++i)
+    if (host_out[i]) total += align_up((size_t)B * len[i] * es);
+  int e = g_ws.ensure(total);
+  if (e) return cuda_fail(e, "abrb_rbd_eval_host(workspace)");
+  char *base = static_cast<char *>(g_ws.ptr);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char *p = base + off; off += align_up(bytes); return (void *)p; };
+  void *dq_q = take((size_t)B * n * es), *dq_dq = take((size_t)B * n * es);
+  cudaStream_t s = g_ws.stream;
+  cudaMemcpyAsync(dq_q, q, (size_t)B * n * es, cudaMemcpyHostToDevice, s);
+  if (dq) cudaMemcpyAsync(dq_dq, dq, (size_t)B * n * es, cudaMemcpyHostToDevice, s);
+  void *dev_out[10];
+  for (int i = 0; i < 10; ++i) dev_out[i] = host_out[i] ? take((size_t)B * len[i] * es) : nullptr;
+  abrb_rbd_out d{dev_out[0], dev_out[1], dev_out[2], dev_out[3], dev_out[4], dev_out[5], dev_out[6], dev_out[7], dev_out[8], dev_out[9]};
+  rc = rbd_eval(m, frame_id, x_off, dq_q, dq ? dq_dq : nullptr, B, &d, s, f32);
+  if (rc) return rc;
+  for (int i = 0; i < 10; ++i)
+    if (host_out[i]) cudaMemcpyAsync(host_out[i], dev_out[i], (size_t)B * len[i] * es, cudaMemcpyDeviceToHost, s);
+  cudaError_t ce = cudaStreamSynchronize(s);
+  return ce ? cuda_fail(ce, "abrb_rbd_eval_host") : ABRB_OK;
+}
+
+int abrb_rbd_eval_host_f64(const abrb_model *m, int frame_id, const double *x_off, const double *q, const double *dq,
+                           int64_t B, const abrb_rbd_out *out) {
+  return rbd_eval_host(m, frame_id, x_off, q, dq, B, out, false);
+}
+int abrb_rbd_eval_host_f32(const abrb_model *m, int frame_id, const double *x_off, const float *q, const float *dq,
+                           int64_t B, const abrb_rbd_out *out) {
+  return rbd_eval_host(m, frame_id, x_off, q, dq, B, out, true);
+}
+
+// ------------------------------------------------------------------------------------------------ osc
+int abrb_osc_create(const abrb_model *m, const abrb_osc_params *p, abrb_osc **out) {
+  if (!m || !p || !out) return fail(ABRB_EINVAL, "abrb_osc_create: NULL argument");
+  *out = nullptr;
+  std::string e = check_osc(m->host.n, *p);
+  if (!e.empty()) return fail(ABRB_EUNSUP, "abrb_osc_create: " + e);
+  abrb_osc *c = new (std::nothrow) abrb_osc;
+  if (!c) return fail(ABRB_ENOMEM, "abrb_osc_create: out of memory");
+  c->model = m;
+  c->params = *p;
+  *out = c;
+  return ABRB_OK;
+}
+
+int abrb_osc_destroy(abrb_osc *c) {
+  delete c;
+  return ABRB_OK;
+}
+
+static int osc_generate(const abrb_osc *c, int frame_id, const double *x_off, const void *q, const void *dq,
+                        const void *target, int target_stride, const void *tv, int tv_stride, void *u, void *train,
+                        int64_t B, void *stream, bool f32) {
+  if (!c) return fail(ABRB_EINVAL, "abrb_osc_generate: NULL controller");
+  if (B < 0) return fail(ABRB_EINVAL, "abrb_osc_generate: B < 0");
+  const int n = c->model->host.n;
+  if (frame_id < 0 || frame_id > 2 * n + 1) return fail(ABRB_EFRAME, "abrb_osc_generate: invalid frame id");
+  if ((target_stride != 0 && target_stride != 6) || (tv && tv_stride != 0 && tv_stride != 6))
+    return fail(ABRB_EINVAL, "abrb_osc_generate: stride must be 0 (broadcast) or 6");
+  if (B == 0) return ABRB_OK;
+  if (!q || !dq || !target || !u) return fail(ABRB_EINVAL, "abrb_osc_generate: NULL q/dq/target/u");
+  const void *ptrs[] = {q, dq, u, train};
+  for (const void *p : ptrs)
+    if (p && !aligned16(p)) return fail(ABRB_EINVAL, "abrb_osc_generate: pointers must be 16-byte aligned");
+  int rc = ensure_device();
+  if (rc) return rc;
+  OscCall k{frame_id, x_off, q, dq, target, tv, target_stride, tv_stride, u, train, B, f32, (cudaStream_t)stream};
+  int e = cudaErrorInvalidValue;
+  switch (n) {
+#define X(j) case j: e = launch_osc<j>(c->model->host, c->params, k); break;
+    ABRB_N_LIST(X)
+#undef X
+  }
+  return e ? cuda_fail(e, "abrb_osc_generate") : ABRB_OK;
+}
+
+int abrb_osc_generate_f64(const abrb_osc *c, int frame_id, const double *x_off, const double *q, const double *dq,
+                          const double *target, int target_stride, const double *target_velocity, int tv_stride,
+                          double *u, double *training_signal, int64_t B, void *stream) {
+  return osc_generate(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride, u,
+                      training_signal, B, stream, false);
+}
+int abrb_osc_generate_f32(const abrb_osc *c, int frame_id, const double *x_off, const float *q, const float *dq,
+                          const float *target, int target_stride, const float *target_velocity, int tv_stride,
+                          float *u, float *training_signal, int64_t B, void *stream) {
+  return osc_generate(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride, u,
+                      training_signal, B, stream, true);
+}
+
+static int osc_generate_host(const abrb_osc *c, int frame_id, const double *x_off, const void *q, const void *dq,
+                             const void *target, int target_stride, const void *tv, int tv_stride, void *u,
+                             void *train, int64_t B, bool f32) {
+  if (!c) return fail(ABRB_EINVAL, "abrb_osc_generate_host: NULL controller");
+  if (B < 0) return fail(ABRB_EINVAL, "abrb_osc_generate_host: B < 0");
+  if (B == 0) return ABRB_OK;
+  if (!q || !dq || !target || !u) return fail(ABRB_EINVAL, "abrb_osc_generate_host: NULL q/dq/target/u");
+  int rc = ensure_device();
+  if (rc) return rc;
+  const size_t es = f32 ? 4 : 8, n = (size_t)c->model->host.n;
+  const size_t sz_state = (size_t)B * n * es;
+  const size_t sz_t = (target_stride ? (size_t)B : 1) * 6 * es, sz_tv = tv ? (tv_stride ? (size_t)B : 1) * 6 * es : 0;
+  int e = g_ws.ensure(4 * align_up(sz_state) + align_up(sz_t) + align_up(sz_tv) + 256);
+  if (e) return cuda_fail(e, "abrb_osc_generate_host(workspace)");
+  char *base = static_cast<char *>(g_ws.ptr);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char *p = base + off; off += align_up(bytes); return (void *)p; };
+  void *d_q = take(sz_state), *d_dq = take(sz_state), *d_u = take(sz_state), *d_tr = take(sz_state);
+  void *d_t = take(sz_t), *d_tv = tv ? take(sz_tv) : nullptr;
+  cudaStream_t s = g_ws.stream;
+  cudaMemcpyAsync(d_q, q, sz_state, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_dq, dq, sz_state, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_t, target, sz_t, cudaMemcpyHostToDevice, s);
+  if (tv) cudaMemcpyAsync(d_tv, tv, sz_tv, cudaMemcpyHostToDevice, s);
+  rc = osc_generate(c, frame_id, x_off, d_q, d_dq, d_t, target_stride, d_tv, tv_stride, d_u, train ? d_tr : nullptr, B,
+                    s, f32);
+  if (rc) return rc;
+  cudaMemcpyAsync(u, d_u, sz_state, cudaMemcpyDeviceToHost, s);
+  if (train) cudaMemcpyAsync(train, d_tr, sz_state, cudaMemcpyDeviceToHost, s);
+  cudaError_t ce = cudaStreamSynchronize(s);
+  return ce ? cuda_fail(ce, "abrb_osc_generate_host") : ABRB_OK;
+}
+
+int abrb_osc_generate_host_f64(const abrb_osc *c, int frame_id, const double *x_off, const double *q, const double *dq,
+                               const double *target, int target_stride, const double *target_velocity,
+                               int tv_stride, double *u, double *training_signal, int64_t B) {
+  return osc_generate_host(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride, u,
+                           training_signal, B, false);
+}
+int abrb_osc_generate_host_f32(const abrb_osc *c, int frame_id, const double *x_off, const float *q, const float *dq,
+                               const float *target, int target_stride, const float *target_velocity, int tv_stride,
+                               float *u, float *training_signal, int64_t B) {
+  return osc_generate_host(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride, u,
+                           training_signal, B, true);
+}
+
+// ------------------------------------------------------------------------------------------------ null
+static int null_generate(const abrb_model *m, const abrb_null_params *p, const void *q, const void *dq, void *u,
+                         int64_t B, void *stream, bool f32) {
+  if (!m || !p) return fail(ABRB_EINVAL, "abrb_null_generate: NULL argument");
+  if (B < 0) return fail(ABRB_EINVAL, "abrb_null_generate: B < 0");
+  std::string e = check_null(m->host.n, *p);
+  if (!e.empty()) return fail(ABRB_EUNSUP, "abrb_null_generate: " + e);
+  if (B == 0) return ABRB_OK;
+  if (!q || !dq || !u) return fail(ABRB_EINVAL, "abrb_null_generate: NULL q/dq/u");
+  if (!aligned16(q) || !aligned16(dq) || !aligned16(u))
+    return fail(ABRB_EINVAL, "abrb_null_generate: pointers must be 16-byte aligned");
+  int rc = ensure_device();
+  if (rc) return rc;
+  NullCall k{q, dq, u, B, f32, (cudaStream_t)stream};
+  int ce = cudaErrorInvalidValue;
+  switch (m->host.n) {
+#define X(j) case j: ce = launch_null<j>(m->host, *p, k); break;
+    ABRB_N_LIST(X)
+#undef X
+  }
+  return ce ? cuda_fail(ce, "abrb_null_generate") : ABRB_OK;
+}
+
+int abrb_null_generate_f64(const abrb_model *m, const abrb_null_params *p, const double *q, const double *dq,
+                           double *u, int64_t B, void *stream) {
+  return null_generate(m, p, q, dq, u, B, stream, false);
+}
+int abrb_null_generate_f32(const abrb_model *m, const abrb_null_params *p, const float *q, const float *dq, float *u,
+                           int64_t B, void *stream) {
+  return null_generate(m, p, q, dq, u, B, stream, true);
+}
+
+// ------------------------------------------------------------------------------------------------ rollout
+static int osc_rollout(const abrb_osc *c, int frame_id, const double *x_off, void *q, void *dq, const void *target,
+                       int target_stride, int steps, double dt, void *q_traj, void *dq_traj, void *u_traj, int64_t B,
+                       void *stream, bool f32) {
+  if (!c) return fail(ABRB_EINVAL, "abrb_osc_rollout: NULL controller");
+  if (B < 0 || steps < 0) return fail(ABRB_EINVAL, "abrb_osc_rollout: B < 0 or steps < 0");
+  const int n = c->model->host.n;
+  if (frame_id < 0 || frame_id > 2 * n + 1) return fail(ABRB_EFRAME, "abrb_osc_rollout: invalid frame id");
+  if (target_stride != 0 && target_stride != 6) return fail(ABRB_EINVAL, "abrb_osc_rollout: stride must be 0 or 6");
+  if (B == 0 || steps == 0) return ABRB_OK;
+  if (!q || !dq || !target) return fail(ABRB_EINVAL, "abrb_osc_rollout: NULL q/dq/target");
+  const void *ptrs[] = {q, dq, q_traj, dq_traj, u_traj};
+  for (const void *p : ptrs)
+    if (p && !aligned16(p)) return fail(ABRB_EINVAL, "abrb_osc_rollout: pointers must be 16-byte aligned");
+  int rc = ensure_device();
+  if (rc) return rc;
+  RolloutCall k{frame_id, x_off, q, dq, target, target_stride, steps, dt, q_traj, dq_traj, u_traj, B, f32, (cudaStream_t)stream};
+  int e = cudaErrorInvalidValue;
+  switch (n) {
+#define X(j) case j: e = launch_rollout<j>(c->model->host, c->params, k); break;
+    ABRB_N_LIST(X)
+#undef X
+  }
+  return e ? cuda_fail(e, "abrb_osc_rollout") : ABRB_OK;
+}
+
+int abrb_osc_rollout_f64(const abrb_osc *c, int frame_id, const double *x_off, double *q, double *dq,
+                         const double *target, int target_stride, int steps, double dt, double *q_traj,
+                         double *dq_traj, double *u_traj, int64_t B, void *stream) {
+  return osc_rollout(c, frame_id, x_off, q, dq, target, target_stride, steps, dt, q_traj, dq_traj, u_traj, B, stream, false);
+}
+int abrb_osc_rollout_f32(const abrb_osc *c, int frame_id, const double *x_off, float *q, float *dq, const float *target,
+                         int target_stride, int steps, double dt, float *q_traj, float *dq_traj, float *u_traj,
+                         int64_t B, void *stream) {
+  return osc_rollout(c, frame_id, x_off, q, dq, target, target_stride, steps, dt, q_traj, dq_traj, u_traj, B, stream, true);
+}
+
+}  // extern "C"

@@ -1,0 +1,396 @@
+// kernels.cu — sm_100a kernels of the batched arm engine, compiled once per joint count (-DABRB_N=<n>).
+//
+// Mapping: ONE JOINT STATE PER THREAD.  The per-state arithmetic (abrb_math.cuh / abrb_rbd.cuh /
+// abrb_osc.cuh) is a straight-line, fully unrolled sequence on registers; chain constants come from the
+// kernel-parameter constant bank (uniform across the warp).  Loads of the (B, n) state arrays are
+// contiguous per warp; every output array is staged per warp in shared memory and written back with
+// fully coalesced 16-byte stores, so HBM sees whole 128-byte lines only.
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+#include "abrb_launch.hpp"
+#include "abrb_osc.cuh"
+#include "abrb_rbd.cuh"
+
+#ifndef ABRB_N
+#error "compile with -DABRB_N=<joint count>"
+#endif
+
+namespace abrb {
+
+namespace {
+
+constexpr int kBlock = 128;
+constexpr int kWarps = kBlock / 32;
+
+template <int N>
+struct MaxRecord {
+  static constexpr int big = N * N > 6 * N ? N * N : 6 * N;
+  static constexpr int value = big > 16 ? big : 16;
+};
+
+// Write one LEN-element record per lane to `out[(warp_b0 + lane) * LEN + e]` through the warp's staging
+// tile: conflict-light scalar writes into smem, then a linear, fully coalesced copy-out (16-byte vectors
+// for full warps).
+template <typename T, int LEN>
+__device__ __forceinline__ void store_records(T *__restrict__ out, int64_t warp_b0, int nvalid, const T *rec,
+                                              T *stage, int lane) {
+#pragma unroll
+  for (int e = 0; e < LEN; ++e) stage[lane * LEN + e] = rec[e];
+  __syncwarp();
+  T *dst = out + warp_b0 * LEN;
+  if (nvalid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    constexpr int kVec = (32 * LEN * (int)sizeof(T)) / 16;
+    const float4 *s4 = reinterpret_cast<const float4 *>(stage);
+    float4 *d4 = reinterpret_cast<float4 *>(dst);
+#pragma unroll
+    for (int i = 0; i < (kVec + 31) / 32; ++i) {
+      const int idx = i * 32 + lane;
+      if (idx < kVec) d4[idx] = s4[idx];
+    }
+  } else {
+    const int total = nvalid * LEN;
+    for (int i = lane; i < total; i += 32) dst[i] = stage[i];
+  }
+  __syncwarp();
+}
+
+template <typename T>
+struct RbdArgs {
+  const T *q, *dq;
+  T *Tx, *Tm, *R, *Tinv, *quat, *J, *dJ, *M, *g, *C;
+  int64_t B;
+  int frame;
+  unsigned want;
+  T xoff[3];
+};
+
+template <typename T, int N, bool ORTHO, bool DYN, bool CMAT>
+__global__ void __launch_bounds__(kBlock)
+rbd_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ RbdArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T *stage = reinterpret_cast<T *>(smem_raw) + warp * 32 * MaxRecord<N>::value;
+  for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
+    const int64_t warp_b0 = base + warp * 32;
+    if (warp_b0 >= a.B) break;  // whole warp out of range (uniform per warp)
+    const int64_t rem = a.B - warp_b0;
+    const int nvalid = rem < 32 ? (int)rem : 32;
+    const int64_t b = warp_b0 + (lane < nvalid ? lane : nvalid - 1);  // clamp: idle lanes redo the last state
+    T q[N], dq[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      q[k] = a.q[b * N + k];
+      dq[k] = a.dq != nullptr ? a.dq[b * N + k] : T(0);
+    }
+    RbdOut<T, N> o;
+    rbd_state<T, N, ORTHO, DYN, CMAT>(P, q, dq, a.frame, a.xoff, a.want, o);
+    if (a.Tx) store_records<T, 3>(a.Tx, warp_b0, nvalid, o.Tx, stage, lane);
+    if (a.Tm) store_records<T, 16>(a.Tm, warp_b0, nvalid, o.Tm, stage, lane);
+    if (a.R) store_records<T, 9>(a.R, warp_b0, nvalid, o.R, stage, lane);
+    if (a.Tinv) store_records<T, 16>(a.Tinv, warp_b0, nvalid, o.Tinv, stage, lane);
+    if (a.quat) store_records<T, 4>(a.quat, warp_b0, nvalid, o.quat, stage, lane);
+    if (a.J) store_records<T, 6 * N>(a.J, warp_b0, nvalid, &o.J[0][0], stage, lane);
+    if (a.dJ) store_records<T, 6 * N>(a.dJ, warp_b0, nvalid, &o.dJ[0][0], stage, lane);
+    if (DYN || CMAT) {
+      if (a.M) store_records<T, N * N>(a.M, warp_b0, nvalid, &o.M[0][0], stage, lane);
+      if (a.g) store_records<T, N>(a.g, warp_b0, nvalid, o.g, stage, lane);
+    }
+    if (CMAT) {
+      if (a.C) store_records<T, N * N>(a.C, warp_b0, nvalid, &o.C[0][0], stage, lane);
+    }
+  }
+}
+
+template <typename T>
+struct OscArgs {
+  const T *q, *dq, *target, *tv;
+  T *u, *train;
+  int64_t B;
+  int target_stride, tv_stride;
+};
+
+template <typename T, int N, bool ORTHO, int KD>
+__global__ void __launch_bounds__(kBlock)
+osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
+           const __grid_constant__ OscArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T *stage = reinterpret_cast<T *>(smem_raw) + warp * 32 * N;
+  for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
+    const int64_t warp_b0 = base + warp * 32;
+    if (warp_b0 >= a.B) break;
+    const int64_t rem = a.B - warp_b0;
+    const int nvalid = rem < 32 ? (int)rem : 32;
+    const int64_t b = warp_b0 + (lane < nvalid ? lane : nvalid - 1);
+    T q[N], dq[N], tg[6], tv[6], u[N], tr[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      q[k] = a.q[b * N + k];
+      dq[k] = a.dq[b * N + k];
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      tg[c] = a.target[b * a.target_stride + c];
+      tv[c] = a.tv != nullptr ? a.tv[b * a.tv_stride + c] : T(0);
+    }
+    osc_state<T, N, ORTHO, KD, false>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, u, tr, nullptr);
+    store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);
+    if (a.train) store_records<T, N>(a.train, warp_b0, nvalid, tr, stage, lane);
+  }
+}
+
+template <typename T>
+struct RolloutArgs {
+  T *q, *dq;
+  const T *target;
+  T *q_traj, *dq_traj, *u_traj;
+  int64_t B;
+  int target_stride, steps;
+  T dt;
+};
+
+// Closed loop: u = OSC(q, dq); ddq = M^-1 (u + g - C dq); dq += ddq dt; q += dq dt  (state stays in registers)
+template <typename T, int N, bool ORTHO, int KD>
+__global__ void __launch_bounds__(kBlock)
+rollout_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
+               const __grid_constant__ RolloutArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T *stage = reinterpret_cast<T *>(smem_raw) + warp * 32 * N;
+  for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
+    const int64_t warp_b0 = base + warp * 32;
+    if (warp_b0 >= a.B) break;
+    const int64_t rem = a.B - warp_b0;
+    const int nvalid = rem < 32 ? (int)rem : 32;
+    const int64_t b = warp_b0 + (lane < nvalid ? lane : nvalid - 1);
+    T q[N], dq[N], tg[6], u[N], acc[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      q[k] = a.q[b * N + k];
+      dq[k] = a.dq[b * N + k];
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) tg[c] = a.target[b * a.target_stride + c];
+    for (int t = 0; t < a.steps; ++t) {
+      osc_state<T, N, ORTHO, KD, true>(P, O, q, dq, tg, nullptr, u, nullptr, acc);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        dq[k] += acc[k] * a.dt;
+        q[k] += dq[k] * a.dt;
+      }
+      const int64_t row0 = (int64_t)t * a.B + warp_b0;
+      if (a.u_traj) store_records<T, N>(a.u_traj, row0, nvalid, u, stage, lane);
+      if (a.q_traj) store_records<T, N>(a.q_traj, row0, nvalid, q, stage, lane);
+      if (a.dq_traj) store_records<T, N>(a.dq_traj, row0, nvalid, dq, stage, lane);
+    }
+    store_records<T, N>(a.q, warp_b0, nvalid, q, stage, lane);
+    store_records<T, N>(a.dq, warp_b0, nvalid, dq, stage, lane);
+  }
+}
+
+template <typename T>
+struct NullArgs {
+  const T *q, *dq;
+  T *u;
+  int64_t B;
+};
+
+template <typename T, int N, bool ORTHO>
+__global__ void __launch_bounds__(kBlock)
+null_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ NullK<T, N> Z,
+            const __grid_constant__ NullArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T *stage = reinterpret_cast<T *>(smem_raw) + warp * 32 * N;
+  for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
+    const int64_t warp_b0 = base + warp * 32;
+    if (warp_b0 >= a.B) break;
+    const int64_t rem = a.B - warp_b0;
+    const int nvalid = rem < 32 ? (int)rem : 32;
+    const int64_t b = warp_b0 + (lane < nvalid ? lane : nvalid - 1);
+    T q[N], dq[N], u[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      q[k] = a.q[b * N + k];
+      dq[k] = a.dq[b * N + k];
+    }
+    null_state<T, N, ORTHO>(P, Z, q, dq, u);
+    store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ launch
+inline int grid_for(int64_t B, int blocks_per_sm) {
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
+      sm_count = 148;
+  }
+  const int64_t tiles = (B + kBlock - 1) / kBlock;
+  const int64_t cap = (int64_t)sm_count * blocks_per_sm;
+  return (int)(tiles < cap ? tiles : cap);
+}
+
+template <typename K>
+inline cudaError_t set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return cudaSuccess;
+}
+
+template <typename T, int N, bool ORTHO, bool DYN, bool CMAT>
+int rbd_go(const ChainHost &h, const RbdCall &c, unsigned want) {
+  ChainK<T, N> P;
+  fill_chain<T, N>(h, P);
+  RbdArgs<T> a;
+  a.q = static_cast<const T *>(c.q);
+  a.dq = static_cast<const T *>(c.dq);
+  a.Tx = static_cast<T *>(c.out.Tx);
+  a.Tm = static_cast<T *>(c.out.T);
+  a.R = static_cast<T *>(c.out.R);
+  a.Tinv = static_cast<T *>(c.out.T_inv);
+  a.quat = static_cast<T *>(c.out.quat);
+  a.J = static_cast<T *>(c.out.J);
+  a.dJ = static_cast<T *>(c.out.dJ);
+  a.M = static_cast<T *>(c.out.M);
+  a.g = static_cast<T *>(c.out.g);
+  a.C = static_cast<T *>(c.out.C);
+  a.B = c.B;
+  a.frame = c.frame;
+  a.want = want;
+  for (int i = 0; i < 3; ++i) a.xoff[i] = c.xoff ? T(c.xoff[i]) : T(0);
+  const size_t smem = (size_t)kWarps * 32 * MaxRecord<N>::value * sizeof(T);
+  auto kern = rbd_kernel<T, N, ORTHO, DYN, CMAT>;
+  cudaError_t e = set_smem(kern, smem);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, a);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+template <typename T, int N>
+int rbd_dispatch(const ChainHost &h, const RbdCall &c) {
+  unsigned want = 0;
+  if (c.out.Tx) want |= kWantTx;
+  if (c.out.T) want |= kWantT;
+  if (c.out.R) want |= kWantR;
+  if (c.out.T_inv) want |= kWantTinv;
+  if (c.out.quat) want |= kWantQuat;
+  if (c.out.J) want |= kWantJ;
+  if (c.out.dJ) want |= kWantdJ | kWantJ;
+  if (c.out.M) want |= kWantM;
+  if (c.out.g) want |= kWantg;
+  if (c.out.C) want |= kWantC;
+  const bool cm = c.out.C != nullptr, dyn = c.out.M != nullptr || c.out.g != nullptr;
+  if (h.ortho) {
+    if (cm) return rbd_go<T, N, true, true, true>(h, c, want);
+    if (dyn) return rbd_go<T, N, true, true, false>(h, c, want);
+    return rbd_go<T, N, true, false, false>(h, c, want);
+  }
+  if (cm) return rbd_go<T, N, false, true, true>(h, c, want);
+  if (dyn) return rbd_go<T, N, false, true, false>(h, c, want);
+  return rbd_go<T, N, false, false, false>(h, c, want);
+}
+
+template <typename T, int N, bool ORTHO, int KD>
+int osc_go(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
+  ChainK<T, N> P;
+  fill_chain<T, N>(h, P);
+  OscK<T, N> O;
+  fill_osc<T, N>(p, c.frame, c.xoff, O);
+  OscArgs<T> a;
+  a.q = static_cast<const T *>(c.q);
+  a.dq = static_cast<const T *>(c.dq);
+  a.target = static_cast<const T *>(c.target);
+  a.tv = static_cast<const T *>(c.tv);
+  a.u = static_cast<T *>(c.u);
+  a.train = static_cast<T *>(c.train);
+  a.B = c.B;
+  a.target_stride = c.target_stride;
+  a.tv_stride = c.tv_stride;
+  const size_t smem = (size_t)kWarps * 32 * N * sizeof(T);
+  osc_kernel<T, N, ORTHO, KD><<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, O, a);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+template <typename T, int N, bool ORTHO, int KD>
+int rollout_go(const ChainHost &h, const abrb_osc_params &p, const RolloutCall &c) {
+  ChainK<T, N> P;
+  fill_chain<T, N>(h, P);
+  OscK<T, N> O;
+  fill_osc<T, N>(p, c.frame, c.xoff, O);
+  RolloutArgs<T> a;
+  a.q = static_cast<T *>(c.q);
+  a.dq = static_cast<T *>(c.dq);
+  a.target = static_cast<const T *>(c.target);
+  a.q_traj = static_cast<T *>(c.q_traj);
+  a.dq_traj = static_cast<T *>(c.dq_traj);
+  a.u_traj = static_cast<T *>(c.u_traj);
+  a.B = c.B;
+  a.target_stride = c.target_stride;
+  a.steps = c.steps;
+  a.dt = T(c.dt);
+  const size_t smem = (size_t)kWarps * 32 * N * sizeof(T);
+  rollout_kernel<T, N, ORTHO, KD><<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, O, a);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+template <typename T, int N, bool ORTHO>
+int null_go(const ChainHost &h, const abrb_null_params &z, const NullCall &c) {
+  ChainK<T, N> P;
+  fill_chain<T, N>(h, P);
+  NullK<T, N> Z;
+  fill_null<T, N>(z, Z);
+  NullArgs<T> a;
+  a.q = static_cast<const T *>(c.q);
+  a.dq = static_cast<const T *>(c.dq);
+  a.u = static_cast<T *>(c.u);
+  a.B = c.B;
+  const size_t smem = (size_t)kWarps * 32 * N * sizeof(T);
+  null_kernel<T, N, ORTHO><<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, Z, a);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+inline bool needs_kd6(const abrb_osc_params &p) { return p.ctrlr_dof[3] || p.ctrlr_dof[4] || p.ctrlr_dof[5]; }
+
+}  // namespace
+
+template <>
+int launch_rbd<ABRB_N>(const ChainHost &h, const RbdCall &c) {
+  return c.f32 ? rbd_dispatch<float, ABRB_N>(h, c) : rbd_dispatch<double, ABRB_N>(h, c);
+}
+
+#define ABRB_OSC_DISPATCH(GO, ...)                                                              \
+  do {                                                                                          \
+    const bool k6 = needs_kd6(p);                                                               \
+    if (c.f32) {                                                                                \
+      if (h.ortho) return k6 ? GO<float, ABRB_N, true, 6>(__VA_ARGS__) : GO<float, ABRB_N, true, 3>(__VA_ARGS__);    \
+      return k6 ? GO<float, ABRB_N, false, 6>(__VA_ARGS__) : GO<float, ABRB_N, false, 3>(__VA_ARGS__);               \
+    }                                                                                           \
+    if (h.ortho) return k6 ? GO<double, ABRB_N, true, 6>(__VA_ARGS__) : GO<double, ABRB_N, true, 3>(__VA_ARGS__);    \
+    return k6 ? GO<double, ABRB_N, false, 6>(__VA_ARGS__) : GO<double, ABRB_N, false, 3>(__VA_ARGS__);               \
+  } while (0)
+
+template <>
+int launch_osc<ABRB_N>(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
+  ABRB_OSC_DISPATCH(osc_go, h, p, c);
+}
+
+template <>
+int launch_rollout<ABRB_N>(const ChainHost &h, const abrb_osc_params &p, const RolloutCall &c) {
+  ABRB_OSC_DISPATCH(rollout_go, h, p, c);
+}
+
+template <>
+int launch_null<ABRB_N>(const ChainHost &h, const abrb_null_params &z, const NullCall &c) {
+  if (c.f32) return h.ortho ? null_go<float, ABRB_N, true>(h, z, c) : null_go<float, ABRB_N, false>(h, z, c);
+  return h.ortho ? null_go<double, ABRB_N, true>(h, z, c) : null_go<double, ABRB_N, false>(h, z, c);
+}
+
+}  // namespace abrb
