@@ -169,6 +169,24 @@ class BaseConfig:
             res = {k: v[0] for k, v in res.items()}
         return res
 
+    def eval_into(self, q, dq, out, name="EE", x=None):
+        """Allocation-free batched evaluation for hot loops: ``q``/``dq`` contiguous CUDA tensors (B, n) of one dtype,
+        ``out`` a dict key -> preallocated contiguous CUDA tensor of the right shape (keys as in ``eval``)."""
+        B = q.shape[0]
+        o = _abi.RbdOut()
+        for k, t in out.items():
+            if k not in _RBD_KEYS or t.dtype != q.dtype or not t.is_contiguous():
+                raise ValueError(f"eval_into: bad output {k}")
+            setattr(o, k, t.data_ptr())
+        xo = None
+        if x is not None:
+            xo = (C.c_double * 3)(*[float(v) for v in x])
+        L = _lib.lib()
+        fn = L.abrb_rbd_eval_f32 if q.dtype == torch.float32 else L.abrb_rbd_eval_f64
+        _lib.check(fn(self._handle, self.frame_id(name), xo, q.data_ptr(), None if dq is None else dq.data_ptr(), B,
+                      C.byref(o), torch.cuda.current_stream(q.device).cuda_stream))
+        return out
+
     def _one(self, key, q, dq=None, name="EE", x=None, ref32=False):
         v = self.eval(q, dq=dq, name=name, x=x, want=(key,))[key]
         if isinstance(v, np.ndarray) and v.ndim == len(self._shapes()[key]):

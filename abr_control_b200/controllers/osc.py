@@ -150,6 +150,33 @@ class OSC(Controller):
         self.training_signal = tr
         return u
 
+    def generate_into(self, q, dq, target, u_out, training_out=None, target_velocity=None, ref_frame="EE",
+                      xyz_offset=None):
+        """Allocation-free batched ``generate`` for hot loops: all arguments are contiguous CUDA tensors of one dtype
+        (``q, dq, u_out, training_out``: (B, n); ``target, target_velocity``: (B, 6) or (6,)); the result is written
+        into ``u_out`` on the current torch stream.  No shape massaging, one ctypes call."""
+        import torch
+
+        rc = self.robot_config
+        B, n = q.shape
+        if n != rc.N_JOINTS or dq.shape != q.shape or u_out.shape != q.shape or not q.is_cuda:
+            raise ValueError("generate_into: q, dq, u_out must be CUDA tensors of shape (B, n_joints)")
+        f32 = q.dtype == torch.float32
+        for t in (dq, target, u_out, training_out, target_velocity):
+            if t is not None and (t.dtype != q.dtype or not t.is_contiguous() or t.device != q.device):
+                raise ValueError("generate_into: tensors must share dtype/device and be contiguous")
+        L = _lib.lib()
+        fn = L.abrb_osc_generate_f32 if f32 else L.abrb_osc_generate_f64
+        xo = None
+        if xyz_offset is not None:
+            xo = (C.c_double * 3)(*[float(v) for v in xyz_offset])
+        _lib.check(fn(self._native(), rc.frame_id(ref_frame), xo, q.data_ptr(), dq.data_ptr(), target.data_ptr(),
+                      6 if target.dim() == 2 else 0, None if target_velocity is None else target_velocity.data_ptr(),
+                      0 if target_velocity is None or target_velocity.dim() == 1 else 6, u_out.data_ptr(),
+                      None if training_out is None else training_out.data_ptr(), B,
+                      torch.cuda.current_stream(q.device).cuda_stream))
+        return u_out
+
     def rollout(self, q, dq, target, steps, dt=1e-3, ref_frame="EE", xyz_offset=None, record=("q", "dq", "u")):
         """Closed-loop rollout on the GPU: ``steps`` iterations of
         ``u = generate(q, dq, target); ddq = M^-1 (u + g - C dq); dq += ddq dt; q += dq dt``

@@ -26,10 +26,12 @@
 #define ABRB_HD __host__ __device__ __forceinline__
 #define ABRB_HD_NOINLINE __host__ __device__ __noinline__
 #define ABRB_UNROLL _Pragma("unroll")
+#define ABRB_NOUNROLL _Pragma("unroll 1")
 #else
 #define ABRB_HD inline
 #define ABRB_HD_NOINLINE __attribute__((noinline))
 #define ABRB_UNROLL
+#define ABRB_NOUNROLL
 #endif
 
 namespace abrb {
@@ -593,56 +595,76 @@ ABRB_HD void bwd_solve(const T (*L)[S_], T *b) {  // L^T x = b
 // works on a private copy so the hot path keeps its registers.
 template <typename T, int S_>
 ABRB_HD_NOINLINE void pinv_apply_sym(const T *Sin, unsigned active, T rcond, const T *y, T *x) {
+  // NOTE: every loop here is kept rolled (ABRB_NOUNROLL): with nvcc 12.9 -O3 for sm_100a the fully unrolled,
+  // register-resident form of these rotations did not converge on the device (tools/dbg/pinv_test.cu, run on a
+  // B200: sum of squares not preserved) while the rolled form matches the host bit for bit.  This is the rare
+  // path, so local-memory arrays are fine.
   T A[S_][S_], V[S_][S_];
-  for (int i = 0; i < S_; ++i)
+  ABRB_NOUNROLL
+  for (int i = 0; i < S_; ++i) {
+    ABRB_NOUNROLL
     for (int j = 0; j < S_; ++j) {
       A[i][j] = Sin[i * S_ + j];
       V[i][j] = i == j ? T(1) : T(0);
     }
-  const T eps = sizeof(T) == 8 ? T(1e-30) : T(1e-18);
-  for (int sweep = 0; sweep < 24; ++sweep) {
+  }
+  const T eps = sizeof(T) == 8 ? T(1e-30) : T(1e-14);
+  ABRB_NOUNROLL
+  for (int sweep = 0; sweep < 30; ++sweep) {
     T off = T(0), diag = T(0);
+    ABRB_NOUNROLL
     for (int i = 0; i < S_; ++i) {
       diag += A[i][i] * A[i][i];
+      ABRB_NOUNROLL
       for (int j = i + 1; j < S_; ++j) off += A[i][j] * A[i][j];
     }
     if (off <= eps * diag) break;
-    for (int p = 0; p < S_ - 1; ++p)
+    ABRB_NOUNROLL
+    for (int p = 0; p < S_ - 1; ++p) {
+      ABRB_NOUNROLL
       for (int q = p + 1; q < S_; ++q) {
         const T apq = A[p][q];
         if (apq == T(0)) continue;
         const T theta = (A[q][q] - A[p][p]) / (T(2) * apq);
         const T t = (theta >= T(0) ? T(1) : T(-1)) / (abs_t(theta) + sqrt_t(theta * theta + T(1)));
         const T c = T(1) / sqrt_t(t * t + T(1)), s = t * c;
+        ABRB_NOUNROLL
         for (int k = 0; k < S_; ++k) {
           const T akp = A[k][p], akq = A[k][q];
           A[k][p] = c * akp - s * akq;
           A[k][q] = s * akp + c * akq;
         }
+        ABRB_NOUNROLL
         for (int k = 0; k < S_; ++k) {
           const T apk = A[p][k], aqk = A[q][k];
           A[p][k] = c * apk - s * aqk;
           A[q][k] = s * apk + c * aqk;
         }
+        ABRB_NOUNROLL
         for (int k = 0; k < S_; ++k) {
           const T vkp = V[k][p], vkq = V[k][q];
           V[k][p] = c * vkp - s * vkq;
           V[k][q] = s * vkp + c * vkq;
         }
       }
+    }
   }
   T lmax = T(0);
+  ABRB_NOUNROLL
   for (int i = 0; i < S_; ++i)
     if ((active >> i) & 1u) lmax = abs_t(A[i][i]) > lmax ? abs_t(A[i][i]) : lmax;
+  ABRB_NOUNROLL
   for (int i = 0; i < S_; ++i) x[i] = T(0);
+  ABRB_NOUNROLL
   for (int e = 0; e < S_; ++e) {
-    // an eigenpair belongs to the active block iff its eigenvector lives there; identity rows have
-    // eigenvalue exactly 1 and never couple to y (y is zero on them)
+    // identity rows (inactive) have eigenvalue exactly 1 and never couple to y (y is zero on them)
     const T lam = A[e][e];
     if (!(abs_t(lam) > rcond * lmax)) continue;
     T proj = T(0);
+    ABRB_NOUNROLL
     for (int k = 0; k < S_; ++k) proj += V[k][e] * y[k];
     proj /= lam;
+    ABRB_NOUNROLL
     for (int k = 0; k < S_; ++k) x[k] += V[k][e] * proj;
   }
 }

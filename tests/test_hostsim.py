@@ -1,0 +1,159 @@
+"""CPU suite: the kernels' per-state arithmetic (abr_control_b200/csrc/*.cuh), instantiated by g++ through
+tests/hostsim (TEST INFRASTRUCTURE, never loaded by the package), against the oracle.
+
+This checks the *formulation* the CUDA path uses (joint-axis operators Omega_k, Cholesky-based task-space solve,
+power-iteration quaternion, Jacobi pinv) on a box without a GPU; the real parity tests (`-m gpu`) run the same code
+as CUDA kernels through the C ABI.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+from abr_control_b200 import _abi
+from oracle import osc_oracle as oo
+from oracle import rbd_oracle as ro
+
+
+def P(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def hs_rbd(hs, arm, q, dq, frame, xoff=None, f32=0, general=0):
+    cd = _abi.chain_desc_from_dict(_abi.load_arm_json(arm))
+    n, B = cd.n_joints, len(q)
+    fid = hs.hs_frame_id(n, frame.encode())
+    shapes = dict(Tx=(3,), T=(4, 4), R=(3, 3), Tinv=(4, 4), quat=(4,), J=(6, n), dJ=(6, n), M=(n, n), g=(n,), C=(n, n))
+    out = {k: np.zeros((B,) + s) for k, s in shapes.items()}
+    xo = None if xoff is None else np.ascontiguousarray(xoff, dtype=np.float64)
+    rc = hs.hs_rbd(C.byref(cd), f32, general, fid, P(xo), P(np.ascontiguousarray(q)), P(np.ascontiguousarray(dq)),
+                   C.c_int64(B), *[P(out[k]) for k in ("Tx", "T", "R", "Tinv", "quat", "J", "dJ", "M", "g", "C")])
+    assert rc == 0
+    return out
+
+
+def hs_osc(hs, cs, q, dq, target, tv, f32=0, general=0):
+    cd = _abi.chain_desc_from_dict(_abi.load_arm_json(cs["arm"]))
+    n, B = cd.n_joints, len(q)
+    nulls = [_abi.null_params(k, n, **kw) for k, kw in cs.get("null", [])]
+    p = _abi.osc_params(n, null=nulls, **cs["osc"])
+    fid = hs.hs_frame_id(n, cs.get("ref_frame", "EE").encode())
+    xo = None if cs.get("xyz_offset") is None else np.array(cs["xyz_offset"], dtype=np.float64)
+    u, tr, acc = np.zeros((B, n)), np.zeros((B, n)), np.zeros((B, n))
+    tvv = np.ascontiguousarray(tv) if cs.get("tv") else None
+    rc = hs.hs_osc(C.byref(cd), C.byref(p), f32, general, fid, P(xo), P(np.ascontiguousarray(q)),
+                   P(np.ascontiguousarray(dq)), P(np.ascontiguousarray(target)), 6, P(tvv), 6, C.c_int64(B), P(u), P(tr),
+                   P(acc))
+    assert rc == 0
+    return u, tr, acc
+
+
+def _err(a, b):
+    return float(np.max(np.abs(a - b)))
+
+
+@pytest.mark.parametrize("arm,general", [("twojoint", 0), ("threejoint", 0), ("ur5", 0), ("ur5", 1), ("jaco2", 0)])
+def test_rbd_math_vs_oracle(hostsim, arm, general):
+    """general=1 forces the non-orthonormal operator path on an orthonormal chain (must agree)."""
+    c = ro.ChainOracle(arm)
+    n = c.n
+    q, dq, _, _ = cases.states(arm, 24)
+    xoff = np.array(cases.XOFF)
+    for fr in cases.frames(n):
+        o = hs_rbd(hostsim, arm, q, dq, fr, general=general)
+        ox = hs_rbd(hostsim, arm, q, dq, fr, xoff, general=general)
+        S = c.walk(q, 1)[fr]
+        assert _err(o["Tx"], c.Tx(fr, q)) < 1e-13
+        assert _err(o["T"], S.T) < 1e-13
+        assert _err(o["R"], c.R(fr, q)) < 1e-13
+        assert _err(o["Tinv"], c.T_inv(fr, q)) < 1e-13
+        assert _err(o["J"], c.J(fr, q)) < 1e-13
+        assert _err(o["dJ"], c.dJ(fr, q, dq)) < 1e-12
+        assert _err(ox["Tx"], c.Tx(fr, q, xoff)) < 1e-13
+        assert _err(ox["J"], c.J(fr, q, xoff)) < 1e-13
+        assert _err(ox["dJ"], c.dJ(fr, q, dq, xoff)) < 1e-12
+        qa, qb = o["quat"], c.quaternion(fr, q)
+        e = np.minimum(np.abs(qa - qb).max(axis=1), np.abs(qa + qb).max(axis=1))
+        assert np.all((np.abs(qa - qb).max(axis=1) < 1e-12) | ((np.abs(qb[:, 0]) < 1e-9) & (e < 1e-12)))
+    o = hs_rbd(hostsim, arm, q, dq, "EE", general=general)
+    assert _err(o["M"], c.M(q)) < 1e-12 * max(1, np.abs(c.M(q)).max())
+    assert _err(o["g"], c.g(q)) < 1e-12 * max(1, np.abs(c.g(q)).max())
+    assert _err(o["C"], c.C(q, dq)) < 1e-12 * max(1, np.abs(c.C(q, dq)).max())
+    # float32 instantiation against the float64 one
+    o32 = hs_rbd(hostsim, arm, q, dq, "EE", f32=1, general=general)
+    for k, tol in (("Tx", 5e-6), ("J", 5e-6), ("M", 5e-5), ("g", 2e-4), ("C", 5e-4), ("dJ", 1e-4)):
+        assert _err(o32[k], o[k]) < tol * max(1, np.abs(o[k]).max()), k
+
+
+@pytest.mark.parametrize("name", list(cases.OSC_CASES))
+def test_osc_math_vs_oracle(hostsim, name):
+    cs = cases.OSC_CASES[name]
+    q, dq, target, tvel = cases.states(cs["arm"], 32)
+    ref, reft = oo.run_case(cs, q, dq, target, tvel, "fp64")
+    u, tr, _ = hs_osc(hostsim, cs, q, dq, target, tvel)
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.max(np.abs(u - ref) / scale) < 1e-9
+    assert np.max(np.abs(tr - reft) / scale) < 1e-9
+    u32, _, _ = hs_osc(hostsim, cs, q, dq, target, tvel, f32=1)
+    assert np.median(np.max(np.abs(u32 - ref) / scale, axis=1)) < 1e-5
+
+
+def test_osc_math_general_path_on_ur5(hostsim):
+    cs = cases.OSC_CASES["ur5_6dof_C_damp"]
+    q, dq, target, tvel = cases.states("ur5", 16)
+    a, _, _ = hs_osc(hostsim, cs, q, dq, target, tvel, general=0)
+    b, _, _ = hs_osc(hostsim, cs, q, dq, target, tvel, general=1)
+    assert np.max(np.abs(a - b)) < 1e-9 * np.abs(a).max()
+
+
+@pytest.mark.parametrize("name", list(cases.NULL_CASES))
+def test_null_math_vs_oracle(hostsim, name):
+    cs = cases.NULL_CASES[name]
+    q, dq, _, _ = cases.states(cs["arm"], 32)
+    cd = _abi.chain_desc_from_dict(_abi.load_arm_json(cs["arm"]))
+    z = _abi.null_params(cs["ctrl"][0], cd.n_joints, **cs["ctrl"][1])
+    u = np.zeros((len(q), cd.n_joints))
+    assert hostsim.hs_null(C.byref(cd), C.byref(z), 0, 0, P(np.ascontiguousarray(q)), P(np.ascontiguousarray(dq)),
+                           C.c_int64(len(q)), P(u)) == 0
+    ref = oo.run_null_case(cs, q, dq)
+    assert _err(u, ref) < 1e-8 * max(1, np.abs(ref).max())
+
+
+def test_singular_states_pinv_branch(hostsim):
+    """rank-deficient J M^-1 J^T -> the reference's pinv(rcond=1e-4) branch (osc.py:143-145), incl. truncation."""
+    for arm, qs in (("twojoint", [[0.3, 0.0], [1.0, np.pi], [2.0, 1e-9]]),
+                    ("threejoint", [[0.5, 0.0, 0.0], [1.0, np.pi, 0.0], [0.2, 1e-7, -1e-7]])):
+        q = np.array(qs)
+        dq = np.full_like(q, 0.3)
+        target = np.tile([0.5, 0.4, 0, 0, 0, 0.0], (len(q), 1))
+        cs = dict(arm=arm, osc=dict(kp=10, ctrlr_dof=[True, True, False, False, False, False]))
+        ref, _ = oo.run_case(cs, q, dq, target)
+        u, _, _ = hs_osc(hostsim, cs, q, dq, target, None)
+        assert np.abs(u - ref).max() < 1e-7 * np.abs(ref).max()
+    # UR5 6-DOF: random states include truncated ones (3.6 % have |det| < 1e-3, some with an eigenvalue below rcond)
+    rng = np.random.default_rng(0)
+    q, dq, target = rng.uniform(0, 2 * np.pi, (64, 6)), rng.uniform(0, 5, (64, 6)), rng.uniform(-1, 1, (64, 6))
+    cs = dict(arm="ur5", osc=dict(kp=50, ctrlr_dof=[True] * 6))
+    ref, _ = oo.run_case(cs, q, dq, target)
+    u, _, _ = hs_osc(hostsim, cs, q, dq, target, None)
+    assert np.max(np.abs(u - ref) / np.abs(ref).max(axis=1, keepdims=True)) < 1e-9
+
+
+def test_plant_acceleration(hostsim):
+    """ddq returned by the rollout variant solves M ddq = u + g - C dq."""
+    cs = cases.OSC_CASES["ur5_xyz"]
+    q, dq, target, _ = cases.states("ur5", 16)
+    u, _, acc = hs_osc(hostsim, cs, q, dq, target, None)
+    c = ro.ChainOracle("ur5")
+    rhs = u + c.g(q) - np.einsum("bij,bj->bi", c.C(q, dq), dq)
+    ref = np.linalg.solve(c.M(q), rhs[..., None])[..., 0]
+    assert np.max(np.abs(acc - ref)) < 1e-8 * np.abs(ref).max()
+
+
+def test_frame_names(hostsim):
+    assert hostsim.hs_frame_id(6, b"link0") == 0 and hostsim.hs_frame_id(6, b"link6") == 6
+    assert hostsim.hs_frame_id(6, b"joint0") == 7 and hostsim.hs_frame_id(6, b"joint5") == 12
+    assert hostsim.hs_frame_id(6, b"EE") == 13
+    for bad in (b"link7", b"joint6", b"ee", b"link", b"hand", b"link-1", b"joint1x"):
+        assert hostsim.hs_frame_id(6, bad) == _abi.EFRAME
