@@ -74,16 +74,51 @@ ABRB_HD int frame_dep(int frame) {  // number of joints the frame moves with == 
   return frame <= N ? frame : (frame <= 2 * N ? frame - (N + 1) : N);
 }
 
-template <typename T, int N, bool ORTHO>
+// Per-state kinematic scratch: joint origins t_k, joint axes z_k, link COMs and (non-orthonormal chains only)
+// columns 0,1 of R_k and rows 0,1 of R_k^-1.  The values live in a "slot store": registers (RegStore) or a strided
+// shared-memory column per thread (StridedStore, slot-major so consecutive lanes hit consecutive words), which is
+// what the fp64 kernels use to stay under the register limit without spilling to local memory.
+template <typename T, int COUNT>
+struct RegStore {
+  T v[COUNT];
+  ABRB_HD T ld(int i) const { return v[i]; }
+  ABRB_HD void st(int i, T x) { v[i] = x; }
+};
+template <typename T, int COUNT>
+struct StridedStore {
+  T *base;
+  int stride;
+  ABRB_HD T ld(int i) const { return base[i * stride]; }
+  ABRB_HD void st(int i, T x) { base[i * stride] = x; }
+};
+
+template <int N, bool ORTHO>
+struct KinSlots {
+  static constexpr int kT = 0, kZ = 3 * N, kPl = 6 * N, kR0 = 9 * N, kR1 = 12 * N, kS0 = 15 * N, kS1 = 18 * N;
+  static constexpr int kCount = ORTHO ? 9 * N : 21 * N;
+};
+
+template <typename T, int N, bool ORTHO_, template <typename, int> class Store = RegStore>
 struct Kin {
-  T t[N][3];                   // joint origins
-  T z[N][3];                   // joint axes (third column of R_k)
-  T r0[ORTHO ? 1 : N][3];      // non-orthonormal chains only: columns 0,1 of R_k and rows 0,1 of R_k^-1
-  T r1[ORTHO ? 1 : N][3];
-  T s0[ORTHO ? 1 : N][3];
-  T s1[ORTHO ? 1 : N][3];
-  T pl[N][3];                  // COM of link i+1
-  T F[12];                     // the requested frame
+  typedef T Scalar;
+  static constexpr int kN = N;
+  static constexpr bool kOrtho = ORTHO_;
+  typedef KinSlots<N, ORTHO_> S;
+  Store<T, S::kCount> s;
+  T F[12];  // the requested frame
+  ABRB_HD void ld3(int slot, T *o) const {
+    o[0] = s.ld(slot);
+    o[1] = s.ld(slot + 1);
+    o[2] = s.ld(slot + 2);
+  }
+  ABRB_HD void st3(int slot, const T *v) {
+    s.st(slot, v[0]);
+    s.st(slot + 1, v[1]);
+    s.st(slot + 2, v[2]);
+  }
+  ABRB_HD void t(int k, T *o) const { ld3(S::kT + 3 * k, o); }
+  ABRB_HD void z(int k, T *o) const { ld3(S::kZ + 3 * k, o); }
+  ABRB_HD void pl(int l, T *o) const { ld3(S::kPl + 3 * l, o); }
 };
 
 template <typename T>
@@ -110,14 +145,22 @@ ABRB_HD void aff_mul(const T *X, const T *C, T *o) {
 }
 
 // Omega_k v
-template <typename T, int N, bool ORTHO>
-ABRB_HD void omega_apply(const Kin<T, N, ORTHO> &K, int k, const T *v, T *o) {
-  if (ORTHO) {
-    cross3(K.z[k], v, o);
+template <class K>
+ABRB_HD void omega_apply(const K &kin, int k, const typename K::Scalar *v, typename K::Scalar *o) {
+  typedef typename K::Scalar T;
+  if (K::kOrtho) {
+    T zk[3];
+    kin.z(k, zk);
+    cross3(zk, v, o);
   } else {
-    const T a = dot3(K.s0[k], v), b = dot3(K.s1[k], v);
+    T r0[3], r1[3], s0[3], s1[3];
+    kin.ld3(K::S::kR0 + 3 * k, r0);
+    kin.ld3(K::S::kR1 + 3 * k, r1);
+    kin.ld3(K::S::kS0 + 3 * k, s0);
+    kin.ld3(K::S::kS1 + 3 * k, s1);
+    const T a = dot3(s0, v), b = dot3(s1, v);
     ABRB_UNROLL
-    for (int c = 0; c < 3; ++c) o[c] = K.r1[k][c] * a - K.r0[k][c] * b;
+    for (int c = 0; c < 3; ++c) o[c] = r1[c] * a - r0[c] * b;
   }
 }
 
@@ -129,17 +172,23 @@ struct Spin {
     ABRB_UNROLL
     for (int i = 0; i < (ORTHO ? 3 : 9); ++i) w[i] = T(0);
   }
-  template <int N>
-  ABRB_HD void add(const Kin<T, N, ORTHO> &K, int k, T dqk) {
+  template <class K>
+  ABRB_HD void add(const K &kin, int k, T dqk) {
     if (ORTHO) {
+      T zk[3];
+      kin.z(k, zk);
       ABRB_UNROLL
-      for (int c = 0; c < 3; ++c) w[c] += dqk * K.z[k][c];
+      for (int c = 0; c < 3; ++c) w[c] += dqk * zk[c];
     } else {
+      T r0[3], r1[3], s0[3], s1[3];
+      kin.ld3(K::S::kR0 + 3 * k, r0);
+      kin.ld3(K::S::kR1 + 3 * k, r1);
+      kin.ld3(K::S::kS0 + 3 * k, s0);
+      kin.ld3(K::S::kS1 + 3 * k, s1);
       ABRB_UNROLL
       for (int r = 0; r < 3; ++r)
         ABRB_UNROLL
-      for (int c = 0; c < 3; ++c)
-        w[r * 3 + c] += dqk * (K.r1[k][r] * K.s0[k][c] - K.r0[k][r] * K.s1[k][c]);
+      for (int c = 0; c < 3; ++c) w[r * 3 + c] += dqk * (r1[r] * s0[c] - r0[r] * s1[c]);
     }
   }
   ABRB_HD void apply(const T *v, T *o) const {
@@ -155,24 +204,24 @@ struct Spin {
 // ------------------------------------------------------------------------------------------------
 // Forward walk along the chain: fills joint origins/axes, link COMs and the
 // full transform of `frame`.
-template <typename T, int N, bool ORTHO>
-ABRB_HD void walk(const ChainK<T, N> &P, const T *q, int frame, Kin<T, N, ORTHO> &K,
+template <typename T, int N, class K>
+ABRB_HD void walk(const ChainK<T, N> &P, const T *q, int frame, K &kin,
                   T (*link_frames)[12] = nullptr) {  // optional: all link(i+1) frames (rare paths only)
   T X[12];
   ABRB_UNROLL
   for (int i = 0; i < 12; ++i) X[i] = P.G0[i];
   if (frame == 0) {
     ABRB_UNROLL
-    for (int i = 0; i < 12; ++i) K.F[i] = P.L0[i];
+    for (int i = 0; i < 12; ++i) kin.F[i] = P.L0[i];
   }
   ABRB_UNROLL
   for (int i = 0; i < N; ++i) {
-    ABRB_UNROLL
-    for (int r = 0; r < 3; ++r) {
-      K.t[i][r] = X[r * 4 + 3];
-      K.z[i][r] = X[r * 4 + 2];
+    {
+      const T tk[3] = {X[3], X[7], X[11]}, zk[3] = {X[2], X[6], X[10]};
+      kin.st3(K::S::kT + 3 * i, tk);
+      kin.st3(K::S::kZ + 3 * i, zk);
     }
-    if (!ORTHO) {
+    if (!K::kOrtho) {
       T c0[3], c1[3], c2[3], c12[3], c20[3];
       ABRB_UNROLL
       for (int r = 0; r < 3; ++r) {
@@ -185,15 +234,17 @@ ABRB_HD void walk(const ChainK<T, N> &P, const T *q, int frame, Kin<T, N, ORTHO>
       const T inv = T(1) / dot3(c0, c12);
       ABRB_UNROLL
       for (int r = 0; r < 3; ++r) {
-        K.r0[ORTHO ? 0 : i][r] = c0[r];
-        K.r1[ORTHO ? 0 : i][r] = c1[r];
-        K.s0[ORTHO ? 0 : i][r] = c12[r] * inv;
-        K.s1[ORTHO ? 0 : i][r] = c20[r] * inv;
+        c12[r] *= inv;
+        c20[r] *= inv;
       }
+      kin.st3(K::S::kR0 + 3 * i, c0);
+      kin.st3(K::S::kR1 + 3 * i, c1);
+      kin.st3(K::S::kS0 + 3 * i, c12);
+      kin.st3(K::S::kS1 + 3 * i, c20);
     }
     if (frame == N + 1 + i) {
       ABRB_UNROLL
-      for (int j = 0; j < 12; ++j) K.F[j] = X[j];
+      for (int j = 0; j < 12; ++j) kin.F[j] = X[j];
     }
     T s, c;
     sincos_t(q[i], &s, &c);
@@ -203,10 +254,14 @@ ABRB_HD void walk(const ChainK<T, N> &P, const T *q, int frame, Kin<T, N, ORTHO>
       X[r * 4 + 0] = c * a + s * b;
       X[r * 4 + 1] = c * b - s * a;
     }
-    ABRB_UNROLL
-    for (int r = 0; r < 3; ++r)
-      K.pl[i][r] = X[r * 4 + 0] * P.Bf[i][3] + X[r * 4 + 1] * P.Bf[i][7] + X[r * 4 + 2] * P.Bf[i][11] + X[r * 4 + 3];
-    if (frame == i + 1) aff_mul(X, P.Bf[i], K.F);
+    {
+      T p[3];
+      ABRB_UNROLL
+      for (int r = 0; r < 3; ++r)
+        p[r] = X[r * 4 + 0] * P.Bf[i][3] + X[r * 4 + 1] * P.Bf[i][7] + X[r * 4 + 2] * P.Bf[i][11] + X[r * 4 + 3];
+      kin.st3(K::S::kPl + 3 * i, p);
+    }
+    if (frame == i + 1) aff_mul(X, P.Bf[i], kin.F);
     if (link_frames != nullptr) aff_mul(X, P.Bf[i], link_frames[i]);
     T Y[12];
     aff_mul(X, P.BA[i], Y);
@@ -215,7 +270,7 @@ ABRB_HD void walk(const ChainK<T, N> &P, const T *q, int frame, Kin<T, N, ORTHO>
   }
   if (frame == 2 * N + 1) {
     ABRB_UNROLL
-    for (int j = 0; j < 12; ++j) K.F[j] = X[j];
+    for (int j = 0; j < 12; ++j) kin.F[j] = X[j];
   }
 }
 
@@ -228,26 +283,29 @@ ABRB_HD void frame_point(const T *F, const T *x, T *p) {
 
 // J[6][N] of world point p attached to a frame that moves with the first `dep` joints
 // (reference J, base_config.py:522-592: rows 0-2 dTx/dq_k, rows 3-5 J_orientation[k] for k < end_point)
-template <typename T, int N, bool ORTHO>
-ABRB_HD void jacobian(const Kin<T, N, ORTHO> &K, const T *p, int dep, T (*J)[N]) {
+template <typename T, int N, class K>
+ABRB_HD void jacobian(const K &kin, const T *p, int dep, T (*J)[N]) {
   ABRB_UNROLL
   for (int k = 0; k < N; ++k) {
-    T d[3], v[3];
+    T d[3], v[3], tk[3], zk[3];
+    kin.t(k, tk);
+    kin.z(k, zk);
     ABRB_UNROLL
-    for (int c = 0; c < 3; ++c) d[c] = p[c] - K.t[k][c];
-    omega_apply(K, k, d, v);
+    for (int c = 0; c < 3; ++c) d[c] = p[c] - tk[c];
+    omega_apply(kin, k, d, v);
     const bool on = k < dep;
     ABRB_UNROLL
     for (int c = 0; c < 3; ++c) {
       J[c][k] = on ? v[c] : T(0);
-      J[3 + c][k] = on ? K.z[k][c] : T(0);
+      J[3 + c][k] = on ? zk[c] : T(0);
     }
   }
 }
 
 // dJ/dt = sum_i dJ/dq_i dq_i (reference dJ, base_config.py:470-520) given J's position rows
-template <typename T, int N, bool ORTHO>
-ABRB_HD void jacobian_dot(const Kin<T, N, ORTHO> &K, const T (*J)[N], const T *dq, int dep, T (*dJ)[N]) {
+template <typename T, int N, class K_>
+ABRB_HD void jacobian_dot(const K_ &K, const T (*J)[N], const T *dq, int dep, T (*dJ)[N]) {
+  constexpr bool ORTHO = K_::kOrtho;
   // suffix sums s_k = sum_{k<=i<dep} dq_i v_i
   T suf[N][3];
   T run[3] = {T(0), T(0), T(0)};
@@ -265,17 +323,18 @@ ABRB_HD void jacobian_dot(const Kin<T, N, ORTHO> &K, const T (*J)[N], const T *d
   ABRB_UNROLL
   for (int k = 0; k < N; ++k) {
     T v[3] = {J[0][k], J[1][k], J[2][k]};
-    T a[3], b[3], zd[3];
+    T a[3], b[3], zd[3], zk[3];
+    K.z(k, zk);
     W.apply(v, a);
     omega_apply(K, k, suf[k], b);
-    W.apply(K.z[k], zd);
+    W.apply(zk, zd);
     const bool on = k < dep;
     ABRB_UNROLL
     for (int c = 0; c < 3; ++c) {
       dJ[c][k] = on ? a[c] + b[c] : T(0);
       dJ[3 + c][k] = on ? zd[c] : T(0);
     }
-    W.template add<N>(K, k, dq[k]);
+    W.add(K, k, dq[k]);
   }
 }
 
@@ -287,9 +346,9 @@ ABRB_HD void jacobian_dot(const Kin<T, N, ORTHO> &K, const T (*J)[N], const T *d
 //   C[k][j] = sum_i 1/2 (d_i M_kj + d_j M_ki - d_k M_ij) dq_i     base_config.py:706-714
 // Translational part of C:  sum_l (W_l v_lk) . (d/dt v_lj)   — the symmetric second-derivative terms of
 // the Christoffel sum cancel exactly; rotational part: explicit Christoffel sum.
-template <typename T, int N, bool ORTHO, bool CMAT, bool CDQ>
-ABRB_HD void dynamics(const ChainK<T, N> &P, const Kin<T, N, ORTHO> &K, const T *dq, T (*M)[N], T *g,
-                      T (*C)[N], T *cdq) {
+template <typename T, int N, bool CMAT, bool CDQ, class K_>
+ABRB_HD void dynamics(const ChainK<T, N> &P, const K_ &K, const T *dq, T (*M)[N], T *g, T (*C)[N], T *cdq) {
+  constexpr bool ORTHO = K_::kOrtho;
   ABRB_UNROLL
   for (int a = 0; a < N; ++a) {
     g[a] = T(0);
@@ -303,13 +362,15 @@ ABRB_HD void dynamics(const ChainK<T, N> &P, const Kin<T, N, ORTHO> &K, const T 
   // ---- translational part, link by link (link l = 1..N has COM K.pl[l-1] and moves with joints < l)
   ABRB_UNROLL
   for (int l = 1; l <= N; ++l) {
-    T v[N][3], wv[N][3];
+    T v[N][3], wv[N][3], pl[3];
+    K.pl(l - 1, pl);
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) {
       if (k < l) {
-        T d[3];
+        T d[3], tk[3];
+        K.t(k, tk);
         ABRB_UNROLL
-        for (int c = 0; c < 3; ++c) d[c] = K.pl[l - 1][c] - K.t[k][c];
+        for (int c = 0; c < 3; ++c) d[c] = pl[c] - tk[c];
         omega_apply(K, k, d, v[k]);
         ABRB_UNROLL
         for (int c = 0; c < 3; ++c) wv[k][c] = P.Wp[l][c] * v[k][c];
@@ -354,7 +415,7 @@ ABRB_HD void dynamics(const ChainK<T, N> &P, const Kin<T, N, ORTHO> &K, const T 
             ABRB_UNROLL
             for (int c = 0; c < 3; ++c) acc[c] += dq[j] * aj[c];
           }
-          W.template add<N>(K, j, dq[j]);
+          W.add(K, j, dq[j]);
         }
       }
       if (CDQ) {
@@ -365,13 +426,15 @@ ABRB_HD void dynamics(const ChainK<T, N> &P, const Kin<T, N, ORTHO> &K, const T 
     }
   }
   // ---- rotational part: M_ab += sum_c z_a[c] Wos[max(a,b)][c] z_b[c]
+  T Z[N][3];  // joint axes, fetched once for the rotational terms
+  ABRB_UNROLL
+  for (int a = 0; a < N; ++a) K.z(a, Z[a]);
   ABRB_UNROLL
   for (int a = 0; a < N; ++a) {
-    g[a] += dot3(K.z[a], P.gos[a]);
+    g[a] += dot3(Z[a], P.gos[a]);
     ABRB_UNROLL
     for (int b = a; b < N; ++b)
-      M[a][b] += K.z[a][0] * P.Wos[b][0] * K.z[b][0] + K.z[a][1] * P.Wos[b][1] * K.z[b][1] +
-                 K.z[a][2] * P.Wos[b][2] * K.z[b][2];
+      M[a][b] += Z[a][0] * P.Wos[b][0] * Z[b][0] + Z[a][1] * P.Wos[b][1] * Z[b][1] + Z[a][2] * P.Wos[b][2] * Z[b][2];
   }
   if (CMAT) {
     // dz[i][a] = Omega_i z_a (i<a);  dMo(i;a,b) = sum_c Wos[max(a,b)][c] (dz[i][a][c] z_b[c] + z_a[c] dz[i][b][c])
@@ -381,7 +444,7 @@ ABRB_HD void dynamics(const ChainK<T, N> &P, const Kin<T, N, ORTHO> &K, const T 
       ABRB_UNROLL
     for (int a = 0; a < N; ++a) {
       if (i < a) {
-        omega_apply(K, i, K.z[a], dz[i][a]);
+        omega_apply(K, i, Z[a], dz[i][a]);
       } else {
         dz[i][a][0] = dz[i][a][1] = dz[i][a][2] = T(0);
       }
@@ -390,7 +453,7 @@ ABRB_HD void dynamics(const ChainK<T, N> &P, const Kin<T, N, ORTHO> &K, const T 
       const int m = a > b ? a : b;
       T s = T(0);
       ABRB_UNROLL
-      for (int c = 0; c < 3; ++c) s += P.Wos[m][c] * (dz[i][a][c] * K.z[b][c] + K.z[a][c] * dz[i][b][c]);
+      for (int c = 0; c < 3; ++c) s += P.Wos[m][c] * (dz[i][a][c] * Z[b][c] + Z[a][c] * dz[i][b][c]);
       return s;
     };
     ABRB_UNROLL
@@ -410,8 +473,8 @@ ABRB_HD void dynamics(const ChainK<T, N> &P, const Kin<T, N, ORTHO> &K, const T 
     W.clear();
     ABRB_UNROLL
     for (int a = 0; a < N; ++a) {
-      W.apply(K.z[a], zd[a]);
-      W.template add<N>(K, a, dq[a]);
+      W.apply(Z[a], zd[a]);
+      W.add(K, a, dq[a]);
     }
     ABRB_UNROLL
     for (int i = 0; i < N; ++i) {
@@ -420,7 +483,7 @@ ABRB_HD void dynamics(const ChainK<T, N> &P, const Kin<T, N, ORTHO> &K, const T 
       for (int j = 0; j < N; ++j) {
         const int m = i > j ? i : j;
         ABRB_UNROLL
-        for (int c = 0; c < 3; ++c) h[i][c] += dq[j] * P.Wos[m][c] * K.z[j][c];
+        for (int c = 0; c < 3; ++c) h[i][c] += dq[j] * P.Wos[m][c] * Z[j][c];
       }
     }
     ABRB_UNROLL
@@ -431,14 +494,14 @@ ABRB_HD void dynamics(const ChainK<T, N> &P, const Kin<T, N, ORTHO> &K, const T 
         const int m = k > j ? k : j;
         T e = T(0);
         ABRB_UNROLL
-        for (int c = 0; c < 3; ++c) e += P.Wos[m][c] * (zd[k][c] * K.z[j][c] + K.z[k][c] * zd[j][c]);
+        for (int c = 0; c < 3; ++c) e += P.Wos[m][c] * (zd[k][c] * Z[j][c] + Z[k][c] * zd[j][c]);
         s += dq[j] * e;
       }
       ABRB_UNROLL
       for (int i = 0; i < N; ++i) {
         if (i > k) {
           T oz[3];
-          omega_apply(K, k, K.z[i], oz);
+          omega_apply(K, k, Z[i], oz);
           s -= dq[i] * dot3(oz, h[i]);
         }
       }
@@ -540,7 +603,7 @@ ABRB_HD void quat_mul(const T *q1, const T *q0, T *o) {  // utils/transformation
 // In-place lower Cholesky of the symmetric S (reads the upper OR lower triangle consistently: we use
 // S[i][j], j<=i).  Returns false if a pivot is not positive.
 template <typename T, int S_>
-ABRB_HD bool chol(T (*A)[S_]) {
+ABRB_HD bool chol(T (*A)[S_], T *invd) {  // invd[j] = 1 / L[j][j] (the solves multiply instead of dividing)
   bool ok = true;
   ABRB_UNROLL
   for (int j = 0; j < S_; ++j) {
@@ -552,6 +615,7 @@ ABRB_HD bool chol(T (*A)[S_]) {
     const T ljj = sqrt_t(d > T(0) ? d : T(1));
     A[j][j] = ljj;
     const T inv = T(1) / ljj;
+    invd[j] = inv;
     ABRB_UNROLL
     for (int i = 0; i < S_; ++i) {
       if (i > j) {
@@ -566,25 +630,25 @@ ABRB_HD bool chol(T (*A)[S_]) {
   return ok;
 }
 template <typename T, int S_>
-ABRB_HD void fwd_solve(const T (*L)[S_], T *b) {  // L y = b
+ABRB_HD void fwd_solve(const T (*L)[S_], const T *invd, T *b) {  // L y = b
   ABRB_UNROLL
   for (int i = 0; i < S_; ++i) {
     T s = b[i];
     ABRB_UNROLL
     for (int k = 0; k < S_; ++k)
       if (k < i) s -= L[i][k] * b[k];
-    b[i] = s / L[i][i];
+    b[i] = s * invd[i];
   }
 }
 template <typename T, int S_>
-ABRB_HD void bwd_solve(const T (*L)[S_], T *b) {  // L^T x = b
+ABRB_HD void bwd_solve(const T (*L)[S_], const T *invd, T *b) {  // L^T x = b
   ABRB_UNROLL
   for (int i = S_ - 1; i >= 0; --i) {
     T s = b[i];
     ABRB_UNROLL
     for (int k = 0; k < S_; ++k)
       if (k > i) s -= L[k][i] * b[k];
-    b[i] = s / L[i][i];
+    b[i] = s * invd[i];
   }
 }
 

@@ -38,19 +38,19 @@ struct OscK {
 template <typename T, int N, bool ORTHO>
 ABRB_HD_NOINLINE void avoid_generate(const ChainK<T, N> &P, const NullK<T, N> &A, const T *q, const T *Lm,
                                      T *u_out) {
-  Kin<T, N, ORTHO> K;
+  Kin<T, N, ORTHO> K;  // private register/local copy: this path is rare
   T LFs[N][12];
-  walk<T, N, ORTHO>(P, q, 2 * N + 1, K, LFs);  // K.F = EE frame, LFs[i] = link(i+1) frame
+  walk<T, N>(P, q, 2 * N + 1, K, LFs);  // K.F = EE frame, LFs[i] = link(i+1) frame
   T up[N];
   for (int k = 0; k < N; ++k) up[k] = T(0);
   const T thr = A.threshold;
   for (int seg = 0; seg < N; ++seg) {
     const T *LF = LFs[seg];
     T p1[3], p2[3];
-    for (int r = 0; r < 3; ++r) {
-      p1[r] = K.t[seg][r];
-      p2[r] = seg == N - 1 ? K.F[r * 4 + 3] : K.t[seg + 1 < N ? seg + 1 : N - 1][r];
-    }
+    K.t(seg, p1);
+    K.t(seg + 1 < N ? seg + 1 : N - 1, p2);
+    if (seg == N - 1)
+      for (int r = 0; r < 3; ++r) p2[r] = K.F[r * 4 + 3];
     for (int ob = 0; ob < A.n_obs; ++ob) {
       const T *O = A.obs[ob];
       T line[3], obl[3];
@@ -78,8 +78,9 @@ ABRB_HD_NOINLINE void avoid_generate(const ChainK<T, N> &P, const NullK<T, N> &A
       // Jp (3 x N) of that point, W = L^-1 Jp^T (N x 3)
       T Jp[3][N], Wc[3][N];
       for (int k = 0; k < N; ++k) {
-        T dd[3] = {pw[0] - K.t[k][0], pw[1] - K.t[k][1], pw[2] - K.t[k][2]};
-        T v[3];
+        T tk[3], v[3];
+        K.t(k, tk);
+        T dd[3] = {pw[0] - tk[0], pw[1] - tk[1], pw[2] - tk[2]};
         omega_apply(K, k, dd, v);
         for (int r = 0; r < 3; ++r) Jp[r][k] = k < seg + 1 ? v[r] : T(0);
       }
@@ -122,11 +123,15 @@ ABRB_HD T wrap_pm_pi(T d) {
 
 // One OSC evaluation.  KD = 3: only (a subset of) x,y,z controlled; KD = 6: any mask.
 // PLANT: also return ddq = M^-1 (u + g - C dq) for the rollout kernel.
-template <typename T, int N, bool ORTHO, int KD, bool PLANT>
-ABRB_HD void osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, const T *dq, const T *target,
-                       const T *tv, T *u, T *train, T *ddq) {
-  Kin<T, N, ORTHO> K;
-  walk<T, N, ORTHO>(P, q, O.frame, K);
+// defer_slow: if the state needs the eigen-decomposition (truncating pinv) path, return true WITHOUT computing u;
+// the kernel re-runs such states densely packed in a second pass (they are a few % of random states but would
+// otherwise drag most warps through the divergent slow path).  Returns false when u has been produced.
+// `K`: caller-provided kinematic scratch (registers or shared memory).
+template <typename T, int N, int KD, bool PLANT, class K_>
+ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, const T *dq, const T *target,
+                       const T *tv, T *u, T *train, T *ddq, K_ &K, bool defer_slow = false) {
+  constexpr bool ORTHO = K_::kOrtho;
+  walk<T, N>(P, q, O.frame, K);
   const int dep = frame_dep<N>(O.frame);
   T pF[3];
   frame_point(K.F, O.xoff, pF);
@@ -134,9 +139,9 @@ ABRB_HD void osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
   // ---- joint-space dynamics
   T M[N][N], g[N], cdq[N];
   if (PLANT || O.use_C)
-    dynamics<T, N, ORTHO, false, true>(P, K, dq, M, g, nullptr, cdq);
+    dynamics<T, N, false, true>(P, K, dq, M, g, nullptr, cdq);
   else
-    dynamics<T, N, ORTHO, false, false>(P, K, dq, M, g, nullptr, nullptr);
+    dynamics<T, N, false, false>(P, K, dq, M, g, nullptr, nullptr);
   ABRB_UNROLL
   for (int a = 0; a < N; ++a)
     ABRB_UNROLL
@@ -182,7 +187,7 @@ ABRB_HD void osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
   T xdot[KD];
   {
     T J[6][N];
-    jacobian<T, N, ORTHO>(K, pF, dep, J);
+    jacobian<T, N>(K, pF, dep, J);
     ABRB_UNROLL
     for (int r = 0; r < KD; ++r) {
       const bool on = (O.dof_mask >> r) & 1u;
@@ -268,9 +273,10 @@ ABRB_HD void osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
   for (int r = 0; r < KD; ++r) y[r] = ((O.dof_mask >> r) & 1u) ? err[r] : T(0);
 
   // ---- M = L L^T ;  A <- rows of (L^-1 J^T)^T ;  S = J M^-1 J^T = A A^T   (osc.py:136-137)
-  chol<T, N>(M);
+  T Mi[N];
+  chol<T, N>(M, Mi);
   ABRB_UNROLL
-  for (int r = 0; r < KD; ++r) fwd_solve<T, N>(M, A[r]);
+  for (int r = 0; r < KD; ++r) fwd_solve<T, N>(M, Mi, A[r]);
   T S[KD][KD];
   ABRB_UNROLL
   for (int a = 0; a < KD; ++a)
@@ -291,7 +297,8 @@ ABRB_HD void osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
   for (int a = 0; a < KD; ++a)
     ABRB_UNROLL
   for (int b = 0; b < KD; ++b) Sc[a][b] = S[a][b];
-  const bool pd = chol<T, KD>(Sc);
+  T Si[KD];
+  const bool pd = chol<T, KD>(Sc, Si);
   T det = T(1);
   ABRB_UNROLL
   for (int a = 0; a < KD; ++a) det *= Sc[a][a] * Sc[a][a];
@@ -308,18 +315,19 @@ ABRB_HD void osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
         T e[KD];
         ABRB_UNROLL
         for (int b = 0; b < KD; ++b) e[b] = b == a ? T(1) : T(0);
-        fwd_solve<T, KD>(Sc, e);
-        bwd_solve<T, KD>(Sc, e);
+        fwd_solve<T, KD>(Sc, Si, e);
+        bwd_solve<T, KD>(Sc, Si, e);
         ABRB_UNROLL
         for (int b = 0; b < KD; ++b) fro += e[b] * e[b];
       }
     }
     fast = rcond * tr * sqrt_t(fro) < T(1);
   }
+  if (!fast && defer_slow) return true;
   auto mx_apply = [&](T *v) {  // v <- Mx v
     if (fast) {
-      fwd_solve<T, KD>(Sc, v);
-      bwd_solve<T, KD>(Sc, v);
+      fwd_solve<T, KD>(Sc, Si, v);
+      bwd_solve<T, KD>(Sc, Si, v);
     } else {
       T Sf[KD * KD], yi[KD], xo[KD];
       for (int a = 0; a < KD; ++a) {
@@ -385,7 +393,7 @@ ABRB_HD void osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
     T w[N], z[KD], jt[N];
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) w[k] = un[k];
-    fwd_solve<T, N>(M, w);  // L^-1 u_null
+    fwd_solve<T, N>(M, Mi, w);  // L^-1 u_null
     ABRB_UNROLL
     for (int r = 0; r < KD; ++r) {
       T s = T(0);
@@ -402,27 +410,29 @@ ABRB_HD void osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
     T rhs[N];
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) rhs[k] = u[k] + g[k] - cdq[k];
-    fwd_solve<T, N>(M, rhs);
-    bwd_solve<T, N>(M, rhs);
+    fwd_solve<T, N>(M, Mi, rhs);
+    bwd_solve<T, N>(M, Mi, rhs);
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) ddq[k] = rhs[k];
   }
+  return false;
 }
 
 // Standalone secondary controller (`Damping/RestingConfig/AvoidObstacles.generate`)
-template <typename T, int N, bool ORTHO>
-ABRB_HD void null_state(const ChainK<T, N> &P, const NullK<T, N> &Z, const T *q, const T *dq, T *u) {
-  Kin<T, N, ORTHO> K;
-  walk<T, N, ORTHO>(P, q, 0, K);
+template <typename T, int N, class K_>
+ABRB_HD void null_state(const ChainK<T, N> &P, const NullK<T, N> &Z, const T *q, const T *dq, T *u, K_ &K) {
+  constexpr bool ORTHO = K_::kOrtho;
+  walk<T, N>(P, q, 0, K);
   T M[N][N], g[N];
-  dynamics<T, N, ORTHO, false, false>(P, K, dq, M, g, nullptr, nullptr);
+  dynamics<T, N, false, false>(P, K, dq, M, g, nullptr, nullptr);
   ABRB_UNROLL
   for (int a = 0; a < N; ++a)
     ABRB_UNROLL
   for (int b = 0; b < N; ++b)
     if (b < a) M[a][b] = M[b][a];
   if (Z.kind == kNullAvoid) {
-    chol<T, N>(M);
+    T Mi[N];
+    chol<T, N>(M, Mi);
     T Lf[N * N];
     for (int a = 0; a < N; ++a)
       for (int b = 0; b < N; ++b) Lf[a * N + b] = M[a][b];

@@ -33,11 +33,11 @@ struct RbdOut {
 };
 
 // DYN: M and/or g requested; CMAT: C requested (implies the dynamics pass).  `want` is uniform over the launch.
-template <typename T, int N, bool ORTHO, bool DYN, bool CMAT>
+// `K` is the caller-provided kinematic scratch (register- or shared-memory-backed, see Kin in abrb_math.cuh).
+template <typename T, int N, bool DYN, bool CMAT, class K_>
 ABRB_HD void rbd_state(const ChainK<T, N> &P, const T *q, const T *dq, int frame, const T *xoff, unsigned want,
-                       RbdOut<T, N> &o) {
-  Kin<T, N, ORTHO> K;
-  walk<T, N, ORTHO>(P, q, frame, K);
+                       RbdOut<T, N> &o, K_ &K) {
+  walk<T, N>(P, q, frame, K);
   const int dep = frame_dep<N>(frame);
   T pF[3];
   frame_point(K.F, xoff, pF);
@@ -80,11 +80,11 @@ ABRB_HD void rbd_state(const ChainK<T, N> &P, const T *q, const T *dq, int frame
     quat_from_R(R, o.quat);
   }
   if (want & (kWantJ | kWantdJ)) {
-    jacobian<T, N, ORTHO>(K, pF, dep, o.J);
-    if (want & kWantdJ) jacobian_dot<T, N, ORTHO>(K, o.J, dq, dep, o.dJ);
+    jacobian<T, N>(K, pF, dep, o.J);
+    if (want & kWantdJ) jacobian_dot<T, N>(K, o.J, dq, dep, o.dJ);
   }
   if (DYN || CMAT) {
-    dynamics<T, N, ORTHO, CMAT, false>(P, K, dq, o.M, o.g, o.C, nullptr);
+    dynamics<T, N, CMAT, false>(P, K, dq, o.M, o.g, o.C, nullptr);
     ABRB_UNROLL
     for (int a = 0; a < N; ++a)
       ABRB_UNROLL

@@ -30,12 +30,39 @@ struct MaxRecord {
   static constexpr int value = big > 16 ? big : 16;
 };
 
+// Per-warp shared-memory region: holds the warp's kinematic scratch (slot-major, stride 32: lane i owns column i,
+// conflict-free) while a state is being evaluated and is then re-used as the staging tile for the coalesced
+// stores.  KSMEM selects the shared-memory scratch (fp64 kernels: keeps them under the register limit without
+// local-memory spills); otherwise the scratch lives in registers and only the staging tile is needed.
+template <typename T, int N, bool ORTHO, bool KSMEM>
+struct KinSel;
+template <typename T, int N, bool ORTHO>
+struct KinSel<T, N, ORTHO, false> {
+  typedef Kin<T, N, ORTHO, RegStore> type;
+  static constexpr int kSlots = 0;
+  static __device__ __forceinline__ void bind(type &, T *, int) {}
+};
+template <typename T, int N, bool ORTHO>
+struct KinSel<T, N, ORTHO, true> {
+  typedef Kin<T, N, ORTHO, StridedStore> type;
+  static constexpr int kSlots = KinSlots<N, ORTHO>::kCount;
+  static __device__ __forceinline__ void bind(type &k, T *warp_region, int lane) {
+    k.s.base = warp_region + lane;
+    k.s.stride = 32;
+  }
+};
+template <int A, int B>
+struct MaxI {
+  static constexpr int value = A > B ? A : B;
+};
+
 // Write one LEN-element record per lane to `out[(warp_b0 + lane) * LEN + e]` through the warp's staging
 // tile: conflict-light scalar writes into smem, then a linear, fully coalesced copy-out (16-byte vectors
 // for full warps).
 template <typename T, int LEN>
 __device__ __forceinline__ void store_records(T *__restrict__ out, int64_t warp_b0, int nvalid, const T *rec,
                                               T *stage, int lane) {
+  __syncwarp();  // the tile aliases the warp's kinematic scratch: every lane must be done reading it
 #pragma unroll
   for (int e = 0; e < LEN; ++e) stage[lane * LEN + e] = rec[e];
   __syncwarp();
@@ -66,12 +93,16 @@ struct RbdArgs {
   T xoff[3];
 };
 
-template <typename T, int N, bool ORTHO, bool DYN, bool CMAT>
+template <typename T, int N, bool ORTHO, bool DYN, bool CMAT, bool KSMEM>
 __global__ void __launch_bounds__(kBlock)
 rbd_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ RbdArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef KinSel<T, N, ORTHO, KSMEM> KS;
+  constexpr int kRegion = 32 * MaxI<MaxRecord<N>::value, KS::kSlots>::value;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T *stage = reinterpret_cast<T *>(smem_raw) + warp * 32 * MaxRecord<N>::value;
+  T *stage = reinterpret_cast<T *>(smem_raw) + warp * kRegion;
+  typename KS::type K;
+  KS::bind(K, stage, lane);
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
     const int64_t warp_b0 = base + warp * 32;
     if (warp_b0 >= a.B) break;  // whole warp out of range (uniform per warp)
@@ -85,7 +116,7 @@ rbd_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ RbdAr
       dq[k] = a.dq != nullptr ? a.dq[b * N + k] : T(0);
     }
     RbdOut<T, N> o;
-    rbd_state<T, N, ORTHO, DYN, CMAT>(P, q, dq, a.frame, a.xoff, a.want, o);
+    rbd_state<T, N, DYN, CMAT>(P, q, dq, a.frame, a.xoff, a.want, o, K);
     if (a.Tx) store_records<T, 3>(a.Tx, warp_b0, nvalid, o.Tx, stage, lane);
     if (a.Tm) store_records<T, 16>(a.Tm, warp_b0, nvalid, o.Tm, stage, lane);
     if (a.R) store_records<T, 9>(a.R, warp_b0, nvalid, o.R, stage, lane);
@@ -111,33 +142,69 @@ struct OscArgs {
   int target_stride, tv_stride;
 };
 
-template <typename T, int N, bool ORTHO, int KD>
+// Two passes per 128-state tile: pass 0 evaluates every state but defers the few that need the truncating
+// pseudo-inverse (eigen-decomposition) by queueing them in shared memory; pass 1 re-evaluates the queued states
+// densely packed on the first threads of the CTA, so the divergent slow path runs on full warps.
+template <typename T, int N, bool ORTHO, int KD, bool KSMEM>
 __global__ void __launch_bounds__(kBlock)
 osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
            const __grid_constant__ OscArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_cnt;
+  __shared__ int s_idx[kBlock];
+  typedef KinSel<T, N, ORTHO, KSMEM> KS;
+  constexpr int kRegion = 32 * MaxI<N, KS::kSlots>::value;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T *stage = reinterpret_cast<T *>(smem_raw) + warp * 32 * N;
+  T *stage = reinterpret_cast<T *>(smem_raw) + warp * kRegion;
+  typename KS::type K;
+  KS::bind(K, stage, lane);
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
     const int64_t warp_b0 = base + warp * 32;
-    if (warp_b0 >= a.B) break;
     const int64_t rem = a.B - warp_b0;
-    const int nvalid = rem < 32 ? (int)rem : 32;
-    const int64_t b = warp_b0 + (lane < nvalid ? lane : nvalid - 1);
-    T q[N], dq[N], tg[6], tv[6], u[N], tr[N];
+    const int nvalid = rem < 32 ? (rem > 0 ? (int)rem : 0) : 32;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      bool active;
+      int64_t b;
+      if (pass == 0) {
+        active = nvalid > 0;  // uniform per warp; idle lanes of a ragged warp redo its last state
+        b = warp_b0 + (lane < nvalid ? lane : nvalid - 1);
+      } else {
+        const int cnt = s_cnt;
+        if (cnt == 0) break;  // uniform per CTA
+        active = (int)threadIdx.x < cnt;
+        b = base + (active ? s_idx[threadIdx.x] : 0);
+      }
+      if (active) {
+        T q[N], dq[N], tg[6], tv[6], u[N], tr[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      q[k] = a.q[b * N + k];
-      dq[k] = a.dq[b * N + k];
-    }
+        for (int k = 0; k < N; ++k) {
+          q[k] = a.q[b * N + k];
+          dq[k] = a.dq[b * N + k];
+        }
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      tg[c] = a.target[b * a.target_stride + c];
-      tv[c] = a.tv != nullptr ? a.tv[b * a.tv_stride + c] : T(0);
+        for (int c = 0; c < 6; ++c) {
+          tg[c] = a.target[b * a.target_stride + c];
+          tv[c] = a.tv != nullptr ? a.tv[b * a.tv_stride + c] : T(0);
+        }
+        const bool deferred =
+            osc_state<T, N, KD, false>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, u, tr, nullptr, K, pass == 0);
+        if (pass == 0) {
+          if (deferred && lane < nvalid) s_idx[atomicAdd(&s_cnt, 1)] = (int)threadIdx.x;
+          store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);  // deferred rows are rewritten in pass 1
+          if (a.train) store_records<T, N>(a.train, warp_b0, nvalid, tr, stage, lane);
+        } else {
+#pragma unroll
+          for (int k = 0; k < N; ++k) {
+            a.u[b * N + k] = u[k];
+            if (a.train) a.train[b * N + k] = tr[k];
+          }
+        }
+      }
+      __syncthreads();  // pass 0 -> 1: queue complete and pass-0 stores ordered before the rewrites
     }
-    osc_state<T, N, ORTHO, KD, false>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, u, tr, nullptr);
-    store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);
-    if (a.train) store_records<T, N>(a.train, warp_b0, nvalid, tr, stage, lane);
   }
 }
 
@@ -152,13 +219,17 @@ struct RolloutArgs {
 };
 
 // Closed loop: u = OSC(q, dq); ddq = M^-1 (u + g - C dq); dq += ddq dt; q += dq dt  (state stays in registers)
-template <typename T, int N, bool ORTHO, int KD>
+template <typename T, int N, bool ORTHO, int KD, bool KSMEM>
 __global__ void __launch_bounds__(kBlock)
 rollout_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
                const __grid_constant__ RolloutArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef KinSel<T, N, ORTHO, KSMEM> KS;
+  constexpr int kRegion = 32 * MaxI<N, KS::kSlots>::value;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T *stage = reinterpret_cast<T *>(smem_raw) + warp * 32 * N;
+  T *stage = reinterpret_cast<T *>(smem_raw) + warp * kRegion;
+  typename KS::type K;
+  KS::bind(K, stage, lane);
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
     const int64_t warp_b0 = base + warp * 32;
     if (warp_b0 >= a.B) break;
@@ -174,7 +245,7 @@ rollout_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ O
 #pragma unroll
     for (int c = 0; c < 6; ++c) tg[c] = a.target[b * a.target_stride + c];
     for (int t = 0; t < a.steps; ++t) {
-      osc_state<T, N, ORTHO, KD, true>(P, O, q, dq, tg, nullptr, u, nullptr, acc);
+      osc_state<T, N, KD, true>(P, O, q, dq, tg, nullptr, u, nullptr, acc, K);
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         dq[k] += acc[k] * a.dt;
@@ -216,7 +287,8 @@ null_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ Null
       q[k] = a.q[b * N + k];
       dq[k] = a.dq[b * N + k];
     }
-    null_state<T, N, ORTHO>(P, Z, q, dq, u);
+    Kin<T, N, ORTHO> K;
+    null_state<T, N>(P, Z, q, dq, u, K);
     store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);
   }
 }
@@ -262,8 +334,9 @@ int rbd_go(const ChainHost &h, const RbdCall &c, unsigned want) {
   a.frame = c.frame;
   a.want = want;
   for (int i = 0; i < 3; ++i) a.xoff[i] = c.xoff ? T(c.xoff[i]) : T(0);
-  const size_t smem = (size_t)kWarps * 32 * MaxRecord<N>::value * sizeof(T);
-  auto kern = rbd_kernel<T, N, ORTHO, DYN, CMAT>;
+  constexpr bool KSMEM = sizeof(T) == 8;
+  const size_t smem = (size_t)kWarps * 32 * MaxI<MaxRecord<N>::value, KinSel<T, N, ORTHO, KSMEM>::kSlots>::value * sizeof(T);
+  auto kern = rbd_kernel<T, N, ORTHO, DYN, CMAT, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, a);
@@ -311,8 +384,12 @@ int osc_go(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
   a.B = c.B;
   a.target_stride = c.target_stride;
   a.tv_stride = c.tv_stride;
-  const size_t smem = (size_t)kWarps * 32 * N * sizeof(T);
-  osc_kernel<T, N, ORTHO, KD><<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, O, a);
+  constexpr bool KSMEM = sizeof(T) == 8;
+  const size_t smem = (size_t)kWarps * 32 * MaxI<N, KinSel<T, N, ORTHO, KSMEM>::kSlots>::value * sizeof(T);
+  auto kern = osc_kernel<T, N, ORTHO, KD, KSMEM>;
+  cudaError_t e = set_smem(kern, smem);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, O, a);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -334,8 +411,12 @@ int rollout_go(const ChainHost &h, const abrb_osc_params &p, const RolloutCall &
   a.target_stride = c.target_stride;
   a.steps = c.steps;
   a.dt = T(c.dt);
-  const size_t smem = (size_t)kWarps * 32 * N * sizeof(T);
-  rollout_kernel<T, N, ORTHO, KD><<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, O, a);
+  constexpr bool KSMEM = sizeof(T) == 8;
+  const size_t smem = (size_t)kWarps * 32 * MaxI<N, KinSel<T, N, ORTHO, KSMEM>::kSlots>::value * sizeof(T);
+  auto kern = rollout_kernel<T, N, ORTHO, KD, KSMEM>;
+  cudaError_t e = set_smem(kern, smem);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, O, a);
   count_launch();
   return (int)cudaGetLastError();
 }

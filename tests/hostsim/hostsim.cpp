@@ -26,7 +26,8 @@ void rbd_loop(const ChainHost &h, int frame, const double *xoff, const double *q
       dd[k] = dq ? T(dq[b * N + k]) : T(0);
     }
     RbdOut<T, N> o;
-    rbd_state<T, N, ORTHO, true, true>(P, qq, dd, frame, xo, want, o);
+    Kin<T, N, ORTHO> K;
+    rbd_state<T, N, true, true>(P, qq, dd, frame, xo, want, o, K);
     auto put = [&](double *dst, const T *src, int len) {
       if (dst)
         for (int i = 0; i < len; ++i) dst[b * len + i] = double(src[i]);
@@ -63,10 +64,11 @@ void osc_loop(const ChainHost &h, const abrb_osc_params &p, int frame, const dou
       tg[c] = T(target[b * tstride + c]);
       tvv[c] = tv ? T(tv[b * tvstride + c]) : T(0);
     }
+    Kin<T, N, ORTHO> K;
     if (kd6)
-      osc_state<T, N, ORTHO, 6, true>(P, O, qq, dd, tg, tv ? tvv : nullptr, uu, tr, acc);
+      osc_state<T, N, 6, true>(P, O, qq, dd, tg, tv ? tvv : nullptr, uu, tr, acc, K);
     else
-      osc_state<T, N, ORTHO, 3, true>(P, O, qq, dd, tg, tv ? tvv : nullptr, uu, tr, acc);
+      osc_state<T, N, 3, true>(P, O, qq, dd, tg, tv ? tvv : nullptr, uu, tr, acc, K);
     for (int k = 0; k < N; ++k) {
       u[b * N + k] = double(uu[k]);
       if (train) train[b * N + k] = double(tr[k]);
@@ -87,7 +89,8 @@ void null_loop(const ChainHost &h, const abrb_null_params &z, const double *q, c
       qq[k] = T(q[b * N + k]);
       dd[k] = T(dq[b * N + k]);
     }
-    null_state<T, N, ORTHO>(P, Z, qq, dd, uu);
+    Kin<T, N, ORTHO> K;
+    null_state<T, N>(P, Z, qq, dd, uu, K);
     for (int k = 0; k < N; ++k) u[b * N + k] = double(uu[k]);
   }
 }
