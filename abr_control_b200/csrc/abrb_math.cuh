@@ -339,94 +339,97 @@ ABRB_HD void jacobian_dot(const K_ &K, const T (*J)[N], const T *dq, int dep, T 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Joint-space dynamics.  M (upper triangle a<=b filled, mirrored by the caller), g, and optionally
-// the Coriolis matrix C (CMAT) or only the product C.dq (CDQ).
-//   M = sum_l J_l^T W_l J_l            base_config.py:625-632
+// Joint-space dynamics, written for a small live set (one link at a time, only the link's Jacobian columns
+// v_k = d p_l / d q_k are kept; everything else is accumulated on the fly).
+//   M = sum_l J_l^T W_l J_l            base_config.py:625-632      (upper triangle a<=b is filled)
 //   g = sum_l J_l^T W_l gravity        base_config.py:448-455
 //   C[k][j] = sum_i 1/2 (d_i M_kj + d_j M_ki - d_k M_ij) dq_i     base_config.py:706-714
-// Translational part of C:  sum_l (W_l v_lk) . (d/dt v_lj)   — the symmetric second-derivative terms of
-// the Christoffel sum cancel exactly; rotational part: explicit Christoffel sum.
-template <typename T, int N, bool CMAT, bool CDQ, class K_>
-ABRB_HD void dynamics(const ChainK<T, N> &P, const K_ &K, const T *dq, T (*M)[N], T *g, T (*C)[N], T *cdq) {
+// Translational part of C:  sum_l v_lk . W_l (d/dt v_lj)  — the second derivatives of a point are symmetric, so
+// the symmetric pieces of the Christoffel sum cancel exactly.  With
+//   W_j = sum_{i<j} dq_i Omega_i,   suf_j = sum_{j<=i<l} dq_i v_li
+// d/dt v_lj = W_j v_lj + Omega_j suf_j; walking j downwards needs only the running tail of both sums.
+// Rotational part: explicit Christoffel sum over the derivative index (C matrix) or the product form (C dq).
+
+// difference of two running operator sums applied to v:  (A - B) v
+template <typename T, bool ORTHO>
+ABRB_HD void spin_diff_apply(const Spin<T, ORTHO> &A, const Spin<T, ORTHO> &B, const T *v, T *o) {
+  Spin<T, ORTHO> D;
+  ABRB_UNROLL
+  for (int i = 0; i < (ORTHO ? 3 : 9); ++i) D.w[i] = A.w[i] - B.w[i];
+  D.apply(v, o);
+}
+
+// Jacobian columns of link l's COM: v[k] = Omega_k (p_l - t_k), k < l
+template <typename T, int N, class K_>
+ABRB_HD void link_columns(const K_ &K, int l, T (*v)[3]) {
+  T pl[3];
+  K.pl(l - 1, pl);
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) {
+    if (k < l) {
+      T d[3], tk[3];
+      K.t(k, tk);
+      ABRB_UNROLL
+      for (int c = 0; c < 3; ++c) d[c] = pl[c] - tk[c];
+      omega_apply(K, k, d, v[k]);
+    }
+  }
+}
+
+// M (upper triangle), g and, if CDQ, the product C.dq
+template <typename T, int N, bool CDQ, class K_>
+ABRB_HD void dynamics_Mg(const ChainK<T, N> &P, const K_ &K, const T *dq, T (*M)[N], T *g, T *cdq) {
   constexpr bool ORTHO = K_::kOrtho;
   ABRB_UNROLL
   for (int a = 0; a < N; ++a) {
     g[a] = T(0);
     if (CDQ) cdq[a] = T(0);
     ABRB_UNROLL
-    for (int b = 0; b < N; ++b) {
-      M[a][b] = T(0);
-      if (CMAT) C[a][b] = T(0);
-    }
+    for (int b = 0; b < N; ++b) M[a][b] = T(0);
   }
-  // ---- translational part, link by link (link l = 1..N has COM K.pl[l-1] and moves with joints < l)
+  Spin<T, ORTHO> Wl;  // sum_{i<l} dq_i Omega_i, carried from link to link
+  Wl.clear();
   ABRB_UNROLL
   for (int l = 1; l <= N; ++l) {
-    T v[N][3], wv[N][3], pl[3];
-    K.pl(l - 1, pl);
+    T v[N][3];
+    link_columns<T, N>(K, l, v);
     ABRB_UNROLL
-    for (int k = 0; k < N; ++k) {
-      if (k < l) {
-        T d[3], tk[3];
-        K.t(k, tk);
+    for (int b = 0; b < N; ++b) {
+      if (b < l) {
+        const T wb[3] = {P.Wp[l][0] * v[b][0], P.Wp[l][1] * v[b][1], P.Wp[l][2] * v[b][2]};
+        g[b] += dot3(v[b], P.gp[l]);
         ABRB_UNROLL
-        for (int c = 0; c < 3; ++c) d[c] = pl[c] - tk[c];
-        omega_apply(K, k, d, v[k]);
-        ABRB_UNROLL
-        for (int c = 0; c < 3; ++c) wv[k][c] = P.Wp[l][c] * v[k][c];
-        g[k] += dot3(v[k], P.gp[l]);
+        for (int a = 0; a < N; ++a)
+          if (a <= b) M[a][b] += dot3(v[a], wb);
       }
     }
-    ABRB_UNROLL
-    for (int a = 0; a < N; ++a)
+    if (CDQ) {
+      Wl.add(K, l - 1, dq[l - 1]);
+      Spin<T, ORTHO> tail;
+      tail.clear();
+      T suf[3] = {T(0), T(0), T(0)}, acc[3] = {T(0), T(0), T(0)};
       ABRB_UNROLL
-    for (int b = a; b < N; ++b)
-      if (b < l) M[a][b] += dot3(wv[a], v[b]);
-    if (CMAT || CDQ) {
-      T suf[N][3];
-      T run[3] = {T(0), T(0), T(0)};
-      ABRB_UNROLL
-      for (int k = N - 1; k >= 0; --k) {
-        if (k < l) {
-          ABRB_UNROLL
-          for (int c = 0; c < 3; ++c) {
-            run[c] += dq[k] * v[k][c];
-            suf[k][c] = run[c];
-          }
-        }
-      }
-      Spin<T, ORTHO> W;
-      W.clear();
-      T acc[3] = {T(0), T(0), T(0)};
-      ABRB_UNROLL
-      for (int j = 0; j < N; ++j) {
+      for (int j = N - 1; j >= 0; --j) {
         if (j < l) {
-          T a1[3], a2[3], aj[3];
-          W.apply(v[j], a1);
-          omega_apply(K, j, suf[j], a2);
+          tail.add(K, j, dq[j]);
           ABRB_UNROLL
-          for (int c = 0; c < 3; ++c) aj[c] = a1[c] + a2[c];
-          if (CMAT) {
-            ABRB_UNROLL
-            for (int k = 0; k < N; ++k)
-              if (k < l) C[k][j] += dot3(wv[k], aj);
-          }
-          if (CDQ) {
-            ABRB_UNROLL
-            for (int c = 0; c < 3; ++c) acc[c] += dq[j] * aj[c];
-          }
-          W.add(K, j, dq[j]);
+          for (int c = 0; c < 3; ++c) suf[c] += dq[j] * v[j][c];
+          T a1[3], a2[3];
+          spin_diff_apply(Wl, tail, v[j], a1);  // W_j v_j
+          omega_apply(K, j, suf, a2);           // Omega_j suf_j
+          ABRB_UNROLL
+          for (int c = 0; c < 3; ++c) acc[c] += dq[j] * (a1[c] + a2[c]);
         }
       }
-      if (CDQ) {
-        ABRB_UNROLL
-        for (int k = 0; k < N; ++k)
-          if (k < l) cdq[k] += dot3(wv[k], acc);
-      }
+      ABRB_UNROLL
+      for (int c = 0; c < 3; ++c) acc[c] *= P.Wp[l][c];
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k)
+        if (k < l) cdq[k] += dot3(v[k], acc);
     }
   }
   // ---- rotational part: M_ab += sum_c z_a[c] Wos[max(a,b)][c] z_b[c]
-  T Z[N][3];  // joint axes, fetched once for the rotational terms
+  T Z[N][3];
   ABRB_UNROLL
   for (int a = 0; a < N; ++a) K.z(a, Z[a]);
   ABRB_UNROLL
@@ -436,39 +439,11 @@ ABRB_HD void dynamics(const ChainK<T, N> &P, const K_ &K, const T *dq, T (*M)[N]
     for (int b = a; b < N; ++b)
       M[a][b] += Z[a][0] * P.Wos[b][0] * Z[b][0] + Z[a][1] * P.Wos[b][1] * Z[b][1] + Z[a][2] * P.Wos[b][2] * Z[b][2];
   }
-  if (CMAT) {
-    // dz[i][a] = Omega_i z_a (i<a);  dMo(i;a,b) = sum_c Wos[max(a,b)][c] (dz[i][a][c] z_b[c] + z_a[c] dz[i][b][c])
-    T dz[N][N][3];
-    ABRB_UNROLL
-    for (int i = 0; i < N; ++i)
-      ABRB_UNROLL
-    for (int a = 0; a < N; ++a) {
-      if (i < a) {
-        omega_apply(K, i, Z[a], dz[i][a]);
-      } else {
-        dz[i][a][0] = dz[i][a][1] = dz[i][a][2] = T(0);
-      }
-    }
-    auto dMo = [&](int i, int a, int b) -> T {
-      const int m = a > b ? a : b;
-      T s = T(0);
-      ABRB_UNROLL
-      for (int c = 0; c < 3; ++c) s += P.Wos[m][c] * (dz[i][a][c] * Z[b][c] + Z[a][c] * dz[i][b][c]);
-      return s;
-    };
-    ABRB_UNROLL
-    for (int k = 0; k < N; ++k)
-      ABRB_UNROLL
-    for (int j = 0; j < N; ++j) {
-      T s = T(0);
-      ABRB_UNROLL
-      for (int i = 0; i < N; ++i) s += (dMo(i, k, j) + dMo(j, k, i) - dMo(k, i, j)) * dq[i];
-      C[k][j] += T(0.5) * s;
-    }
-  }
   if (CDQ) {
-    // (C dq)_k = (dM/dt dq)_k - 1/2 d/dq_k (dq^T M dq), rotational part
-    T zd[N][3], h[N][3];
+    // (C dq)_k = (dM/dt dq)_k - 1/2 d/dq_k (dq^T M dq), rotational part, with
+    //   zd_a = W_a z_a,  hz_k = sum_j dq_j Wos[max(k,j)] o z_j,  hd_k = sum_j dq_j Wos[max(k,j)] o zd_j
+    //   (dM/dt dq)_k = zd_k . hz_k + z_k . hd_k ;   1/2 d_k(..) = sum_{i>k} dq_i (Omega_k z_i) . hz_i
+    T zd[N][3];
     Spin<T, ORTHO> W;
     W.clear();
     ABRB_UNROLL
@@ -477,35 +452,107 @@ ABRB_HD void dynamics(const ChainK<T, N> &P, const K_ &K, const T *dq, T (*M)[N]
       W.add(K, a, dq[a]);
     }
     ABRB_UNROLL
-    for (int i = 0; i < N; ++i) {
-      h[i][0] = h[i][1] = h[i][2] = T(0);
+    for (int k = 0; k < N; ++k) {
+      T hz[3] = {T(0), T(0), T(0)}, hd[3] = {T(0), T(0), T(0)};
       ABRB_UNROLL
       for (int j = 0; j < N; ++j) {
-        const int m = i > j ? i : j;
+        const int m = k > j ? k : j;
         ABRB_UNROLL
-        for (int c = 0; c < 3; ++c) h[i][c] += dq[j] * P.Wos[m][c] * Z[j][c];
+        for (int c = 0; c < 3; ++c) {
+          hz[c] += dq[j] * P.Wos[m][c] * Z[j][c];
+          hd[c] += dq[j] * P.Wos[m][c] * zd[j][c];
+        }
+      }
+      cdq[k] += dot3(zd[k], hz) + dot3(Z[k], hd);
+      // -(1/2) d/dq_i terms: state k receives from every i < k:  - dq_k (Omega_i z_k) . hz_k
+      ABRB_UNROLL
+      for (int i = 0; i < N; ++i) {
+        if (i < k) {
+          T oz[3];
+          omega_apply(K, i, Z[k], oz);
+          cdq[i] -= dq[k] * dot3(oz, hz);
+        }
+      }
+    }
+  }
+}
+
+// The full Coriolis matrix C (only the rbd kernel materialises it)
+template <typename T, int N, class K_>
+ABRB_HD void dynamics_C(const ChainK<T, N> &P, const K_ &K, const T *dq, T (*C)[N]) {
+  constexpr bool ORTHO = K_::kOrtho;
+  ABRB_UNROLL
+  for (int a = 0; a < N; ++a)
+    ABRB_UNROLL
+  for (int b = 0; b < N; ++b) C[a][b] = T(0);
+  Spin<T, ORTHO> Wl;
+  Wl.clear();
+  ABRB_UNROLL
+  for (int l = 1; l <= N; ++l) {
+    T v[N][3];
+    link_columns<T, N>(K, l, v);
+    Wl.add(K, l - 1, dq[l - 1]);
+    Spin<T, ORTHO> tail;
+    tail.clear();
+    T suf[3] = {T(0), T(0), T(0)};
+    ABRB_UNROLL
+    for (int j = N - 1; j >= 0; --j) {
+      if (j < l) {
+        tail.add(K, j, dq[j]);
+        ABRB_UNROLL
+        for (int c = 0; c < 3; ++c) suf[c] += dq[j] * v[j][c];
+        T a1[3], a2[3], wa[3];
+        spin_diff_apply(Wl, tail, v[j], a1);
+        omega_apply(K, j, suf, a2);
+        ABRB_UNROLL
+        for (int c = 0; c < 3; ++c) wa[c] = P.Wp[l][c] * (a1[c] + a2[c]);
+        ABRB_UNROLL
+        for (int k = 0; k < N; ++k)
+          if (k < l) C[k][j] += dot3(v[k], wa);
+      }
+    }
+  }
+  // ---- rotational part, one derivative index d at a time.  With dz_a = Omega_d z_a (a > d, else 0) and
+  //   D(a,b) = sum_c Wos[max(a,b)][c] (dz_a[c] z_b[c] + z_a[c] dz_b[c])   (= d M_ab / d q_d, symmetric)
+  //   E_a    = sum_i dq_i D(a,i)
+  // the Christoffel sum contributes  C[k][j] += 1/2 dq_d D(k,j),  C[k][d] += 1/2 E_k,  C[d][j] -= 1/2 E_j.
+  T Z[N][3];
+  ABRB_UNROLL
+  for (int a = 0; a < N; ++a) K.z(a, Z[a]);
+  ABRB_UNROLL
+  for (int d = 0; d < N; ++d) {
+    T dz[N][3], E[N];
+    ABRB_UNROLL
+    for (int a = 0; a < N; ++a) {
+      E[a] = T(0);
+      if (a > d) {
+        omega_apply(K, d, Z[a], dz[a]);
+      } else {
+        dz[a][0] = dz[a][1] = dz[a][2] = T(0);
+      }
+    }
+    ABRB_UNROLL
+    for (int a = 0; a < N; ++a) {
+      ABRB_UNROLL
+      for (int b = a; b < N; ++b) {
+        if (b > d) {  // D(a,b) vanishes unless max(a,b) > d
+          T Dab = T(0);
+          ABRB_UNROLL
+          for (int c = 0; c < 3; ++c) Dab += P.Wos[b][c] * (dz[a][c] * Z[b][c] + Z[a][c] * dz[b][c]);
+          const T h = T(0.5) * dq[d] * Dab;
+          C[a][b] += h;
+          E[a] += dq[b] * Dab;
+          if (b != a) {
+            C[b][a] += h;
+            E[b] += dq[a] * Dab;
+          }
+        }
       }
     }
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) {
-      T s = T(0);
-      ABRB_UNROLL
-      for (int j = 0; j < N; ++j) {
-        const int m = k > j ? k : j;
-        T e = T(0);
-        ABRB_UNROLL
-        for (int c = 0; c < 3; ++c) e += P.Wos[m][c] * (zd[k][c] * Z[j][c] + Z[k][c] * zd[j][c]);
-        s += dq[j] * e;
-      }
-      ABRB_UNROLL
-      for (int i = 0; i < N; ++i) {
-        if (i > k) {
-          T oz[3];
-          omega_apply(K, k, Z[i], oz);
-          s -= dq[i] * dot3(oz, h[i]);
-        }
-      }
-      cdq[k] += s;
+      C[k][d] += T(0.5) * E[k];
+      C[d][k] -= T(0.5) * E[k];
     }
   }
 }
@@ -678,7 +725,7 @@ ABRB_HD_NOINLINE void pinv_apply_sym(const T *Sin, unsigned active, T rcond, con
     T off = T(0), diag = T(0);
     ABRB_NOUNROLL
     for (int i = 0; i < S_; ++i) {
-      diag += A[i][i] * A[i][i];
+      if ((active >> i) & 1u) diag += A[i][i] * A[i][i];  // identity rows must not set the scale
       ABRB_NOUNROLL
       for (int j = i + 1; j < S_; ++j) off += A[i][j] * A[i][j];
     }
@@ -731,6 +778,191 @@ ABRB_HD_NOINLINE void pinv_apply_sym(const T *Sin, unsigned active, T rcond, con
     ABRB_NOUNROLL
     for (int k = 0; k < S_; ++k) x[k] += V[k][e] * proj;
   }
+}
+
+// Fast route to x = pinv(S, rcond) y for a symmetric positive definite (possibly very ill-conditioned) S whose
+// Cholesky factor L (with reciprocal diagonal invd) is already known.  numpy.linalg.pinv drops the eigenvalues
+// <= rcond * lambda_max; instead of a full eigen-decomposition this
+//   1. brackets lambda_max: Rayleigh quotient rho of a few power iterations (a lower bound) and an inertia count
+//      (LDL^T of S - sigma I, Sylvester) proving that no eigenvalue exceeds rho (1 + 1e-7);
+//   2. counts the eigenvalues below the cutoff with the same inertia count, at both ends of the bracket;
+//   3. finds the (at most 2) truncated eigenvectors by inverse subspace iteration with L and projects them out:
+//      x = P S^-1 P y,  P = I - V V^T.
+// Returns false whenever a step is inconclusive (more than 2 truncated eigenvalues, slow convergence, a vanishing
+// pivot, the bracket straddling an eigenvalue): the caller then falls back to the Jacobi routine above.
+// Rows not in `active` must be decoupled from the rest (zero off-diagonals) with a diagonal >= lambda_max, and
+// y must vanish on them.  All loops are rolled: this is a rare path and must stay small.
+template <typename T, int S_>
+ABRB_HD_NOINLINE bool pinv_solve_fast(const T *Sin, const T *Lin, const T *invd, unsigned active, T rcond, int nrhs,
+                                      const T *y, T *x) {
+  T Sm[S_][S_], L[S_][S_], idg[S_];
+  ABRB_NOUNROLL
+  for (int i = 0; i < S_; ++i) {
+    idg[i] = invd[i];
+    ABRB_NOUNROLL
+    for (int j = 0; j < S_; ++j) {
+      Sm[i][j] = Sin[i * S_ + j];
+      L[i][j] = Lin[i * S_ + j];
+    }
+  }
+  // number of eigenvalues of S below sigma (-1: inconclusive)
+  auto count_below = [&](T sigma) -> int {
+    T D[S_][S_];
+    ABRB_NOUNROLL
+    for (int i = 0; i < S_; ++i) {
+      ABRB_NOUNROLL
+      for (int j = 0; j < S_; ++j) D[i][j] = Sm[i][j] - (i == j ? sigma : T(0));
+    }
+    int neg = 0;
+    ABRB_NOUNROLL
+    for (int j = 0; j < S_; ++j) {
+      const T d = D[j][j];
+      if (!(abs_t(d) > T(0))) return -1;
+      if (d < T(0)) ++neg;
+      const T inv = T(1) / d;
+      ABRB_NOUNROLL
+      for (int i = j + 1; i < S_; ++i) {
+        const T f = D[i][j] * inv;
+        ABRB_NOUNROLL
+        for (int k = j + 1; k < S_; ++k) D[i][k] -= f * D[j][k];
+      }
+    }
+    return neg;
+  };
+  auto solve = [&](T *b) {  // b <- S^-1 b
+    ABRB_NOUNROLL
+    for (int i = 0; i < S_; ++i) {
+      T acc = b[i];
+      ABRB_NOUNROLL
+      for (int k = 0; k < i; ++k) acc -= L[i][k] * b[k];
+      b[i] = acc * idg[i];
+    }
+    ABRB_NOUNROLL
+    for (int i = S_ - 1; i >= 0; --i) {
+      T acc = b[i];
+      ABRB_NOUNROLL
+      for (int k = i + 1; k < S_; ++k) acc -= L[k][i] * b[k];
+      b[i] = acc * idg[i];
+    }
+  };
+  // ---- 1. lambda_max on the active block
+  T v[S_], w[S_];
+  ABRB_NOUNROLL
+  for (int i = 0; i < S_; ++i) v[i] = ((active >> i) & 1u) ? T(1) + T(0.37) * T(i) : T(0);
+  T rho = T(0);
+  ABRB_NOUNROLL
+  for (int it = 0; it < 20; ++it) {
+    T nn = T(0), num = T(0), den = T(0);
+    ABRB_NOUNROLL
+    for (int i = 0; i < S_; ++i) {
+      T acc = T(0);
+      ABRB_NOUNROLL
+      for (int j = 0; j < S_; ++j) acc += Sm[i][j] * v[j];
+      w[i] = ((active >> i) & 1u) ? acc : T(0);
+      num += v[i] * w[i];
+      den += v[i] * v[i];
+      nn += w[i] * w[i];
+    }
+    rho = num / den;
+    const T sc = T(1) / sqrt_t(nn);
+    ABRB_NOUNROLL
+    for (int i = 0; i < S_; ++i) v[i] = w[i] * sc;
+  }
+  const T slack = sizeof(T) == 8 ? T(1e-7) : T(1e-3);
+  // every eigenvalue of the active block must lie below rho (1 + slack); inactive rows carry diag >= lambda_max,
+  // so test the active block only by temporarily shrinking them out of the way
+  int n_act = 0, n_inact_below = 0;
+  ABRB_NOUNROLL
+  for (int i = 0; i < S_; ++i) {
+    if ((active >> i) & 1u) ++n_act;
+    else if (Sm[i][i] < rho * (T(1) + slack)) ++n_inact_below;
+  }
+  const int below_top = count_below(rho * (T(1) + slack));
+  if (below_top < 0 || below_top - n_inact_below != n_act) return false;  // power iteration not converged
+  // ---- 2. how many eigenvalues are truncated
+  const int m_lo = count_below(rcond * rho), m_hi = count_below(rcond * rho * (T(1) + slack));
+  if (m_lo < 0 || m_lo != m_hi || m_lo > 2) return false;
+  const int m = m_lo;
+  // ---- 3. truncated eigenvectors by inverse subspace iteration
+  T V[2][S_];
+  ABRB_NOUNROLL
+  for (int e = 0; e < 2; ++e) {
+    ABRB_NOUNROLL
+    for (int i = 0; i < S_; ++i) V[e][i] = ((active >> i) & 1u) ? T(1) / T(1 + i + 2 * e) + (e == 1 && (i & 1) ? T(-0.7) : T(0.1)) : T(0);
+  }
+  T theta[2] = {T(0), T(0)};
+  ABRB_NOUNROLL
+  for (int it = 0; it < 10; ++it) {
+    ABRB_NOUNROLL
+    for (int e = 0; e < m; ++e) {
+      solve(V[e]);
+      ABRB_NOUNROLL
+      for (int f = 0; f < e; ++f) {  // Gram-Schmidt against the previous vector
+        T d = T(0);
+        ABRB_NOUNROLL
+        for (int i = 0; i < S_; ++i) d += V[f][i] * V[e][i];
+        ABRB_NOUNROLL
+        for (int i = 0; i < S_; ++i) V[e][i] -= d * V[f][i];
+      }
+      T nn = T(0);
+      ABRB_NOUNROLL
+      for (int i = 0; i < S_; ++i) nn += V[e][i] * V[e][i];
+      if (!(nn > T(0))) return false;
+      const T sc = T(1) / sqrt_t(nn);
+      ABRB_NOUNROLL
+      for (int i = 0; i < S_; ++i) V[e][i] *= sc;
+    }
+  }
+  // Ritz values + residual check: the span must be invariant (||S v - theta v|| tiny relative to the cutoff)
+  ABRB_NOUNROLL
+  for (int e = 0; e < m; ++e) {
+    T r2 = T(0), th = T(0);
+    ABRB_NOUNROLL
+    for (int i = 0; i < S_; ++i) {
+      T acc = T(0);
+      ABRB_NOUNROLL
+      for (int j = 0; j < S_; ++j) acc += Sm[i][j] * V[e][j];
+      w[i] = acc;
+      th += V[e][i] * acc;
+    }
+    theta[e] = th;
+    ABRB_NOUNROLL
+    for (int i = 0; i < S_; ++i) {
+      T r = w[i] - th * V[e][i];
+      if (m == 2) {  // for two vectors only the span needs to be invariant
+        const int o = 1 - e;
+        T c = T(0);
+        ABRB_NOUNROLL
+        for (int j = 0; j < S_; ++j) c += V[o][j] * w[j];
+        r -= c * V[o][i];
+      }
+      r2 += r * r;
+    }
+    const T tol = (sizeof(T) == 8 ? T(1e-9) : T(1e-4)) * rcond * rho;
+    if (!(r2 <= tol * tol)) return false;
+  }
+  // ---- 4. x = P S^-1 P y
+  ABRB_NOUNROLL
+  for (int r = 0; r < nrhs; ++r) {
+    T b[S_];
+    ABRB_NOUNROLL
+    for (int i = 0; i < S_; ++i) b[i] = y[r * S_ + i];
+    ABRB_NOUNROLL
+    for (int pass = 0; pass < 2; ++pass) {
+      ABRB_NOUNROLL
+      for (int e = 0; e < m; ++e) {
+        T d = T(0);
+        ABRB_NOUNROLL
+        for (int i = 0; i < S_; ++i) d += V[e][i] * b[i];
+        ABRB_NOUNROLL
+        for (int i = 0; i < S_; ++i) b[i] -= d * V[e][i];
+      }
+      if (pass == 0) solve(b);
+    }
+    ABRB_NOUNROLL
+    for (int i = 0; i < S_; ++i) x[r * S_ + i] = b[i];
+  }
+  return true;
 }
 
 }  // namespace abrb

@@ -126,82 +126,20 @@ ABRB_HD T wrap_pm_pi(T d) {
 // defer_slow: if the state needs the eigen-decomposition (truncating pinv) path, return true WITHOUT computing u;
 // the kernel re-runs such states densely packed in a second pass (they are a few % of random states but would
 // otherwise drag most warps through the divergent slow path).  Returns false when u has been produced.
-// `K`: caller-provided kinematic scratch (registers or shared memory).
+// `K`: caller-provided kinematic scratch (registers or shared memory).  Once the dynamics are done its t_k / z_k
+// slots are overwritten IN PLACE by the task Jacobian (column k of J only needs t_k, z_k), which later becomes
+// A = (L^-1 J^T)^T; so J, A never occupy registers of their own.
 template <typename T, int N, int KD, bool PLANT, class K_>
 ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, const T *dq, const T *target,
                        const T *tv, T *u, T *train, T *ddq, K_ &K, bool defer_slow = false) {
   constexpr bool ORTHO = K_::kOrtho;
+  typedef typename K_::S SL;
   walk<T, N>(P, q, O.frame, K);
   const int dep = frame_dep<N>(O.frame);
   T pF[3];
   frame_point(K.F, O.xoff, pF);
 
-  // ---- joint-space dynamics
-  T M[N][N], g[N], cdq[N];
-  if (PLANT || O.use_C)
-    dynamics<T, N, false, true>(P, K, dq, M, g, nullptr, cdq);
-  else
-    dynamics<T, N, false, false>(P, K, dq, M, g, nullptr, nullptr);
-  ABRB_UNROLL
-  for (int a = 0; a < N; ++a)
-    ABRB_UNROLL
-  for (int b = 0; b < N; ++b)
-    if (b < a) M[a][b] = M[b][a];
-
-  // secondary controllers that are M.(something): accumulate the something
-  T wn[N];
-  bool any_null = false, any_avoid = false;
-  ABRB_UNROLL
-  for (int k = 0; k < N; ++k) wn[k] = T(0);
-  for (int i = 0; i < O.n_null; ++i) {
-    const NullK<T, N> &Z = O.nul[i];
-    any_null = true;
-    if (Z.kind == kNullDamping) {
-      ABRB_UNROLL
-      for (int k = 0; k < N; ++k) wn[k] -= Z.kv * dq[k];
-    } else if (Z.kind == kNullResting) {
-      ABRB_UNROLL
-      for (int k = 0; k < N; ++k) {
-        const T qt = ((Z.rest_mask >> k) & 1u) ? wrap_pm_pi(Z.rest[k] - q[k]) : T(0);
-        wn[k] += Z.kp * qt - Z.kv * dq[k];
-      }
-    } else {
-      any_avoid = true;
-    }
-  }
-  T Mdq[N], un[N];
-  ABRB_UNROLL
-  for (int a = 0; a < N; ++a) {
-    T s1 = T(0), s2 = T(0);
-    ABRB_UNROLL
-    for (int b = 0; b < N; ++b) {
-      s1 += M[a][b] * dq[b];
-      s2 += M[a][b] * wn[b];
-    }
-    Mdq[a] = s1;
-    un[a] = s2;
-  }
-
-  // ---- Jacobian rows of the controlled DOF (uncontrolled rows are zeroed; osc.py:242-244)
-  T A[KD][N];  // first J[KD][N], then (L^-1 J^T)^T
-  T xdot[KD];
-  {
-    T J[6][N];
-    jacobian<T, N>(K, pF, dep, J);
-    ABRB_UNROLL
-    for (int r = 0; r < KD; ++r) {
-      const bool on = (O.dof_mask >> r) & 1u;
-      T s = T(0);
-      ABRB_UNROLL
-      for (int k = 0; k < N; ++k) {
-        A[r][k] = on ? J[r][k] : T(0);
-        s += A[r][k] * dq[k];
-      }
-      xdot[r] = s;
-    }
-  }
-
-  // ---- task-space error (osc.py:250-272)
+  // ---- task-space error (osc.py:250-272), needs only the frame
   T err[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
   if (O.dof_mask & 7u) {
     ABRB_UNROLL
@@ -256,14 +194,81 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
       err[3 + c] *= O.ko;
     }
   }
+
+  // ---- joint-space dynamics
+  T M[N][N], g[N], cdq[N];
+  if (PLANT || O.use_C)
+    dynamics_Mg<T, N, true>(P, K, dq, M, g, cdq);
+  else
+    dynamics_Mg<T, N, false>(P, K, dq, M, g, nullptr);
+  ABRB_UNROLL
+  for (int a = 0; a < N; ++a)
+    ABRB_UNROLL
+  for (int b = 0; b < N; ++b)
+    if (b < a) M[a][b] = M[b][a];
+
+  // secondary controllers that are M.(something): accumulate the something
+  T wn[N];
+  bool any_null = false, any_avoid = false;
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) wn[k] = T(0);
+  for (int i = 0; i < O.n_null; ++i) {
+    const NullK<T, N> &Z = O.nul[i];
+    any_null = true;
+    if (Z.kind == kNullDamping) {
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) wn[k] -= Z.kv * dq[k];
+    } else if (Z.kind == kNullResting) {
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) {
+        const T qt = ((Z.rest_mask >> k) & 1u) ? wrap_pm_pi(Z.rest[k] - q[k]) : T(0);
+        wn[k] += Z.kp * qt - Z.kv * dq[k];
+      }
+    } else {
+      any_avoid = true;
+    }
+  }
   // velocity compensation (osc.py:275-282): joint space if the target velocity is all zero
   bool tv_zero = true;
   if (tv != nullptr) {
     ABRB_UNROLL
     for (int c = 0; c < 6; ++c) tv_zero = tv_zero && (tv[c] == T(0));
   }
+  T un[N];
   ABRB_UNROLL
-  for (int k = 0; k < N; ++k) u[k] = tv_zero ? -O.kv * Mdq[k] : T(0);
+  for (int a = 0; a < N; ++a) {
+    T s1 = T(0), s2 = T(0);
+    ABRB_UNROLL
+    for (int b = 0; b < N; ++b) {
+      s1 += M[a][b] * dq[b];
+      s2 += M[a][b] * wn[b];
+    }
+    u[a] = tv_zero ? -O.kv * s1 : T(0);
+    un[a] = s2;
+  }
+
+  // ---- task Jacobian rows of the controlled DOF written in place over t_k / z_k (osc.py:242-244):
+  //      A(r,k): r<3 -> slot kT+3k+r,  r>=3 -> slot kZ+3k+r-3.  Uncontrolled rows are zero.
+  auto Aslot = [](int r, int k) { return r < 3 ? SL::kT + 3 * k + r : SL::kZ + 3 * k + (r - 3); };
+  T xdot[KD];
+  ABRB_UNROLL
+  for (int r = 0; r < KD; ++r) xdot[r] = T(0);
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) {
+    T tk[3], zk[3], d[3], v[3];
+    K.t(k, tk);
+    K.z(k, zk);
+    ABRB_UNROLL
+    for (int c = 0; c < 3; ++c) d[c] = pF[c] - tk[c];
+    omega_apply(K, k, d, v);
+    const bool on = k < dep;
+    ABRB_UNROLL
+    for (int r = 0; r < KD; ++r) {
+      const T val = (on && ((O.dof_mask >> r) & 1u)) ? (r < 3 ? v[r < 3 ? r : 0] : zk[r < 3 ? 0 : r - 3]) : T(0);
+      K.s.st(Aslot(r, k), val);
+      xdot[r] += val * dq[k];
+    }
+  }
   if (!tv_zero) {
     ABRB_UNROLL
     for (int r = 0; r < KD; ++r) err[r] += O.kv * (xdot[r] - tv[r]);
@@ -276,28 +281,38 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
   T Mi[N];
   chol<T, N>(M, Mi);
   ABRB_UNROLL
-  for (int r = 0; r < KD; ++r) fwd_solve<T, N>(M, Mi, A[r]);
+  for (int r = 0; r < KD; ++r) {
+    T row[N];
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) row[k] = K.s.ld(Aslot(r, k));
+    fwd_solve<T, N>(M, Mi, row);
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) K.s.st(Aslot(r, k), row[k]);
+  }
   T S[KD][KD];
   ABRB_UNROLL
-  for (int a = 0; a < KD; ++a)
+  for (int a = 0; a < KD; ++a) {
+    T ra[N];
     ABRB_UNROLL
-  for (int b = 0; b < KD; ++b) {
-    if (b <= a) {
-      T s = T(0);
-      ABRB_UNROLL
-      for (int k = 0; k < N; ++k) s += A[a][k] * A[b][k];
-      const bool on = ((O.dof_mask >> a) & 1u) && ((O.dof_mask >> b) & 1u);
-      S[a][b] = on ? s : (a == b ? T(1) : T(0));
-      S[b][a] = S[a][b];
+    for (int k = 0; k < N; ++k) ra[k] = K.s.ld(Aslot(a, k));
+    ABRB_UNROLL
+    for (int b = 0; b < KD; ++b) {
+      if (b <= a) {
+        T s = T(0);
+        ABRB_UNROLL
+        for (int k = 0; k < N; ++k) s += ra[k] * K.s.ld(Aslot(b, k));
+        const bool on = ((O.dof_mask >> a) & 1u) && ((O.dof_mask >> b) & 1u);
+        S[a][b] = on ? s : (a == b ? T(1) : T(0));
+        S[b][a] = S[a][b];
+      }
     }
   }
   // ---- Mx: inverse if |det| >= threshold else pinv(rcond = threshold*0.1)   (osc.py:138-145)
-  T Sc[KD][KD];
+  T Sc[KD][KD], Si[KD];
   ABRB_UNROLL
   for (int a = 0; a < KD; ++a)
     ABRB_UNROLL
   for (int b = 0; b < KD; ++b) Sc[a][b] = S[a][b];
-  T Si[KD];
   const bool pd = chol<T, KD>(Sc, Si);
   T det = T(1);
   ABRB_UNROLL
@@ -329,23 +344,41 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
       fwd_solve<T, KD>(Sc, Si, v);
       bwd_solve<T, KD>(Sc, Si, v);
     } else {
-      T Sf[KD * KD], yi[KD], xo[KD];
+      // static indices only (a rolled loop would force S and v into local memory for the whole function)
+      T Sf[KD * KD], Lf[KD * KD], idg[KD], yi[KD], xo[KD];
+      const unsigned mask = O.dof_mask & ((1u << KD) - 1u);
+      T tr = T(0);
+      ABRB_UNROLL
+      for (int a = 0; a < KD; ++a) tr += ((mask >> a) & 1u) ? S[a][a] : T(0);
+      ABRB_UNROLL
       for (int a = 0; a < KD; ++a) {
         yi[a] = v[a];
-        for (int b = 0; b < KD; ++b) Sf[a * KD + b] = S[a][b];
+        idg[a] = Si[a];
+        ABRB_UNROLL
+        for (int b = 0; b < KD; ++b) {
+          Sf[a * KD + b] = (a == b && !((mask >> a) & 1u)) ? tr : S[a][b];  // inactive rows: diag >= lambda_max
+          Lf[a * KD + b] = Sc[a][b];
+        }
       }
-      pinv_apply_sym<T, KD>(Sf, O.dof_mask & ((1u << KD) - 1u), rcond, yi, xo);
+      // cheap route first (inertia counts + inverse iteration); full Jacobi eigen-decomposition as the fallback
+      if (!(pd && pinv_solve_fast<T, KD>(Sf, Lf, idg, mask, rcond, 1, yi, xo))) {
+        ABRB_UNROLL
+        for (int a = 0; a < KD; ++a)
+          if (!((mask >> a) & 1u)) Sf[a * KD + a] = T(1);
+        pinv_apply_sym<T, KD>(Sf, mask, rcond, yi, xo);
+      }
+      ABRB_UNROLL
       for (int a = 0; a < KD; ++a) v[a] = xo[a];
     }
   };
-  // u -= J^T Mx y ;  J^T x = L (A^T x)   (osc.py:285-288)
+  // J^T x = L (A^T x)   (osc.py:285-288)
   auto JT_apply = [&](const T *x, T *out) {
     T w[N];
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) {
       T s = T(0);
       ABRB_UNROLL
-      for (int r = 0; r < KD; ++r) s += A[r][k] * x[r];
+      for (int r = 0; r < KD; ++r) s += K.s.ld(Aslot(r, k)) * x[r];
       w[k] = s;
     }
     ABRB_UNROLL
@@ -380,12 +413,17 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
   if (any_null) {
     if (any_avoid) {
       T Lf[N * N];
+      ABRB_UNROLL
       for (int a = 0; a < N; ++a)
-        for (int b = 0; b < N; ++b) Lf[a * N + b] = M[a][b];
+        ABRB_UNROLL
+      for (int b = 0; b < N; ++b) Lf[a * N + b] = M[a][b];
       for (int i = 0; i < O.n_null; ++i) {
         if (O.nul[i].kind == kNullAvoid) {
-          T ua[N];
-          avoid_generate<T, N, ORTHO>(P, O.nul[i], q, Lf, ua);
+          T ua[N], qa[N];  // private copies: only these (not the caller's register arrays) have their address taken
+          ABRB_UNROLL
+          for (int k = 0; k < N; ++k) qa[k] = q[k];
+          avoid_generate<T, N, ORTHO>(P, O.nul[i], qa, Lf, ua);
+          ABRB_UNROLL
           for (int k = 0; k < N; ++k) un[k] += ua[k];
         }
       }
@@ -398,7 +436,7 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
     for (int r = 0; r < KD; ++r) {
       T s = T(0);
       ABRB_UNROLL
-      for (int k = 0; k < N; ++k) s += A[r][k] * w[k];
+      for (int k = 0; k < N; ++k) s += K.s.ld(Aslot(r, k)) * w[k];
       z[r] = ((O.dof_mask >> r) & 1u) ? s : T(0);
     }
     mx_apply(z);
@@ -424,7 +462,7 @@ ABRB_HD void null_state(const ChainK<T, N> &P, const NullK<T, N> &Z, const T *q,
   constexpr bool ORTHO = K_::kOrtho;
   walk<T, N>(P, q, 0, K);
   T M[N][N], g[N];
-  dynamics<T, N, false, false>(P, K, dq, M, g, nullptr, nullptr);
+  dynamics_Mg<T, N, false>(P, K, dq, M, g, nullptr);
   ABRB_UNROLL
   for (int a = 0; a < N; ++a)
     ABRB_UNROLL
@@ -434,9 +472,16 @@ ABRB_HD void null_state(const ChainK<T, N> &P, const NullK<T, N> &Z, const T *q,
     T Mi[N];
     chol<T, N>(M, Mi);
     T Lf[N * N];
+    ABRB_UNROLL
     for (int a = 0; a < N; ++a)
-      for (int b = 0; b < N; ++b) Lf[a * N + b] = M[a][b];
-    avoid_generate<T, N, ORTHO>(P, Z, q, Lf, u);
+      ABRB_UNROLL
+    for (int b = 0; b < N; ++b) Lf[a * N + b] = M[a][b];
+    T ua[N], qa[N];
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) qa[k] = q[k];
+    avoid_generate<T, N, ORTHO>(P, Z, qa, Lf, ua);
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) u[k] = ua[k];
     return;
   }
   T w[N];

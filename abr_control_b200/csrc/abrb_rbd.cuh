@@ -18,78 +18,83 @@ enum : unsigned {
   kWantC = 1u << 9,
 };
 
-template <typename T, int N>
-struct RbdOut {
-  T Tx[3];
-  T Tm[16];
-  T R[9];
-  T Tinv[16];
-  T quat[4];
-  T J[6][N];
-  T dJ[6][N];
-  T M[N][N];
-  T g[N];
-  T C[N][N];
-};
+enum { kOutTx = 0, kOutT, kOutR, kOutTinv, kOutQuat, kOutJ, kOutdJ, kOutM, kOutg, kOutC, kOutCount };
 
-// DYN: M and/or g requested; CMAT: C requested (implies the dynamics pass).  `want` is uniform over the launch.
+// One state.  Every requested quantity is handed to `out.template put<LEN>(which, record)` as soon as it is complete,
+// so that no more than one or two output records are ever live in registers (the kernel's `put` stages the record
+// through shared memory and writes it out coalesced; the host test shim copies it into an array).
+// DYN: M and/or g requested; CMAT: C requested.  `want` is uniform over the launch.
 // `K` is the caller-provided kinematic scratch (register- or shared-memory-backed, see Kin in abrb_math.cuh).
-template <typename T, int N, bool DYN, bool CMAT, class K_>
+template <typename T, int N, bool DYN, bool CMAT, class K_, class Out>
 ABRB_HD void rbd_state(const ChainK<T, N> &P, const T *q, const T *dq, int frame, const T *xoff, unsigned want,
-                       RbdOut<T, N> &o, K_ &K) {
+                       K_ &K, Out &out) {
   walk<T, N>(P, q, frame, K);
   const int dep = frame_dep<N>(frame);
   T pF[3];
   frame_point(K.F, xoff, pF);
-  if (want & kWantTx) {
-    ABRB_UNROLL
-    for (int c = 0; c < 3; ++c) o.Tx[c] = pF[c];
-  }
+  if (want & kWantTx) out.template put<3>(kOutTx, pF);
   if (want & kWantT) {  // base_config.py:338-369
+    T Tm[16];
     ABRB_UNROLL
-    for (int i = 0; i < 12; ++i) o.Tm[i] = K.F[i];
-    o.Tm[12] = o.Tm[13] = o.Tm[14] = T(0);
-    o.Tm[15] = T(1);
+    for (int i = 0; i < 12; ++i) Tm[i] = K.F[i];
+    Tm[12] = Tm[13] = Tm[14] = T(0);
+    Tm[15] = T(1);
+    out.template put<16>(kOutT, Tm);
   }
-  if (want & kWantR) {  // base_config.py:647-676
-    ABRB_UNROLL
-    for (int r = 0; r < 3; ++r)
-      ABRB_UNROLL
-    for (int c = 0; c < 3; ++c) o.R[r * 3 + c] = K.F[r * 4 + c];
-  }
-  if (want & kWantTinv) {  // [[R^T, -R^T t],[0,1]] with the TRANSPOSE (base_config.py:820-824)
-    ABRB_UNROLL
-    for (int r = 0; r < 3; ++r) {
-      T s = T(0);
-      ABRB_UNROLL
-      for (int c = 0; c < 3; ++c) {
-        o.Tinv[r * 4 + c] = K.F[c * 4 + r];
-        s -= K.F[c * 4 + r] * K.F[c * 4 + 3];
-      }
-      o.Tinv[r * 4 + 3] = s;
-    }
-    o.Tinv[12] = o.Tinv[13] = o.Tinv[14] = T(0);
-    o.Tinv[15] = T(1);
-  }
-  if (want & kWantQuat) {  // base_config.py:304-318
+  if (want & (kWantR | kWantQuat)) {  // base_config.py:647-676, :304-318
     T R[9];
     ABRB_UNROLL
     for (int r = 0; r < 3; ++r)
       ABRB_UNROLL
     for (int c = 0; c < 3; ++c) R[r * 3 + c] = K.F[r * 4 + c];
-    quat_from_R(R, o.quat);
+    if (want & kWantR) out.template put<9>(kOutR, R);
+    if (want & kWantQuat) {
+      T qt[4];
+      quat_from_R(R, qt);
+      out.template put<4>(kOutQuat, qt);
+    }
+  }
+  if (want & kWantTinv) {  // [[R^T, -R^T t],[0,1]] with the TRANSPOSE (base_config.py:820-824)
+    T Ti[16];
+    ABRB_UNROLL
+    for (int r = 0; r < 3; ++r) {
+      T s = T(0);
+      ABRB_UNROLL
+      for (int c = 0; c < 3; ++c) {
+        Ti[r * 4 + c] = K.F[c * 4 + r];
+        s -= K.F[c * 4 + r] * K.F[c * 4 + 3];
+      }
+      Ti[r * 4 + 3] = s;
+    }
+    Ti[12] = Ti[13] = Ti[14] = T(0);
+    Ti[15] = T(1);
+    out.template put<16>(kOutTinv, Ti);
   }
   if (want & (kWantJ | kWantdJ)) {
-    jacobian<T, N>(K, pF, dep, o.J);
-    if (want & kWantdJ) jacobian_dot<T, N>(K, o.J, dq, dep, o.dJ);
+    T J[6][N];
+    jacobian<T, N>(K, pF, dep, J);
+    if (want & kWantJ) out.template put<6 * N>(kOutJ, &J[0][0]);
+    if (want & kWantdJ) {
+      T dJ[6][N];
+      jacobian_dot<T, N>(K, J, dq, dep, dJ);
+      out.template put<6 * N>(kOutdJ, &dJ[0][0]);
+    }
   }
-  if (DYN || CMAT) {
-    dynamics<T, N, CMAT, false>(P, K, dq, o.M, o.g, o.C, nullptr);
+  if (DYN) {
+    T M[N][N], g[N];
+    dynamics_Mg<T, N, false>(P, K, dq, M, g, nullptr);
     ABRB_UNROLL
     for (int a = 0; a < N; ++a)
       ABRB_UNROLL
     for (int b = 0; b < N; ++b)
-      if (b < a) o.M[a][b] = o.M[b][a];
+      if (b < a) M[a][b] = M[b][a];
+    if (want & kWantM) out.template put<N * N>(kOutM, &M[0][0]);
+    if (want & kWantg) out.template put<N>(kOutg, g);
+  }
+  if (CMAT) {
+    T C[N][N];
+    dynamics_C<T, N>(P, K, dq, C);
+    out.template put<N * N>(kOutC, &C[0][0]);
   }
 }
 

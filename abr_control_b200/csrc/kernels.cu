@@ -56,32 +56,41 @@ struct MaxI {
   static constexpr int value = A > B ? A : B;
 };
 
-// Write one LEN-element record per lane to `out[(warp_b0 + lane) * LEN + e]` through the warp's staging
-// tile: conflict-light scalar writes into smem, then a linear, fully coalesced copy-out (16-byte vectors
-// for full warps).
+// Write one LEN-element record per lane to `out[(warp_b0 + lane) * LEN + e]` through the warp's staging tile.
+// The tile is element-major with a row pitch of 33 (`tile[e * 33 + lane]`): the per-lane writes are conflict-free
+// (consecutive lanes -> consecutive words) and so are the reads of the linear copy-out (consecutive output
+// elements -> pitch 33 -> distinct banks); the copy-out itself is perfectly coalesced (each warp instruction
+// writes 32 consecutive elements = whole 128-byte lines).
+constexpr int kPitch = 33;
 template <typename T, int LEN>
 __device__ __forceinline__ void store_records(T *__restrict__ out, int64_t warp_b0, int nvalid, const T *rec,
-                                              T *stage, int lane) {
-  __syncwarp();  // the tile aliases the warp's kinematic scratch: every lane must be done reading it
+                                              T *tile, int lane) {
+  __syncwarp();
 #pragma unroll
-  for (int e = 0; e < LEN; ++e) stage[lane * LEN + e] = rec[e];
+  for (int e = 0; e < LEN; ++e) tile[e * kPitch + lane] = rec[e];
   __syncwarp();
   T *dst = out + warp_b0 * LEN;
-  if (nvalid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-    constexpr int kVec = (32 * LEN * (int)sizeof(T)) / 16;
-    const float4 *s4 = reinterpret_cast<const float4 *>(stage);
-    float4 *d4 = reinterpret_cast<float4 *>(dst);
+  const int total = nvalid * LEN;
 #pragma unroll
-    for (int i = 0; i < (kVec + 31) / 32; ++i) {
-      const int idx = i * 32 + lane;
-      if (idx < kVec) d4[idx] = s4[idx];
-    }
-  } else {
-    const int total = nvalid * LEN;
-    for (int i = lane; i < total; i += 32) dst[i] = stage[i];
+  for (int it = 0; it < LEN; ++it) {
+    const int i = it * 32 + lane;
+    const int r = i / LEN, e = i - r * LEN;
+    if (i < total) dst[i] = tile[e * kPitch + r];
   }
-  __syncwarp();
 }
+
+// Output functor handed to rbd_state: stores each finished record immediately (keeps the live register set small)
+template <typename T>
+struct RbdSink {
+  T *ptr[kOutCount];
+  T *tile;
+  int64_t warp_b0;
+  int nvalid, lane;
+  template <int LEN>
+  __device__ __forceinline__ void put(int which, const T *rec) {
+    if (ptr[which] != nullptr) store_records<T, LEN>(ptr[which], warp_b0, nvalid, rec, tile, lane);
+  }
+};
 
 template <typename T>
 struct RbdArgs {
@@ -93,19 +102,40 @@ struct RbdArgs {
   T xoff[3];
 };
 
+// shared memory per warp: [ kinematic scratch (KSMEM only): kSlots x 32 ][ staging tile: kPitch x max record ]
+template <typename T, int N, bool ORTHO, bool KSMEM, int MAXREC>
+struct WarpSmem {
+  static constexpr int kKin = 32 * KinSel<T, N, ORTHO, KSMEM>::kSlots;
+  static constexpr int kTile = kPitch * MAXREC;
+  static constexpr int kElems = kKin + kTile;
+};
+
 template <typename T, int N, bool ORTHO, bool DYN, bool CMAT, bool KSMEM>
 __global__ void __launch_bounds__(kBlock)
 rbd_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ RbdArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef KinSel<T, N, ORTHO, KSMEM> KS;
-  constexpr int kRegion = 32 * MaxI<MaxRecord<N>::value, KS::kSlots>::value;
+  typedef WarpSmem<T, N, ORTHO, KSMEM, MaxRecord<N>::value> WS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T *stage = reinterpret_cast<T *>(smem_raw) + warp * kRegion;
+  T *region = reinterpret_cast<T *>(smem_raw) + warp * WS::kElems;
   typename KS::type K;
-  KS::bind(K, stage, lane);
+  KS::bind(K, region, lane);
+  RbdSink<T> sink;
+  sink.ptr[kOutTx] = a.Tx;
+  sink.ptr[kOutT] = a.Tm;
+  sink.ptr[kOutR] = a.R;
+  sink.ptr[kOutTinv] = a.Tinv;
+  sink.ptr[kOutQuat] = a.quat;
+  sink.ptr[kOutJ] = a.J;
+  sink.ptr[kOutdJ] = a.dJ;
+  sink.ptr[kOutM] = a.M;
+  sink.ptr[kOutg] = a.g;
+  sink.ptr[kOutC] = a.C;
+  sink.tile = region + WS::kKin;
+  sink.lane = lane;
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
     const int64_t warp_b0 = base + warp * 32;
-    if (warp_b0 >= a.B) break;  // whole warp out of range (uniform per warp)
+    if (warp_b0 >= a.B) break;  // whole warp out of range (uniform per warp; no block barriers in this kernel)
     const int64_t rem = a.B - warp_b0;
     const int nvalid = rem < 32 ? (int)rem : 32;
     const int64_t b = warp_b0 + (lane < nvalid ? lane : nvalid - 1);  // clamp: idle lanes redo the last state
@@ -115,22 +145,9 @@ rbd_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ RbdAr
       q[k] = a.q[b * N + k];
       dq[k] = a.dq != nullptr ? a.dq[b * N + k] : T(0);
     }
-    RbdOut<T, N> o;
-    rbd_state<T, N, DYN, CMAT>(P, q, dq, a.frame, a.xoff, a.want, o, K);
-    if (a.Tx) store_records<T, 3>(a.Tx, warp_b0, nvalid, o.Tx, stage, lane);
-    if (a.Tm) store_records<T, 16>(a.Tm, warp_b0, nvalid, o.Tm, stage, lane);
-    if (a.R) store_records<T, 9>(a.R, warp_b0, nvalid, o.R, stage, lane);
-    if (a.Tinv) store_records<T, 16>(a.Tinv, warp_b0, nvalid, o.Tinv, stage, lane);
-    if (a.quat) store_records<T, 4>(a.quat, warp_b0, nvalid, o.quat, stage, lane);
-    if (a.J) store_records<T, 6 * N>(a.J, warp_b0, nvalid, &o.J[0][0], stage, lane);
-    if (a.dJ) store_records<T, 6 * N>(a.dJ, warp_b0, nvalid, &o.dJ[0][0], stage, lane);
-    if (DYN || CMAT) {
-      if (a.M) store_records<T, N * N>(a.M, warp_b0, nvalid, &o.M[0][0], stage, lane);
-      if (a.g) store_records<T, N>(a.g, warp_b0, nvalid, o.g, stage, lane);
-    }
-    if (CMAT) {
-      if (a.C) store_records<T, N * N>(a.C, warp_b0, nvalid, &o.C[0][0], stage, lane);
-    }
+    sink.warp_b0 = warp_b0;
+    sink.nvalid = nvalid;
+    rbd_state<T, N, DYN, CMAT>(P, q, dq, a.frame, a.xoff, a.want, K, sink);
   }
 }
 
@@ -153,11 +170,12 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
   __shared__ int s_cnt;
   __shared__ int s_idx[kBlock];
   typedef KinSel<T, N, ORTHO, KSMEM> KS;
-  constexpr int kRegion = 32 * MaxI<N, KS::kSlots>::value;
+  typedef WarpSmem<T, N, ORTHO, KSMEM, N> WS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T *stage = reinterpret_cast<T *>(smem_raw) + warp * kRegion;
+  T *region = reinterpret_cast<T *>(smem_raw) + warp * WS::kElems;
+  T *stage = region + WS::kKin;
   typename KS::type K;
-  KS::bind(K, stage, lane);
+  KS::bind(K, region, lane);
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
@@ -225,11 +243,12 @@ rollout_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ O
                const __grid_constant__ RolloutArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef KinSel<T, N, ORTHO, KSMEM> KS;
-  constexpr int kRegion = 32 * MaxI<N, KS::kSlots>::value;
+  typedef WarpSmem<T, N, ORTHO, KSMEM, N> WS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T *stage = reinterpret_cast<T *>(smem_raw) + warp * kRegion;
+  T *region = reinterpret_cast<T *>(smem_raw) + warp * WS::kElems;
+  T *stage = region + WS::kKin;
   typename KS::type K;
-  KS::bind(K, stage, lane);
+  KS::bind(K, region, lane);
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
     const int64_t warp_b0 = base + warp * 32;
     if (warp_b0 >= a.B) break;
@@ -274,7 +293,7 @@ null_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ Null
             const __grid_constant__ NullArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T *stage = reinterpret_cast<T *>(smem_raw) + warp * 32 * N;
+  T *stage = reinterpret_cast<T *>(smem_raw) + warp * kPitch * N;
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
     const int64_t warp_b0 = base + warp * 32;
     if (warp_b0 >= a.B) break;
@@ -335,7 +354,7 @@ int rbd_go(const ChainHost &h, const RbdCall &c, unsigned want) {
   a.want = want;
   for (int i = 0; i < 3; ++i) a.xoff[i] = c.xoff ? T(c.xoff[i]) : T(0);
   constexpr bool KSMEM = sizeof(T) == 8;
-  const size_t smem = (size_t)kWarps * 32 * MaxI<MaxRecord<N>::value, KinSel<T, N, ORTHO, KSMEM>::kSlots>::value * sizeof(T);
+  const size_t smem = (size_t)kWarps * WarpSmem<T, N, ORTHO, KSMEM, MaxRecord<N>::value>::kElems * sizeof(T);
   auto kern = rbd_kernel<T, N, ORTHO, DYN, CMAT, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
   if (e != cudaSuccess) return (int)e;
@@ -385,7 +404,7 @@ int osc_go(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
   a.target_stride = c.target_stride;
   a.tv_stride = c.tv_stride;
   constexpr bool KSMEM = sizeof(T) == 8;
-  const size_t smem = (size_t)kWarps * 32 * MaxI<N, KinSel<T, N, ORTHO, KSMEM>::kSlots>::value * sizeof(T);
+  const size_t smem = (size_t)kWarps * WarpSmem<T, N, ORTHO, KSMEM, N>::kElems * sizeof(T);
   auto kern = osc_kernel<T, N, ORTHO, KD, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
   if (e != cudaSuccess) return (int)e;
@@ -412,7 +431,7 @@ int rollout_go(const ChainHost &h, const abrb_osc_params &p, const RolloutCall &
   a.steps = c.steps;
   a.dt = T(c.dt);
   constexpr bool KSMEM = sizeof(T) == 8;
-  const size_t smem = (size_t)kWarps * 32 * MaxI<N, KinSel<T, N, ORTHO, KSMEM>::kSlots>::value * sizeof(T);
+  const size_t smem = (size_t)kWarps * WarpSmem<T, N, ORTHO, KSMEM, N>::kElems * sizeof(T);
   auto kern = rollout_kernel<T, N, ORTHO, KD, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
   if (e != cudaSuccess) return (int)e;
@@ -432,7 +451,7 @@ int null_go(const ChainHost &h, const abrb_null_params &z, const NullCall &c) {
   a.dq = static_cast<const T *>(c.dq);
   a.u = static_cast<T *>(c.u);
   a.B = c.B;
-  const size_t smem = (size_t)kWarps * 32 * N * sizeof(T);
+  const size_t smem = (size_t)kWarps * kPitch * N * sizeof(T);
   null_kernel<T, N, ORTHO><<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, Z, a);
   count_launch();
   return (int)cudaGetLastError();

@@ -3,6 +3,7 @@
 // the kernel arithmetic can be unit-tested against the oracle on a machine without a GPU
 // (`pytest -m "not gpu"`).  The shipped library (libabrb.so) reaches the same functions only through
 // CUDA kernels.
+#include <type_traits>
 #include <vector>
 
 #include "../../abr_control_b200/csrc/abrb_host.hpp"
@@ -11,6 +12,17 @@
 using namespace abrb;
 
 namespace {
+
+template <typename T>
+struct Sink {  // receives each finished per-state record from rbd_state
+  double *dst[kOutCount];
+  int64_t b;
+  template <int LEN>
+  void put(int which, const T *rec) {
+    if (dst[which])
+      for (int i = 0; i < LEN; ++i) dst[which][b * LEN + i] = double(rec[i]);
+  }
+};
 
 template <typename T, int N, bool ORTHO>
 void rbd_loop(const ChainHost &h, int frame, const double *xoff, const double *q, const double *dq, int64_t B,
@@ -25,23 +37,9 @@ void rbd_loop(const ChainHost &h, int frame, const double *xoff, const double *q
       qq[k] = T(q[b * N + k]);
       dd[k] = dq ? T(dq[b * N + k]) : T(0);
     }
-    RbdOut<T, N> o;
+    Sink<T> sink{{Tx, Tm, R, Tinv, quat, J, dJ, M, g, C}, b};
     Kin<T, N, ORTHO> K;
-    rbd_state<T, N, true, true>(P, qq, dd, frame, xo, want, o, K);
-    auto put = [&](double *dst, const T *src, int len) {
-      if (dst)
-        for (int i = 0; i < len; ++i) dst[b * len + i] = double(src[i]);
-    };
-    put(Tx, o.Tx, 3);
-    put(Tm, o.Tm, 16);
-    put(R, o.R, 9);
-    put(Tinv, o.Tinv, 16);
-    put(quat, o.quat, 4);
-    put(J, &o.J[0][0], 6 * N);
-    put(dJ, &o.dJ[0][0], 6 * N);
-    put(M, &o.M[0][0], N * N);
-    put(g, o.g, N);
-    put(C, &o.C[0][0], N * N);
+    rbd_state<T, N, true, true>(P, qq, dd, frame, xo, want, K, sink);
   }
 }
 
@@ -156,4 +154,38 @@ int hs_null(const abrb_chain_desc *d, const abrb_null_params *z, int f32, int fo
 }
 
 int hs_frame_id(int n, const char *name) { return parse_frame(n, name); }
+
+// x = pinv(S, rcond) y for a 6x6 (K=6) or 3x3 (K=3) symmetric S with identity rows outside `active`.
+// which = 0: cheap route (returns 1 if it was conclusive, 0 if it asked for the fallback); which = 1: Jacobi.
+int hs_pinv(int K, const double *S, unsigned active, double rcond, const double *y, double *x, int which, int f32) {
+  auto run = [&](auto tag, auto kc) -> int {
+    typedef decltype(tag) T;
+    constexpr int KK = decltype(kc)::value;
+    T Sm[KK][KK], Sc[KK][KK], Si[KK], Sf[KK * KK], Lf[KK * KK], yi[KK], xo[KK];
+    T tr = 0;
+    for (int a = 0; a < KK; ++a) {
+      yi[a] = T(y[a]);
+      for (int b = 0; b < KK; ++b) Sm[a][b] = Sc[a][b] = T(S[a * KK + b]);
+      if ((active >> a) & 1u) tr += Sm[a][a];
+    }
+    const bool pd = chol<T, KK>(Sc, Si);
+    for (int a = 0; a < KK; ++a)
+      for (int b = 0; b < KK; ++b) {
+        Sf[a * KK + b] = (a == b && !((active >> a) & 1u)) ? tr : Sm[a][b];
+        Lf[a * KK + b] = Sc[a][b];
+      }
+    int ok = 1;
+    if (which == 0) {
+      ok = pd && pinv_solve_fast<T, KK>(Sf, Lf, Si, active, T(rcond), 1, yi, xo);
+    } else {
+      for (int a = 0; a < KK * KK; ++a) Sf[a] = T(S[a]);
+      pinv_apply_sym<T, KK>(Sf, active, T(rcond), yi, xo);
+    }
+    for (int a = 0; a < KK; ++a) x[a] = ok ? double(xo[a]) : 0.0;
+    return ok;
+  };
+  if (K == 6) return f32 ? run(float(0), std::integral_constant<int, 6>()) : run(double(0), std::integral_constant<int, 6>());
+  if (K == 3) return f32 ? run(float(0), std::integral_constant<int, 3>()) : run(double(0), std::integral_constant<int, 3>());
+  return -1;
+}
 }
