@@ -73,6 +73,9 @@ class OSC(Controller):
                 raise TypeError("null_controllers must be abr_control_b200 Damping / RestingConfig / AvoidObstacles")
             nc._owners.append(self)
         self.training_signal = None
+        # the reference stores `training_signal` on every call (osc.py:297); for large host batches it doubles the
+        # device-to-host traffic, so throughput-minded callers may switch it off
+        self.record_training_signal = True
         self._handle = None
 
     # ------------------------------------------------------------------ native handle
@@ -140,10 +143,10 @@ class OSC(Controller):
                               torch.cuda.current_stream(qa.device).cuda_stream))
         else:
             u = np.empty_like(qa)
-            tr = np.empty_like(qa)
+            tr = np.empty_like(qa) if (self.record_training_signal or single) else None
             fn = L.abrb_osc_generate_host_f32 if f32 else L.abrb_osc_generate_host_f64
             _lib.check(fn(h, fid, xo, qa.ctypes.data, dqa.ctypes.data, tgt.ctypes.data, tstride, _batch.ptr(tv),
-                          tvstride, u.ctypes.data, tr.ctypes.data, B))
+                          tvstride, u.ctypes.data, _batch.ptr(tr), B))
         if single:
             self.training_signal = np.array(tr[0], dtype=np.float64) if kind == "numpy" else tr[0]
             return np.array(u[0], dtype=np.float64) if kind == "numpy" else u[0]

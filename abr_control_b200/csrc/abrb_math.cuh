@@ -780,188 +780,225 @@ ABRB_HD_NOINLINE void pinv_apply_sym(const T *Sin, unsigned active, T rcond, con
   }
 }
 
+// ------------------------------------------------------------------------------------------------
 // Fast route to x = pinv(S, rcond) y for a symmetric positive definite (possibly very ill-conditioned) S whose
 // Cholesky factor L (with reciprocal diagonal invd) is already known.  numpy.linalg.pinv drops the eigenvalues
 // <= rcond * lambda_max; instead of a full eigen-decomposition this
-//   1. brackets lambda_max: Rayleigh quotient rho of a few power iterations (a lower bound) and an inertia count
-//      (LDL^T of S - sigma I, Sylvester) proving that no eigenvalue exceeds rho (1 + 1e-7);
-//   2. counts the eigenvalues below the cutoff with the same inertia count, at both ends of the bracket;
+//   1. brackets lambda_max: Rayleigh quotient rho after power iteration with (S/tr)^8 (a lower bound) and an
+//      inertia count (LDL^T of S - sigma I, Sylvester's law) proving that no eigenvalue exceeds rho (1 + delta);
+//   2. counts the eigenvalues below the cutoff with the same inertia count at both ends of the bracket;
 //   3. finds the (at most 2) truncated eigenvectors by inverse subspace iteration with L and projects them out:
 //      x = P S^-1 P y,  P = I - V V^T.
 // Returns false whenever a step is inconclusive (more than 2 truncated eigenvalues, slow convergence, a vanishing
 // pivot, the bracket straddling an eigenvalue): the caller then falls back to the Jacobi routine above.
 // Rows not in `active` must be decoupled from the rest (zero off-diagonals) with a diagonal >= lambda_max, and
-// y must vanish on them.  All loops are rolled: this is a rare path and must stay small.
+// y must vanish on them.  Everything is unrolled on registers (about 1.5 k flops): this is what keeps the
+// "second pass" over the deferred states of a tile short.
 template <typename T, int S_>
-ABRB_HD_NOINLINE bool pinv_solve_fast(const T *Sin, const T *Lin, const T *invd, unsigned active, T rcond, int nrhs,
-                                      const T *y, T *x) {
-  T Sm[S_][S_], L[S_][S_], idg[S_];
-  ABRB_NOUNROLL
-  for (int i = 0; i < S_; ++i) {
-    idg[i] = invd[i];
-    ABRB_NOUNROLL
-    for (int j = 0; j < S_; ++j) {
-      Sm[i][j] = Sin[i * S_ + j];
-      L[i][j] = Lin[i * S_ + j];
-    }
-  }
-  // number of eigenvalues of S below sigma (-1: inconclusive)
-  auto count_below = [&](T sigma) -> int {
-    T D[S_][S_];
-    ABRB_NOUNROLL
+ABRB_HD int inertia_below(const T (*Sm)[S_], T sigma) {  // #eigenvalues of Sm below sigma, -1 if inconclusive
+  T D[S_][S_];
+  ABRB_UNROLL
+  for (int i = 0; i < S_; ++i)
+    ABRB_UNROLL
+  for (int j = 0; j < S_; ++j)
+    if (j >= i) D[i][j] = Sm[i][j] - (i == j ? sigma : T(0));
+  int neg = 0;
+  bool bad = false;
+  ABRB_UNROLL
+  for (int j = 0; j < S_; ++j) {
+    const T d = D[j][j];
+    bad = bad || !(abs_t(d) > T(0));
+    neg += d < T(0) ? 1 : 0;
+    const T inv = T(1) / d;
+    ABRB_UNROLL
     for (int i = 0; i < S_; ++i) {
-      ABRB_NOUNROLL
-      for (int j = 0; j < S_; ++j) D[i][j] = Sm[i][j] - (i == j ? sigma : T(0));
-    }
-    int neg = 0;
-    ABRB_NOUNROLL
-    for (int j = 0; j < S_; ++j) {
-      const T d = D[j][j];
-      if (!(abs_t(d) > T(0))) return -1;
-      if (d < T(0)) ++neg;
-      const T inv = T(1) / d;
-      ABRB_NOUNROLL
-      for (int i = j + 1; i < S_; ++i) {
-        const T f = D[i][j] * inv;
-        ABRB_NOUNROLL
-        for (int k = j + 1; k < S_; ++k) D[i][k] -= f * D[j][k];
+      if (i > j) {
+        const T f = D[j][i] * inv;  // symmetric: use the upper triangle only
+        ABRB_UNROLL
+        for (int k = 0; k < S_; ++k)
+          if (k >= i) D[i][k] -= f * D[j][k];
       }
     }
-    return neg;
-  };
-  auto solve = [&](T *b) {  // b <- S^-1 b
-    ABRB_NOUNROLL
-    for (int i = 0; i < S_; ++i) {
-      T acc = b[i];
-      ABRB_NOUNROLL
-      for (int k = 0; k < i; ++k) acc -= L[i][k] * b[k];
-      b[i] = acc * idg[i];
+  }
+  return bad ? -1 : neg;
+}
+
+template <typename T, int S_>
+ABRB_HD void sym_square(const T (*A)[S_], T (*B)[S_]) {  // B = A A for symmetric A
+  ABRB_UNROLL
+  for (int i = 0; i < S_; ++i)
+    ABRB_UNROLL
+  for (int j = 0; j < S_; ++j) {
+    if (j >= i) {
+      T acc = T(0);
+      ABRB_UNROLL
+      for (int k = 0; k < S_; ++k) acc += A[i][k] * A[k][j];
+      B[i][j] = acc;
+      B[j][i] = acc;
     }
-    ABRB_NOUNROLL
-    for (int i = S_ - 1; i >= 0; --i) {
-      T acc = b[i];
-      ABRB_NOUNROLL
-      for (int k = i + 1; k < S_; ++k) acc -= L[k][i] * b[k];
-      b[i] = acc * idg[i];
-    }
-  };
-  // ---- 1. lambda_max on the active block
-  T v[S_], w[S_];
-  ABRB_NOUNROLL
+  }
+}
+
+template <typename T, int S_>
+ABRB_HD bool pinv_solve_fast(const T (*Sm)[S_], const T (*L)[S_], const T *invd, unsigned active, T rcond,
+                             const T *y, T *x) {
+  // ---- 1. lambda_max of the active block
+  T tr = T(0);
+  ABRB_UNROLL
+  for (int i = 0; i < S_; ++i) tr += ((active >> i) & 1u) ? Sm[i][i] : T(0);
+  if (!(tr > T(0))) return false;
+  const T itr = T(1) / tr;
+  T P1[S_][S_], P2[S_][S_];
+  ABRB_UNROLL
+  for (int i = 0; i < S_; ++i)
+    ABRB_UNROLL
+  for (int j = 0; j < S_; ++j) {
+    const bool on = ((active >> i) & 1u) && ((active >> j) & 1u);
+    P1[i][j] = on ? Sm[i][j] * itr : T(0);  // active block scaled to trace 1 (all powers stay <= 1)
+  }
+  sym_square<T, S_>(P1, P2);  // ^2
+  sym_square<T, S_>(P2, P1);  // ^4
+  sym_square<T, S_>(P1, P2);  // ^8
+  T v[S_];
+  ABRB_UNROLL
   for (int i = 0; i < S_; ++i) v[i] = ((active >> i) & 1u) ? T(1) + T(0.37) * T(i) : T(0);
-  T rho = T(0);
-  ABRB_NOUNROLL
-  for (int it = 0; it < 20; ++it) {
-    T nn = T(0), num = T(0), den = T(0);
-    ABRB_NOUNROLL
+  ABRB_UNROLL
+  for (int it = 0; it < 4; ++it) {
+    T w[S_], nn = T(0);
+    ABRB_UNROLL
     for (int i = 0; i < S_; ++i) {
       T acc = T(0);
-      ABRB_NOUNROLL
-      for (int j = 0; j < S_; ++j) acc += Sm[i][j] * v[j];
-      w[i] = ((active >> i) & 1u) ? acc : T(0);
-      num += v[i] * w[i];
-      den += v[i] * v[i];
-      nn += w[i] * w[i];
+      ABRB_UNROLL
+      for (int j = 0; j < S_; ++j) acc += P2[i][j] * v[j];
+      w[i] = acc;
+      nn += acc * acc;
     }
-    rho = num / den;
+    if (!(nn > T(0))) return false;
     const T sc = T(1) / sqrt_t(nn);
-    ABRB_NOUNROLL
+    ABRB_UNROLL
     for (int i = 0; i < S_; ++i) v[i] = w[i] * sc;
   }
-  const T slack = sizeof(T) == 8 ? T(1e-7) : T(1e-3);
-  // every eigenvalue of the active block must lie below rho (1 + slack); inactive rows carry diag >= lambda_max,
-  // so test the active block only by temporarily shrinking them out of the way
-  int n_act = 0, n_inact_below = 0;
-  ABRB_NOUNROLL
+  T rho = T(0);
+  ABRB_UNROLL
   for (int i = 0; i < S_; ++i) {
-    if ((active >> i) & 1u) ++n_act;
-    else if (Sm[i][i] < rho * (T(1) + slack)) ++n_inact_below;
+    T acc = T(0);
+    ABRB_UNROLL
+    for (int j = 0; j < S_; ++j) acc += Sm[i][j] * v[j];
+    rho += v[i] * acc;  // v is unit and vanishes on inactive rows
   }
-  const int below_top = count_below(rho * (T(1) + slack));
-  if (below_top < 0 || below_top - n_inact_below != n_act) return false;  // power iteration not converged
+  // bracket [rho, rho (1 + delta)]: all eigenvalues of the active block must lie below the upper end
+  int n_act = 0;
+  ABRB_UNROLL
+  for (int i = 0; i < S_; ++i) n_act += ((active >> i) & 1u) ? 1 : 0;
+  const T deltas[3] = {sizeof(T) == 8 ? T(1e-7) : T(2e-4), T(2e-3), T(5e-2)};
+  T delta = T(-1);
+  ABRB_UNROLL
+  for (int t = 0; t < 3; ++t) {
+    if (delta < T(0)) {
+      const T top = rho * (T(1) + deltas[t]);
+      int inact_below = 0;
+      ABRB_UNROLL
+      for (int i = 0; i < S_; ++i) inact_below += (!((active >> i) & 1u) && Sm[i][i] < top) ? 1 : 0;
+      const int c = inertia_below<T, S_>(Sm, top);
+      if (c >= 0 && c - inact_below == n_act) delta = deltas[t];
+    }
+  }
+  if (delta < T(0)) return false;
   // ---- 2. how many eigenvalues are truncated
-  const int m_lo = count_below(rcond * rho), m_hi = count_below(rcond * rho * (T(1) + slack));
+  const int m_lo = inertia_below<T, S_>(Sm, rcond * rho), m_hi = inertia_below<T, S_>(Sm, rcond * rho * (T(1) + delta));
   if (m_lo < 0 || m_lo != m_hi || m_lo > 2) return false;
   const int m = m_lo;
-  // ---- 3. truncated eigenvectors by inverse subspace iteration
-  T V[2][S_];
-  ABRB_NOUNROLL
-  for (int e = 0; e < 2; ++e) {
-    ABRB_NOUNROLL
-    for (int i = 0; i < S_; ++i) V[e][i] = ((active >> i) & 1u) ? T(1) / T(1 + i + 2 * e) + (e == 1 && (i & 1) ? T(-0.7) : T(0.1)) : T(0);
+  // ---- 3. truncated eigenvectors by inverse subspace iteration (two vectors are carried, the second is only
+  //         used when m == 2)
+  T V0[S_], V1[S_];
+  ABRB_UNROLL
+  for (int i = 0; i < S_; ++i) {
+    const bool on = (active >> i) & 1u;
+    V0[i] = on ? T(1) / T(1 + i) + T(0.1) : T(0);
+    V1[i] = on ? ((i & 1) ? T(-0.7) : T(0.45)) + T(0.05) * T(i) : T(0);
   }
-  T theta[2] = {T(0), T(0)};
-  ABRB_NOUNROLL
-  for (int it = 0; it < 10; ++it) {
-    ABRB_NOUNROLL
-    for (int e = 0; e < m; ++e) {
-      solve(V[e]);
-      ABRB_NOUNROLL
-      for (int f = 0; f < e; ++f) {  // Gram-Schmidt against the previous vector
-        T d = T(0);
-        ABRB_NOUNROLL
-        for (int i = 0; i < S_; ++i) d += V[f][i] * V[e][i];
-        ABRB_NOUNROLL
-        for (int i = 0; i < S_; ++i) V[e][i] -= d * V[f][i];
-      }
+  if (m >= 1) {
+    ABRB_UNROLL
+    for (int it = 0; it < 16; ++it) {
+      fwd_solve<T, S_>(L, invd, V0);
+      bwd_solve<T, S_>(L, invd, V0);
       T nn = T(0);
-      ABRB_NOUNROLL
-      for (int i = 0; i < S_; ++i) nn += V[e][i] * V[e][i];
+      ABRB_UNROLL
+      for (int i = 0; i < S_; ++i) nn += V0[i] * V0[i];
       if (!(nn > T(0))) return false;
-      const T sc = T(1) / sqrt_t(nn);
-      ABRB_NOUNROLL
-      for (int i = 0; i < S_; ++i) V[e][i] *= sc;
-    }
-  }
-  // Ritz values + residual check: the span must be invariant (||S v - theta v|| tiny relative to the cutoff)
-  ABRB_NOUNROLL
-  for (int e = 0; e < m; ++e) {
-    T r2 = T(0), th = T(0);
-    ABRB_NOUNROLL
-    for (int i = 0; i < S_; ++i) {
-      T acc = T(0);
-      ABRB_NOUNROLL
-      for (int j = 0; j < S_; ++j) acc += Sm[i][j] * V[e][j];
-      w[i] = acc;
-      th += V[e][i] * acc;
-    }
-    theta[e] = th;
-    ABRB_NOUNROLL
-    for (int i = 0; i < S_; ++i) {
-      T r = w[i] - th * V[e][i];
-      if (m == 2) {  // for two vectors only the span needs to be invariant
-        const int o = 1 - e;
-        T c = T(0);
-        ABRB_NOUNROLL
-        for (int j = 0; j < S_; ++j) c += V[o][j] * w[j];
-        r -= c * V[o][i];
+      T sc = T(1) / sqrt_t(nn);
+      ABRB_UNROLL
+      for (int i = 0; i < S_; ++i) V0[i] *= sc;
+      if (m == 2) {
+        fwd_solve<T, S_>(L, invd, V1);
+        bwd_solve<T, S_>(L, invd, V1);
+        T d = T(0);
+        ABRB_UNROLL
+        for (int i = 0; i < S_; ++i) d += V0[i] * V1[i];
+        nn = T(0);
+        ABRB_UNROLL
+        for (int i = 0; i < S_; ++i) {
+          V1[i] -= d * V0[i];
+          nn += V1[i] * V1[i];
+        }
+        if (!(nn > T(0))) return false;
+        sc = T(1) / sqrt_t(nn);
+        ABRB_UNROLL
+        for (int i = 0; i < S_; ++i) V1[i] *= sc;
       }
-      r2 += r * r;
+    }
+    // the span must be invariant: || S v - (span component) || tiny relative to the cutoff
+    T w0[S_], w1[S_], a00 = T(0), a01 = T(0), a11 = T(0);
+    ABRB_UNROLL
+    for (int i = 0; i < S_; ++i) {
+      T acc0 = T(0), acc1 = T(0);
+      ABRB_UNROLL
+      for (int j = 0; j < S_; ++j) {
+        acc0 += Sm[i][j] * V0[j];
+        acc1 += Sm[i][j] * V1[j];
+      }
+      w0[i] = acc0;
+      w1[i] = acc1;
+      a00 += V0[i] * acc0;
+      a01 += V1[i] * acc0;
+      a11 += V1[i] * acc1;
+    }
+    T r0 = T(0), r1 = T(0);
+    ABRB_UNROLL
+    for (int i = 0; i < S_; ++i) {
+      const T e0 = w0[i] - a00 * V0[i] - (m == 2 ? a01 * V1[i] : T(0));
+      const T e1 = w1[i] - a11 * V1[i] - a01 * V0[i];
+      r0 += e0 * e0;
+      r1 += e1 * e1;
     }
     const T tol = (sizeof(T) == 8 ? T(1e-9) : T(1e-4)) * rcond * rho;
-    if (!(r2 <= tol * tol)) return false;
+    if (!(r0 <= tol * tol)) return false;
+    if (m == 2 && !(r1 <= tol * tol)) return false;
   }
   // ---- 4. x = P S^-1 P y
-  ABRB_NOUNROLL
-  for (int r = 0; r < nrhs; ++r) {
-    T b[S_];
-    ABRB_NOUNROLL
-    for (int i = 0; i < S_; ++i) b[i] = y[r * S_ + i];
-    ABRB_NOUNROLL
-    for (int pass = 0; pass < 2; ++pass) {
-      ABRB_NOUNROLL
-      for (int e = 0; e < m; ++e) {
-        T d = T(0);
-        ABRB_NOUNROLL
-        for (int i = 0; i < S_; ++i) d += V[e][i] * b[i];
-        ABRB_NOUNROLL
-        for (int i = 0; i < S_; ++i) b[i] -= d * V[e][i];
+  T b[S_];
+  ABRB_UNROLL
+  for (int i = 0; i < S_; ++i) b[i] = y[i];
+  ABRB_UNROLL
+  for (int pass = 0; pass < 2; ++pass) {
+    if (m >= 1) {
+      T d0 = T(0), d1 = T(0);
+      ABRB_UNROLL
+      for (int i = 0; i < S_; ++i) {
+        d0 += V0[i] * b[i];
+        d1 += V1[i] * b[i];
       }
-      if (pass == 0) solve(b);
+      if (m < 2) d1 = T(0);
+      ABRB_UNROLL
+      for (int i = 0; i < S_; ++i) b[i] -= d0 * V0[i] + d1 * V1[i];
     }
-    ABRB_NOUNROLL
-    for (int i = 0; i < S_; ++i) x[r * S_ + i] = b[i];
+    if (pass == 0) {
+      fwd_solve<T, S_>(L, invd, b);
+      bwd_solve<T, S_>(L, invd, b);
+    }
   }
+  ABRB_UNROLL
+  for (int i = 0; i < S_; ++i) x[i] = b[i];
   return true;
 }
 

@@ -344,27 +344,31 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
       fwd_solve<T, KD>(Sc, Si, v);
       bwd_solve<T, KD>(Sc, Si, v);
     } else {
-      // static indices only (a rolled loop would force S and v into local memory for the whole function)
-      T Sf[KD * KD], Lf[KD * KD], idg[KD], yi[KD], xo[KD];
+      // cheap register-resident route first (inertia counts + inverse iteration, abrb_math.cuh); the rolled,
+      // local-memory Jacobi eigen-decomposition only when that is inconclusive.  Static indices everywhere: a
+      // rolled loop over S or v here would force them into local memory for the whole function.
       const unsigned mask = O.dof_mask & ((1u << KD) - 1u);
-      T tr = T(0);
-      ABRB_UNROLL
-      for (int a = 0; a < KD; ++a) tr += ((mask >> a) & 1u) ? S[a][a] : T(0);
-      ABRB_UNROLL
-      for (int a = 0; a < KD; ++a) {
-        yi[a] = v[a];
-        idg[a] = Si[a];
+      T xo[KD];
+      bool done = false;
+      if (pd) {
+        T tr = T(0);
         ABRB_UNROLL
-        for (int b = 0; b < KD; ++b) {
-          Sf[a * KD + b] = (a == b && !((mask >> a) & 1u)) ? tr : S[a][b];  // inactive rows: diag >= lambda_max
-          Lf[a * KD + b] = Sc[a][b];
-        }
-      }
-      // cheap route first (inertia counts + inverse iteration); full Jacobi eigen-decomposition as the fallback
-      if (!(pd && pinv_solve_fast<T, KD>(Sf, Lf, idg, mask, rcond, 1, yi, xo))) {
+        for (int a = 0; a < KD; ++a) tr += ((mask >> a) & 1u) ? S[a][a] : T(0);
+        T Sb[KD][KD];  // inactive rows: diagonal >= lambda_max so that they are never counted as truncated
         ABRB_UNROLL
         for (int a = 0; a < KD; ++a)
-          if (!((mask >> a) & 1u)) Sf[a * KD + a] = T(1);
+          ABRB_UNROLL
+        for (int b = 0; b < KD; ++b) Sb[a][b] = (a == b && !((mask >> a) & 1u)) ? tr : S[a][b];
+        done = pinv_solve_fast<T, KD>(Sb, Sc, Si, mask, rcond, v, xo);
+      }
+      if (!done) {
+        T Sf[KD * KD], yi[KD];
+        ABRB_UNROLL
+        for (int a = 0; a < KD; ++a) {
+          yi[a] = v[a];
+          ABRB_UNROLL
+          for (int b = 0; b < KD; ++b) Sf[a * KD + b] = S[a][b];
+        }
         pinv_apply_sym<T, KD>(Sf, mask, rcond, yi, xo);
       }
       ABRB_UNROLL

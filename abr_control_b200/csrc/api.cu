@@ -64,10 +64,15 @@ struct Workspace {
   void *ptr = nullptr;
   size_t cap = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t lanes[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of the *_host OSC call
   int ensure(size_t bytes) {
     if (stream == nullptr) {
       cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
       if (e != cudaSuccess) return (int)e;
+      for (auto &l : lanes) {
+        e = cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return (int)e;
+      }
     }
     if (bytes <= cap) return 0;
     if (ptr) cudaFree(ptr);
@@ -290,18 +295,38 @@ static int osc_generate_host(const abrb_osc *c, int frame_id, const double *x_of
   auto take = [&](size_t bytes) { char *p = base + off; off += align_up(bytes); return (void *)p; };
   void *d_q = take(sz_state), *d_dq = take(sz_state), *d_u = take(sz_state), *d_tr = take(sz_state);
   void *d_t = take(sz_t), *d_tv = tv ? take(sz_tv) : nullptr;
-  cudaStream_t s = g_ws.stream;
-  cudaMemcpyAsync(d_q, q, sz_state, cudaMemcpyHostToDevice, s);
-  cudaMemcpyAsync(d_dq, dq, sz_state, cudaMemcpyHostToDevice, s);
-  cudaMemcpyAsync(d_t, target, sz_t, cudaMemcpyHostToDevice, s);
-  if (tv) cudaMemcpyAsync(d_tv, tv, sz_tv, cudaMemcpyHostToDevice, s);
-  rc = osc_generate(c, frame_id, x_off, d_q, d_dq, d_t, target_stride, d_tv, tv_stride, d_u, train ? d_tr : nullptr, B,
-                    s, f32);
-  if (rc) return rc;
-  cudaMemcpyAsync(u, d_u, sz_state, cudaMemcpyDeviceToHost, s);
-  if (train) cudaMemcpyAsync(train, d_tr, sz_state, cudaMemcpyDeviceToHost, s);
-  cudaError_t ce = cudaStreamSynchronize(s);
-  return ce ? cuda_fail(ce, "abrb_osc_generate_host") : ABRB_OK;
+  // Chunked 3-stage pipeline over three streams: the H2D copy of chunk c+1 overlaps the kernel of chunk c and the
+  // D2H copy of chunk c-1 (the copy engines are full duplex), so a large batch costs ~max(H2D, kernel, D2H).
+  const size_t row = n * es;
+  // chunks stay large: a launch is latency bound below ~64k states, so splitting smaller batches only adds latency
+  const int64_t chunk = B <= 131072 ? B : ((B + 3) / 4 + 127) / 128 * 128;
+  if (!target_stride) cudaMemcpyAsync(d_t, target, sz_t, cudaMemcpyHostToDevice, g_ws.stream);
+  if (tv && !tv_stride) cudaMemcpyAsync(d_tv, tv, sz_tv, cudaMemcpyHostToDevice, g_ws.stream);
+  cudaError_t ce = cudaStreamSynchronize(g_ws.stream);
+  if (ce) return cuda_fail(ce, "abrb_osc_generate_host");
+  int lane = 0;
+  for (int64_t b0 = 0; b0 < B; b0 += chunk, lane = (lane + 1) % 3) {
+    const int64_t nb = B - b0 < chunk ? B - b0 : chunk;
+    cudaStream_t s = g_ws.lanes[lane];
+    const size_t off_s = (size_t)b0 * row, off_t = (size_t)b0 * 6 * es;
+    auto at = [](const void *p, size_t o) { return (const void *)((const char *)p + o); };
+    auto atw = [](void *p, size_t o) { return (void *)((char *)p + o); };
+    cudaMemcpyAsync(atw(d_q, off_s), at(q, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(atw(d_dq, off_s), at(dq, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, s);
+    if (target_stride) cudaMemcpyAsync(atw(d_t, off_t), at(target, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s);
+    if (tv && tv_stride) cudaMemcpyAsync(atw(d_tv, off_t), at(tv, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s);
+    rc = osc_generate(c, frame_id, x_off, at(d_q, off_s), at(d_dq, off_s), target_stride ? at(d_t, off_t) : d_t,
+                      target_stride, tv ? (tv_stride ? at(d_tv, off_t) : d_tv) : nullptr, tv_stride, atw(d_u, off_s),
+                      train ? atw(d_tr, off_s) : nullptr, nb, s, f32);
+    if (rc) return rc;
+    cudaMemcpyAsync(atw(u, off_s), at(d_u, off_s), (size_t)nb * row, cudaMemcpyDeviceToHost, s);
+    if (train) cudaMemcpyAsync(atw(train, off_s), at(d_tr, off_s), (size_t)nb * row, cudaMemcpyDeviceToHost, s);
+  }
+  for (auto &l : g_ws.lanes) {
+    ce = cudaStreamSynchronize(l);
+    if (ce) return cuda_fail(ce, "abrb_osc_generate_host");
+  }
+  return ABRB_OK;
 }
 
 int abrb_osc_generate_host_f64(const abrb_osc *c, int frame_id, const double *x_off, const double *q, const double *dq,

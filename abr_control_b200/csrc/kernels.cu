@@ -159,16 +159,14 @@ struct OscArgs {
   int target_stride, tv_stride;
 };
 
-// Two passes per 128-state tile: pass 0 evaluates every state but defers the few that need the truncating
-// pseudo-inverse (eigen-decomposition) by queueing them in shared memory; pass 1 re-evaluates the queued states
-// densely packed on the first threads of the CTA, so the divergent slow path runs on full warps.
+// One pass: the few states that need the truncating pseudo-inverse take the register-resident inertia-count route
+// in line (about half the cost of the main path, so the divergence it causes is bounded); a block-level "defer and
+// re-run densely" scheme was measured slower on B200 because the other warps of the CTA idle at the barrier.
 template <typename T, int N, bool ORTHO, int KD, bool KSMEM>
 __global__ void __launch_bounds__(kBlock)
 osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
            const __grid_constant__ OscArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_cnt;
-  __shared__ int s_idx[kBlock];
   typedef KinSel<T, N, ORTHO, KSMEM> KS;
   typedef WarpSmem<T, N, ORTHO, KSMEM, N> WS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -177,52 +175,25 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
   typename KS::type K;
   KS::bind(K, region, lane);
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
     const int64_t warp_b0 = base + warp * 32;
+    if (warp_b0 >= a.B) break;  // uniform per warp; this kernel has no block barriers
     const int64_t rem = a.B - warp_b0;
-    const int nvalid = rem < 32 ? (rem > 0 ? (int)rem : 0) : 32;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      bool active;
-      int64_t b;
-      if (pass == 0) {
-        active = nvalid > 0;  // uniform per warp; idle lanes of a ragged warp redo its last state
-        b = warp_b0 + (lane < nvalid ? lane : nvalid - 1);
-      } else {
-        const int cnt = s_cnt;
-        if (cnt == 0) break;  // uniform per CTA
-        active = (int)threadIdx.x < cnt;
-        b = base + (active ? s_idx[threadIdx.x] : 0);
-      }
-      if (active) {
-        T q[N], dq[N], tg[6], tv[6], u[N], tr[N];
+    const int nvalid = rem < 32 ? (int)rem : 32;
+    const int64_t b = warp_b0 + (lane < nvalid ? lane : nvalid - 1);  // idle lanes of a ragged warp redo its last state
+    T q[N], dq[N], tg[6], tv[6], u[N], tr[N];
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-          q[k] = a.q[b * N + k];
-          dq[k] = a.dq[b * N + k];
-        }
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          tg[c] = a.target[b * a.target_stride + c];
-          tv[c] = a.tv != nullptr ? a.tv[b * a.tv_stride + c] : T(0);
-        }
-        const bool deferred =
-            osc_state<T, N, KD, false>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, u, tr, nullptr, K, pass == 0);
-        if (pass == 0) {
-          if (deferred && lane < nvalid) s_idx[atomicAdd(&s_cnt, 1)] = (int)threadIdx.x;
-          store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);  // deferred rows are rewritten in pass 1
-          if (a.train) store_records<T, N>(a.train, warp_b0, nvalid, tr, stage, lane);
-        } else {
-#pragma unroll
-          for (int k = 0; k < N; ++k) {
-            a.u[b * N + k] = u[k];
-            if (a.train) a.train[b * N + k] = tr[k];
-          }
-        }
-      }
-      __syncthreads();  // pass 0 -> 1: queue complete and pass-0 stores ordered before the rewrites
+    for (int k = 0; k < N; ++k) {
+      q[k] = a.q[b * N + k];
+      dq[k] = a.dq[b * N + k];
     }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      tg[c] = a.target[b * a.target_stride + c];
+      tv[c] = a.tv != nullptr ? a.tv[b * a.tv_stride + c] : T(0);
+    }
+    osc_state<T, N, KD, false>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, u, tr, nullptr, K);
+    store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);
+    if (a.train) store_records<T, N>(a.train, warp_b0, nvalid, tr, stage, lane);
   }
 }
 

@@ -132,18 +132,30 @@ def cpu_reference_run(n_evals, repeats=3):
     lib = ref_lib()
     if lib is not None:
         lib.ref_max_threads.restype = C.c_int
-        cores = int(lib.ref_max_threads())
+        online = int(lib.ref_max_threads())
+        try:
+            online = min(online, len(os.sched_getaffinity(0)))
+        except AttributeError:
+            pass
         cfg = osc_cfg()
         u = np.empty((n_evals, 6))
-        args = (C.byref(cfg), q.ctypes.data_as(C.c_void_p), dq.ctypes.data_as(C.c_void_p),
-                target.ctypes.data_as(C.c_void_p), C.c_long(n_evals), u.ctypes.data_as(C.c_void_p), C.c_int(cores))
-        lib.ref_ur5_osc_batch(*args)  # warm (page in, spawn threads once)
-        best = float("inf")
-        for _ in range(repeats):
+
+        def run(nthreads, count):
+            a = (C.byref(cfg), q.ctypes.data_as(C.c_void_p), dq.ctypes.data_as(C.c_void_p),
+                 target.ctypes.data_as(C.c_void_p), C.c_long(count), u.ctypes.data_as(C.c_void_p), C.c_int(nthreads))
             t0 = time.perf_counter()
-            lib.ref_ur5_osc_batch(*args)
-            best = min(best, time.perf_counter() - t0)
+            lib.ref_ur5_osc_batch(*a)
+            return time.perf_counter() - t0
+
+        # the box may expose more hardware threads than it lets us use: pick the best thread count on a short probe
+        probe = min(n_evals, 400_000)
+        run(online, probe)  # warm (page in)
+        cands = sorted({c for c in (1, online // 8, online // 4, online // 2, online) if c >= 1})
+        rates = {c: probe / min(run(c, probe) for _ in range(2)) for c in cands}
+        cores = max(rates, key=rates.get)
+        best = min(run(cores, n_evals) for _ in range(repeats))
         return dict(value=n_evals / best, unit=UNIT, cores=cores, kind="reference",
+                    threads_probe={str(k): round(v) for k, v in rates.items()}, hw_threads_online=online,
                     sample=f"{n_evals} UR5 OSC evals (same controller, seeded states), best of {repeats}, "
                            "reference-generated C for J/Tx/M/g/C/R + C restatement of the NumPy half, pthreads"), u, (q, dq, target)
     from oracle import osc_oracle
@@ -275,6 +287,7 @@ def run_ours(args):
     # ---- end to end through the public API with pinned HOST buffers (H2D + kernel + D2H inside every call)
     hq, hdq, htg = (torch.as_tensor(a).pin_memory() for a in synth(B, n, 77 + rank))
     nq, ndq, ntg = hq.numpy(), hdq.numpy(), htg.numpy()
+    ctrlr.record_training_signal = False  # the side channel for DynamicsAdaptation is not part of the metric
     for _ in range(3):
         ctrlr.generate(nq, ndq, ntg)
     fence()
@@ -364,9 +377,9 @@ def run_ours(args):
                    "l2": f"inputs rotate over a ring of {n_sets} buffer sets ({ring_mb:.0f} MB > 126 MB L2)"},
         "clocks": clocks,
         "gpu_launches": int(launches),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * 18 * 8), "d2h_bytes_per_step": int(B * 6 * 8 * 2),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * 18 * 8), "d2h_bytes_per_step": int(B * 6 * 8),
                 "steps": e2e_steps, "how": "OSC.generate(q, dq, target) on pinned host NumPy buffers -> abrb_osc_generate_host_f64 "
-                                           "(H2D, kernel, D2H of u and training_signal, stream sync inside every call); wall clock"},
+                                           "(chunked H2D / kernel / D2H pipeline and stream sync inside every call); wall clock"},
         "roofline": {"bound": "hbm", "achieved": (B * bytes_per_state / kernel_s / 1e9) if kernel_s else None,
                      "peak": hbm_peak, "unit": "GB/s",
                      "frac": (B * bytes_per_state / kernel_s / 1e9 / hbm_peak) if kernel_s else None, "traffic": traffic,

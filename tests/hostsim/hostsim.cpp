@@ -176,7 +176,10 @@ int hs_pinv(int K, const double *S, unsigned active, double rcond, const double 
       }
     int ok = 1;
     if (which == 0) {
-      ok = pd && pinv_solve_fast<T, KK>(Sf, Lf, Si, active, T(rcond), 1, yi, xo);
+      T Sb[KK][KK];
+      for (int a = 0; a < KK; ++a)
+        for (int b = 0; b < KK; ++b) Sb[a][b] = Sf[a * KK + b];
+      ok = pd && pinv_solve_fast<T, KK>(Sb, Sc, Si, active, T(rcond), yi, xo);
     } else {
       for (int a = 0; a < KK * KK; ++a) Sf[a] = T(S[a]);
       pinv_apply_sym<T, KK>(Sf, active, T(rcond), yi, xo);

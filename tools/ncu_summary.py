@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Condense an Nsight Compute report (.ncu-rep, read here with `ncu -i`) into a small text summary for profiles/.
+
+usage: tools/ncu_summary.py gpurun_out/prof.ncu-rep [--json out.json] > profiles/rNN_<kernel>.txt
+"""
+import csv
+import io
+import json
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed_op_local_ld.sum",
+    "smsp__inst_executed_op_local_st.sum", "sm__cycles_elapsed.max",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+]
+
+
+def main():
+    rep = sys.argv[1]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    H, U = rows[0], rows[1]
+    out = []
+    for r in rows[2:]:
+        d = {"kernel": r[H.index("Kernel Name")]}
+        for k in KEYS:
+            if k in H:
+                d[k] = (r[H.index(k)], U[H.index(k)])
+        out.append(d)
+    for d in out:
+        print(d["kernel"])
+        for k in KEYS:
+            if k in d:
+                print(f"  {k:85s} {d[k][0]:>16s} {d[k][1]}")
+        if "dram__bytes_read.sum" in d:
+            def mb(v):
+                x, u = v
+                x = float(x.replace(",", ""))
+                return x * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1, "Gbyte": 1e3}[u]
+            print(f"  -> DRAM traffic per launch: {mb(d['dram__bytes_read.sum']) + mb(d['dram__bytes_write.sum']):.2f} MB")
+        print()
+    if "--json" in sys.argv:
+        json.dump(out, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
