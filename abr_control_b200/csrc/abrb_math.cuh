@@ -83,6 +83,7 @@ struct RegStore {
   T v[COUNT];
   ABRB_HD T ld(int i) const { return v[i]; }
   ABRB_HD void st(int i, T x) { v[i] = x; }
+  ABRB_HD void sync() const {}
 };
 template <typename T, int COUNT>
 struct StridedStore {
@@ -90,6 +91,14 @@ struct StridedStore {
   int stride;
   ABRB_HD T ld(int i) const { return base[i * stride]; }
   ABRB_HD void st(int i, T x) { base[i * stride] = x; }
+  // Phase barrier of the CTA.  The kernels are ~10^4 straight-line instructions per state, far beyond the
+  // instruction caches, and profile as instruction-fetch bound; keeping the warps of a CTA inside the same code
+  // window makes them share the fetched lines.  Only called at points every thread of the CTA reaches.
+  ABRB_HD void sync() const {
+#if defined(__CUDA_ARCH__) && defined(ABRB_PHASE_SYNC)  // measured neutral on B200 (tools/kbench.py): off by default
+    __syncthreads();
+#endif
+  }
 };
 
 template <int N, bool ORTHO>
@@ -116,6 +125,7 @@ struct Kin {
     s.st(slot + 1, v[1]);
     s.st(slot + 2, v[2]);
   }
+  ABRB_HD void sync() const { s.sync(); }
   ABRB_HD void t(int k, T *o) const { ld3(S::kT + 3 * k, o); }
   ABRB_HD void z(int k, T *o) const { ld3(S::kZ + 3 * k, o); }
   ABRB_HD void pl(int l, T *o) const { ld3(S::kPl + 3 * l, o); }
@@ -392,6 +402,7 @@ ABRB_HD void dynamics_Mg(const ChainK<T, N> &P, const K_ &K, const T *dq, T (*M)
   ABRB_UNROLL
   for (int l = 1; l <= N; ++l) {
     T v[N][3];
+    K.sync();
     link_columns<T, N>(K, l, v);
     ABRB_UNROLL
     for (int b = 0; b < N; ++b) {
@@ -429,6 +440,7 @@ ABRB_HD void dynamics_Mg(const ChainK<T, N> &P, const K_ &K, const T *dq, T (*M)
     }
   }
   // ---- rotational part: M_ab += sum_c z_a[c] Wos[max(a,b)][c] z_b[c]
+  K.sync();
   T Z[N][3];
   ABRB_UNROLL
   for (int a = 0; a < N; ++a) K.z(a, Z[a]);
@@ -490,6 +502,7 @@ ABRB_HD void dynamics_C(const ChainK<T, N> &P, const K_ &K, const T *dq, T (*C)[
   ABRB_UNROLL
   for (int l = 1; l <= N; ++l) {
     T v[N][3];
+    K.sync();
     link_columns<T, N>(K, l, v);
     Wl.add(K, l - 1, dq[l - 1]);
     Spin<T, ORTHO> tail;
@@ -522,6 +535,7 @@ ABRB_HD void dynamics_C(const ChainK<T, N> &P, const K_ &K, const T *dq, T (*C)[
   ABRB_UNROLL
   for (int d = 0; d < N; ++d) {
     T dz[N][3], E[N];
+    K.sync();
     ABRB_UNROLL
     for (int a = 0; a < N; ++a) {
       E[a] = T(0);
@@ -918,62 +932,66 @@ ABRB_HD bool pinv_solve_fast(const T (*Sm)[S_], const T (*L)[S_], const T *invd,
     V1[i] = on ? ((i & 1) ? T(-0.7) : T(0.45)) + T(0.05) * T(i) : T(0);
   }
   if (m >= 1) {
-    ABRB_UNROLL
-    for (int it = 0; it < 16; ++it) {
-      fwd_solve<T, S_>(L, invd, V0);
-      bwd_solve<T, S_>(L, invd, V0);
-      T nn = T(0);
-      ABRB_UNROLL
-      for (int i = 0; i < S_; ++i) nn += V0[i] * V0[i];
-      if (!(nn > T(0))) return false;
-      T sc = T(1) / sqrt_t(nn);
-      ABRB_UNROLL
-      for (int i = 0; i < S_; ++i) V0[i] *= sc;
-      if (m == 2) {
-        fwd_solve<T, S_>(L, invd, V1);
-        bwd_solve<T, S_>(L, invd, V1);
-        T d = T(0);
-        ABRB_UNROLL
-        for (int i = 0; i < S_; ++i) d += V0[i] * V1[i];
-        nn = T(0);
-        ABRB_UNROLL
-        for (int i = 0; i < S_; ++i) {
-          V1[i] -= d * V0[i];
-          nn += V1[i] * V1[i];
-        }
-        if (!(nn > T(0))) return false;
-        sc = T(1) / sqrt_t(nn);
-        ABRB_UNROLL
-        for (int i = 0; i < S_; ++i) V1[i] *= sc;
-      }
-    }
-    // the span must be invariant: || S v - (span component) || tiny relative to the cutoff
-    T w0[S_], w1[S_], a00 = T(0), a01 = T(0), a11 = T(0);
-    ABRB_UNROLL
-    for (int i = 0; i < S_; ++i) {
-      T acc0 = T(0), acc1 = T(0);
-      ABRB_UNROLL
-      for (int j = 0; j < S_; ++j) {
-        acc0 += Sm[i][j] * V0[j];
-        acc1 += Sm[i][j] * V1[j];
-      }
-      w0[i] = acc0;
-      w1[i] = acc1;
-      a00 += V0[i] * acc0;
-      a01 += V1[i] * acc0;
-      a11 += V1[i] * acc1;
-    }
-    T r0 = T(0), r1 = T(0);
-    ABRB_UNROLL
-    for (int i = 0; i < S_; ++i) {
-      const T e0 = w0[i] - a00 * V0[i] - (m == 2 ? a01 * V1[i] : T(0));
-      const T e1 = w1[i] - a11 * V1[i] - a01 * V0[i];
-      r0 += e0 * e0;
-      r1 += e1 * e1;
-    }
+    // Blocks of inverse iterations until the span is invariant (|| S v - span component || tiny relative to the
+    // cutoff).  The loops over `blk`/`it` stay rolled (their bodies use static indices only): convergence normally
+    // takes one block because the truncated eigenvalues sit orders of magnitude below the kept ones.
     const T tol = (sizeof(T) == 8 ? T(1e-9) : T(1e-4)) * rcond * rho;
-    if (!(r0 <= tol * tol)) return false;
-    if (m == 2 && !(r1 <= tol * tol)) return false;
+    bool converged = false;
+    ABRB_NOUNROLL
+    for (int blk = 0; blk < 6 && !converged; ++blk) {
+      ABRB_NOUNROLL
+      for (int it = 0; it < 3; ++it) {
+        fwd_solve<T, S_>(L, invd, V0);
+        bwd_solve<T, S_>(L, invd, V0);
+        T nn = T(0);
+        ABRB_UNROLL
+        for (int i = 0; i < S_; ++i) nn += V0[i] * V0[i];
+        T sc = T(1) / sqrt_t(nn);
+        ABRB_UNROLL
+        for (int i = 0; i < S_; ++i) V0[i] *= sc;
+        if (m == 2) {
+          fwd_solve<T, S_>(L, invd, V1);
+          bwd_solve<T, S_>(L, invd, V1);
+          T d = T(0);
+          ABRB_UNROLL
+          for (int i = 0; i < S_; ++i) d += V0[i] * V1[i];
+          nn = T(0);
+          ABRB_UNROLL
+          for (int i = 0; i < S_; ++i) {
+            V1[i] -= d * V0[i];
+            nn += V1[i] * V1[i];
+          }
+          sc = T(1) / sqrt_t(nn);
+          ABRB_UNROLL
+          for (int i = 0; i < S_; ++i) V1[i] *= sc;
+        }
+      }
+      T w0[S_], w1[S_], a00 = T(0), a01 = T(0), a11 = T(0);
+      ABRB_UNROLL
+      for (int i = 0; i < S_; ++i) {
+        T acc0 = T(0), acc1 = T(0);
+        ABRB_UNROLL
+        for (int j = 0; j < S_; ++j) {
+          acc0 += Sm[i][j] * V0[j];
+          acc1 += Sm[i][j] * V1[j];
+        }
+        w0[i] = acc0;
+        w1[i] = acc1;
+        a00 += V0[i] * acc0;
+        a01 += V1[i] * acc0;
+        a11 += V1[i] * acc1;
+      }
+      T r0 = T(0), r1 = T(0);
+      ABRB_UNROLL
+      for (int i = 0; i < S_; ++i) {
+        const T e0 = w0[i] - a00 * V0[i] - (m == 2 ? a01 * V1[i] : T(0));
+        const T e1 = w1[i] - a11 * V1[i] - a01 * V0[i];
+        r0 += e0 * e0;
+        r1 += e1 * e1;
+      }
+      converged = (r0 <= tol * tol) && (m < 2 || r1 <= tol * tol);  // NaNs compare false
+    }
+    if (!converged) return false;
   }
   // ---- 4. x = P S^-1 P y
   T b[S_];

@@ -134,7 +134,9 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
                        const T *tv, T *u, T *train, T *ddq, K_ &K, bool defer_slow = false) {
   constexpr bool ORTHO = K_::kOrtho;
   typedef typename K_::S SL;
+  K.sync();
   walk<T, N>(P, q, O.frame, K);
+  K.sync();
   const int dep = frame_dep<N>(O.frame);
   T pF[3];
   frame_point(K.F, O.xoff, pF);
@@ -196,6 +198,7 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
   }
 
   // ---- joint-space dynamics
+  K.sync();
   T M[N][N], g[N], cdq[N];
   if (PLANT || O.use_C)
     dynamics_Mg<T, N, true>(P, K, dq, M, g, cdq);
@@ -247,6 +250,7 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
     un[a] = s2;
   }
 
+  K.sync();
   // ---- task Jacobian rows of the controlled DOF written in place over t_k / z_k (osc.py:242-244):
   //      A(r,k): r<3 -> slot kT+3k+r,  r>=3 -> slot kZ+3k+r-3.  Uncontrolled rows are zero.
   auto Aslot = [](int r, int k) { return r < 3 ? SL::kT + 3 * k + r : SL::kZ + 3 * k + (r - 3); };
@@ -277,6 +281,7 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
   ABRB_UNROLL
   for (int r = 0; r < KD; ++r) y[r] = ((O.dof_mask >> r) & 1u) ? err[r] : T(0);
 
+  K.sync();
   // ---- M = L L^T ;  A <- rows of (L^-1 J^T)^T ;  S = J M^-1 J^T = A A^T   (osc.py:136-137)
   T Mi[N];
   chol<T, N>(M, Mi);
@@ -307,6 +312,7 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
       }
     }
   }
+  K.sync();  // last common point: from here on the rare truncating-pinv lanes diverge
   // ---- Mx: inverse if |det| >= threshold else pinv(rcond = threshold*0.1)   (osc.py:138-145)
   T Sc[KD][KD], Si[KD];
   ABRB_UNROLL

@@ -28,7 +28,9 @@ enum { kOutTx = 0, kOutT, kOutR, kOutTinv, kOutQuat, kOutJ, kOutdJ, kOutM, kOutg
 template <typename T, int N, bool DYN, bool CMAT, class K_, class Out>
 ABRB_HD void rbd_state(const ChainK<T, N> &P, const T *q, const T *dq, int frame, const T *xoff, unsigned want,
                        K_ &K, Out &out) {
+  K.sync();
   walk<T, N>(P, q, frame, K);
+  K.sync();
   const int dep = frame_dep<N>(frame);
   T pF[3];
   frame_point(K.F, xoff, pF);
@@ -70,6 +72,7 @@ ABRB_HD void rbd_state(const ChainK<T, N> &P, const T *q, const T *dq, int frame
     Ti[15] = T(1);
     out.template put<16>(kOutTinv, Ti);
   }
+  K.sync();
   if (want & (kWantJ | kWantdJ)) {
     T J[6][N];
     jacobian<T, N>(K, pF, dep, J);
@@ -91,6 +94,7 @@ ABRB_HD void rbd_state(const ChainK<T, N> &P, const T *q, const T *dq, int frame
     if (want & kWantM) out.template put<N * N>(kOutM, &M[0][0]);
     if (want & kWantg) out.template put<N>(kOutg, g);
   }
+  K.sync();
   if (CMAT) {
     T C[N][N];
     dynamics_C<T, N>(P, K, dq, C);

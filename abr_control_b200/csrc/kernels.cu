@@ -22,6 +22,16 @@ namespace abrb {
 namespace {
 
 constexpr int kBlock = 128;
+// CTAs per SM the register allocator must allow.  Measured on B200 (tools/kbench.py, B = 65536): the fp64 kernels
+// are fastest with the full 255 registers (2 CTAs/SM; capping them spills and costs 20-50 %), the fp32 kernels with
+// 4 CTAs/SM (128 registers; the 6-DOF OSC kernel goes from 222 to 129 us).
+#ifndef ABRB_KSMEM_F32
+#define ABRB_KSMEM_F32 0  // 1: shared-memory kinematic scratch for the fp32 kernels too
+#endif
+template <typename T>
+struct MinBlocks {
+  static constexpr int value = sizeof(T) == 8 ? 2 : 4;
+};
 constexpr int kWarps = kBlock / 32;
 
 template <int N>
@@ -62,20 +72,32 @@ struct MaxI {
 // elements -> pitch 33 -> distinct banks); the copy-out itself is perfectly coalesced (each warp instruction
 // writes 32 consecutive elements = whole 128-byte lines).
 constexpr int kPitch = 33;
+// Records longer than kChunk elements go through the tile in slices of kChunk (the tile then needs only
+// kPitch * kChunk elements per warp, which is what lets three CTAs of the fp64 kernels share an SM); each slice is a
+// run of kChunk contiguous elements per record in global memory (>= 144 bytes for fp64).
+constexpr int kChunk = 18;
 template <typename T, int LEN>
 __device__ __forceinline__ void store_records(T *__restrict__ out, int64_t warp_b0, int nvalid, const T *rec,
                                               T *tile, int lane) {
-  __syncwarp();
-#pragma unroll
-  for (int e = 0; e < LEN; ++e) tile[e * kPitch + lane] = rec[e];
-  __syncwarp();
   T *dst = out + warp_b0 * LEN;
-  const int total = nvalid * LEN;
 #pragma unroll
-  for (int it = 0; it < LEN; ++it) {
-    const int i = it * 32 + lane;
-    const int r = i / LEN, e = i - r * LEN;
-    if (i < total) dst[i] = tile[e * kPitch + r];
+  for (int c0 = 0; c0 < LEN; c0 += kChunk) {
+    constexpr int kFull = kChunk;
+    const int ch = LEN - c0 < kFull ? LEN - c0 : kFull;  // compile-time after unrolling
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < kChunk; ++e)
+      if (e < ch) tile[e * kPitch + lane] = rec[c0 + e];
+    __syncwarp();
+    const int total = nvalid * ch;
+#pragma unroll
+    for (int it = 0; it < kChunk; ++it) {
+      if (it < ch) {
+        const int i = it * 32 + lane;
+        const int r = i / ch, e = i - r * ch;
+        if (i < total) dst[r * LEN + c0 + e] = tile[e * kPitch + r];
+      }
+    }
   }
 }
 
@@ -106,12 +128,12 @@ struct RbdArgs {
 template <typename T, int N, bool ORTHO, bool KSMEM, int MAXREC>
 struct WarpSmem {
   static constexpr int kKin = 32 * KinSel<T, N, ORTHO, KSMEM>::kSlots;
-  static constexpr int kTile = kPitch * MAXREC;
+  static constexpr int kTile = kPitch * (MAXREC < kChunk ? MAXREC : kChunk);
   static constexpr int kElems = kKin + kTile;
 };
 
 template <typename T, int N, bool ORTHO, bool DYN, bool CMAT, bool KSMEM>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, MinBlocks<T>::value)
 rbd_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ RbdArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef KinSel<T, N, ORTHO, KSMEM> KS;
@@ -134,11 +156,12 @@ rbd_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ RbdAr
   sink.tile = region + WS::kKin;
   sink.lane = lane;
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
+    // no early exit: every thread of the CTA takes part in the phase barriers; idle lanes / warps redo a valid state
     const int64_t warp_b0 = base + warp * 32;
-    if (warp_b0 >= a.B) break;  // whole warp out of range (uniform per warp; no block barriers in this kernel)
     const int64_t rem = a.B - warp_b0;
-    const int nvalid = rem < 32 ? (int)rem : 32;
-    const int64_t b = warp_b0 + (lane < nvalid ? lane : nvalid - 1);  // clamp: idle lanes redo the last state
+    const int nvalid = rem < 32 ? (rem > 0 ? (int)rem : 0) : 32;
+    const int64_t bb = warp_b0 + (lane < nvalid ? lane : nvalid - 1);
+    const int64_t b = bb < a.B ? (bb >= 0 ? bb : 0) : a.B - 1;
     T q[N], dq[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -163,7 +186,7 @@ struct OscArgs {
 // in line (about half the cost of the main path, so the divergence it causes is bounded); a block-level "defer and
 // re-run densely" scheme was measured slower on B200 because the other warps of the CTA idle at the barrier.
 template <typename T, int N, bool ORTHO, int KD, bool KSMEM>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, MinBlocks<T>::value)
 osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
            const __grid_constant__ OscArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -175,11 +198,12 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
   typename KS::type K;
   KS::bind(K, region, lane);
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
+    // no early exit: every thread of the CTA takes part in the phase barriers; idle lanes / warps redo a valid state
     const int64_t warp_b0 = base + warp * 32;
-    if (warp_b0 >= a.B) break;  // uniform per warp; this kernel has no block barriers
     const int64_t rem = a.B - warp_b0;
-    const int nvalid = rem < 32 ? (int)rem : 32;
-    const int64_t b = warp_b0 + (lane < nvalid ? lane : nvalid - 1);  // idle lanes of a ragged warp redo its last state
+    const int nvalid = rem < 32 ? (rem > 0 ? (int)rem : 0) : 32;
+    const int64_t bb = warp_b0 + (lane < nvalid ? lane : nvalid - 1);
+    const int64_t b = bb < a.B ? (bb >= 0 ? bb : 0) : a.B - 1;
     T q[N], dq[N], tg[6], tv[6], u[N], tr[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -221,11 +245,12 @@ rollout_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ O
   typename KS::type K;
   KS::bind(K, region, lane);
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
+    // no early exit (phase barriers inside osc_state): idle lanes / warps redo a valid state and store nothing
     const int64_t warp_b0 = base + warp * 32;
-    if (warp_b0 >= a.B) break;
     const int64_t rem = a.B - warp_b0;
-    const int nvalid = rem < 32 ? (int)rem : 32;
-    const int64_t b = warp_b0 + (lane < nvalid ? lane : nvalid - 1);
+    const int nvalid = rem < 32 ? (rem > 0 ? (int)rem : 0) : 32;
+    const int64_t bb = warp_b0 + (lane < nvalid ? lane : nvalid - 1);
+    const int64_t b = bb < a.B ? (bb >= 0 ? bb : 0) : a.B - 1;
     T q[N], dq[N], tg[6], u[N], acc[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -264,7 +289,7 @@ null_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ Null
             const __grid_constant__ NullArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T *stage = reinterpret_cast<T *>(smem_raw) + warp * kPitch * N;
+  T *stage = reinterpret_cast<T *>(smem_raw) + warp * kPitch * (N < kChunk ? N : kChunk);
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
     const int64_t warp_b0 = base + warp * 32;
     if (warp_b0 >= a.B) break;
@@ -324,7 +349,7 @@ int rbd_go(const ChainHost &h, const RbdCall &c, unsigned want) {
   a.frame = c.frame;
   a.want = want;
   for (int i = 0; i < 3; ++i) a.xoff[i] = c.xoff ? T(c.xoff[i]) : T(0);
-  constexpr bool KSMEM = sizeof(T) == 8;
+  constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32;
   const size_t smem = (size_t)kWarps * WarpSmem<T, N, ORTHO, KSMEM, MaxRecord<N>::value>::kElems * sizeof(T);
   auto kern = rbd_kernel<T, N, ORTHO, DYN, CMAT, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
@@ -374,7 +399,7 @@ int osc_go(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
   a.B = c.B;
   a.target_stride = c.target_stride;
   a.tv_stride = c.tv_stride;
-  constexpr bool KSMEM = sizeof(T) == 8;
+  constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32;
   const size_t smem = (size_t)kWarps * WarpSmem<T, N, ORTHO, KSMEM, N>::kElems * sizeof(T);
   auto kern = osc_kernel<T, N, ORTHO, KD, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
@@ -401,7 +426,7 @@ int rollout_go(const ChainHost &h, const abrb_osc_params &p, const RolloutCall &
   a.target_stride = c.target_stride;
   a.steps = c.steps;
   a.dt = T(c.dt);
-  constexpr bool KSMEM = sizeof(T) == 8;
+  constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32;
   const size_t smem = (size_t)kWarps * WarpSmem<T, N, ORTHO, KSMEM, N>::kElems * sizeof(T);
   auto kern = rollout_kernel<T, N, ORTHO, KD, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
@@ -422,7 +447,7 @@ int null_go(const ChainHost &h, const abrb_null_params &z, const NullCall &c) {
   a.dq = static_cast<const T *>(c.dq);
   a.u = static_cast<T *>(c.u);
   a.B = c.B;
-  const size_t smem = (size_t)kWarps * kPitch * N * sizeof(T);
+  const size_t smem = (size_t)kWarps * kPitch * (N < kChunk ? N : kChunk) * sizeof(T);
   null_kernel<T, N, ORTHO><<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, Z, a);
   count_launch();
   return (int)cudaGetLastError();

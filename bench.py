@@ -396,6 +396,18 @@ def run_ours(args):
 
 
 def main():
+    # rank 0 must print exactly ONE line on stdout (the JSON); libraries (NCCL's version banner, ...) write there too,
+    # so everything else is sent to stderr and the JSON line goes to the saved descriptor
+    global print
+    real_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*a, **k):  # noqa: A001
+        k.setdefault("file", real_out)
+        k.setdefault("flush", True)
+        _print(*a, **k)
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

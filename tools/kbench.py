@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Kernel micro-bench for tuning experiments: CUDA-event time per launch of the main kernels (UR5, B=65536)."""
+import os, sys, json
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from abr_control_b200.arms import ur5, jaco2
+from abr_control_b200.controllers import OSC, Damping
+import bench
+
+dev = torch.device("cuda", 0)
+B, n = int(os.environ.get("KB_B", 65536)), 6
+res = {}
+def sets(dtype, count=24, Bx=B):
+    out = []
+    for s in range(count):
+        q, dq, tg = bench.synth(Bx, n, 100 + s, dtype)
+        out.append(tuple(torch.as_tensor(a, device=dev) for a in (q, dq, tg)))
+    return out
+for name, dt in (("f64", np.float64), ("f32", np.float32)):
+    tdt = torch.float64 if dt == np.float64 else torch.float32
+    S = sets(dt)
+    rc = ur5.Config()
+    shp = dict(J=(B, 6, n), M=(B, n, n), g=(B, n), C=(B, n, n))
+    for key, want in (("rbd_JMgC", ("J", "M", "g", "C")), ("rbd_JMg", ("J", "M", "g"))):
+        o = {k: torch.empty(shp[k], dtype=tdt, device=dev) for k in want}
+        res[f"{key}_{name}"] = bench.time_kernel(lambda s: rc.eval_into(s[0], s[1], o), 200, torch, S) * 1e6
+    import abr_control_b200._abi as _abi
+    _orig = _abi.osc_params
+    cfgs = [("osc6C", dict(kp=10.0, ctrlr_dof=[True] * 6, use_C=True), None), ("osc_xyz", dict(kp=10.0), None)]
+    if os.environ.get("KB_MORE"):
+        cfgs += [("osc6", dict(kp=10.0, ctrlr_dof=[True] * 6), None), ("osc_xyzC", dict(kp=10.0, use_C=True), None),
+                 ("osc6C_noslow", dict(kp=10.0, ctrlr_dof=[True] * 6, use_C=True), 0.0),
+                 ("osc6_alg1", dict(kp=10.0, ctrlr_dof=[True] * 6, orientation_algorithm=1), None),
+                 ("osc5", dict(kp=10.0, ctrlr_dof=[True] * 5 + [False]), None)]
+    for key, kw, thr in cfgs:
+        _abi.osc_params = (lambda *a, **k: _orig(*a, **dict(k, mx_threshold=thr))) if thr is not None else _orig
+        c = OSC(rc, **kw)
+        c._native()
+        _abi.osc_params = _orig
+        u = torch.empty((B, n), dtype=tdt, device=dev)
+        res[f"{key}_{name}"] = bench.time_kernel(lambda s: c.generate_into(s[0], s[1], s[2], u), 200, torch, S) * 1e6
+rc3 = jaco2.Config()
+c3 = OSC(rc3, kp=200, ctrlr_dof=[True] * 5 + [False], null_controllers=[Damping(rc3, kv=10)])
+for name, dt in (("f64", np.float64), ("f32", np.float32)):
+    tdt = torch.float64 if dt == np.float64 else torch.float32
+    S3 = sets(dt, 8, 262144)
+    u3 = torch.empty((262144, 6), dtype=tdt, device=dev)
+    res[f"jaco2_cfg3_B262144_{name}"] = bench.time_kernel(lambda s: c3.generate_into(s[0], s[1], s[2], u3), 50, torch, S3) * 1e6
+print(os.environ.get("ABRB_LIBRARY", "default"), json.dumps({k: round(v, 1) for k, v in res.items()}))

@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Turn the scratch ncu artefacts in gpurun_out/ into the tracked summaries under profiles/.
+
+usage: tools/make_profiles.py <round-tag> [--launches gpurun_out/launches.csv] [--rep name=gpurun_out/x.ncu-rep ...]
+"""
+import collections
+import csv
+import io
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import ncu_summary  # noqa: E402
+
+
+def launches(path, out):
+    rows = list(csv.reader(open(path)))
+    hdr = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+    H = rows[hdr]
+    ki, vi = H.index("Kernel Name"), H.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rows[hdr + 1:]:
+        if len(r) > vi:
+            agg.setdefault(re.sub(r"\(.*", "", r[ki]), []).append(float(r[vi].replace(",", "")))
+    tot = sum(sum(v) for v in agg.values())
+    with open(out, "w") as fh:
+        fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none  (per-launch device time; cold-cache and\n"
+                 "# serialised: compare SHARES, not absolutes)\n")
+        fh.write(f"# source: {os.path.basename(path)}; total {tot/1e3:.1f} us over {sum(len(v) for v in agg.values())} launches\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+            fh.write(f"{sum(v)/tot*100:6.2f}%  n={len(v):4d}  avg {sum(v)/len(v)/1e3:9.2f} us  {k}\n")
+
+
+def main():
+    tag = sys.argv[1]
+    args = sys.argv[2:]
+    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+    traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+    i = 0
+    while i < len(args):
+        if args[i] == "--launches":
+            launches(args[i + 1], os.path.join(ROOT, "profiles", f"{tag}_launches.txt"))
+            i += 2
+        elif args[i] == "--rep":
+            name, rep = args[i + 1].split("=")
+            old = sys.argv
+            buf = io.StringIO()
+            sys.argv, so = ["ncu_summary", rep, "--json", "/tmp/_ncu.json"], sys.stdout
+            sys.stdout = buf
+            try:
+                ncu_summary.main()
+            finally:
+                sys.stdout, sys.argv = so, old
+            with open(os.path.join(ROOT, "profiles", f"{tag}_{name}.txt"), "w") as fh:
+                fh.write(f"# condensed from {os.path.basename(rep)} (ncu --set full --clock-control none --import-source on)\n")
+                fh.write(buf.getvalue())
+            for d in json.load(open("/tmp/_ncu.json")):
+                def mb(v):
+                    return float(v[0].replace(",", "")) * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1, "Gbyte": 1e3}[v[1]]
+                if "dram__bytes_read.sum" in d:
+                    key = re.sub(r"void |unnamed>::|\(.*", "", d["kernel"]).strip()
+                    traffic[f"{name}:{key}"] = {"dram_mb_per_launch": round(mb(d["dram__bytes_read.sum"]) + mb(d["dram__bytes_write.sum"]), 3),
+                                               "ncu_us": float(d["gpu__time_duration.sum"][0]), "tag": tag}
+            i += 2
+        else:
+            raise SystemExit(f"bad arg {args[i]}")
+    json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()
