@@ -808,8 +808,11 @@ ABRB_HD_NOINLINE void pinv_apply_sym(const T *Sin, unsigned active, T rcond, con
 // Rows not in `active` must be decoupled from the rest (zero off-diagonals) with a diagonal >= lambda_max, and
 // y must vanish on them.  Everything is unrolled on registers (about 1.5 k flops): this is what keeps the
 // "second pass" over the deferred states of a tile short.
+// (inertia_below, sym_square and pinv_solve_fast are deliberately NOT inlined: this cold path is executed by a few
+// warps only, so its instructions are never resident in the instruction caches; one shared copy of each helper,
+// called several times, keeps the footprint that has to be fetched small.)
 template <typename T, int S_>
-ABRB_HD int inertia_below(const T (*Sm)[S_], T sigma) {  // #eigenvalues of Sm below sigma, -1 if inconclusive
+ABRB_HD_NOINLINE int inertia_below(const T (*Sm)[S_], T sigma) {  // #eigenvalues of Sm below sigma, -1 if inconclusive
   T D[S_][S_];
   ABRB_UNROLL
   for (int i = 0; i < S_; ++i)
@@ -838,7 +841,7 @@ ABRB_HD int inertia_below(const T (*Sm)[S_], T sigma) {  // #eigenvalues of Sm b
 }
 
 template <typename T, int S_>
-ABRB_HD void sym_square(const T (*A)[S_], T (*B)[S_]) {  // B = A A for symmetric A
+ABRB_HD_NOINLINE void sym_square(const T (*A)[S_], T (*B)[S_]) {  // B = A A for symmetric A
   ABRB_UNROLL
   for (int i = 0; i < S_; ++i)
     ABRB_UNROLL
@@ -854,8 +857,8 @@ ABRB_HD void sym_square(const T (*A)[S_], T (*B)[S_]) {  // B = A A for symmetri
 }
 
 template <typename T, int S_>
-ABRB_HD bool pinv_solve_fast(const T (*Sm)[S_], const T (*L)[S_], const T *invd, unsigned active, T rcond,
-                             const T *y, T *x) {
+ABRB_HD_NOINLINE bool pinv_solve_fast(const T (*Sm)[S_], const T (*L)[S_], const T *invd, unsigned active, T rcond,
+                                      const T *y, T *x) {
   // ---- 1. lambda_max of the active block
   T tr = T(0);
   ABRB_UNROLL

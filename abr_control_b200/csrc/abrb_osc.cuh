@@ -354,29 +354,35 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
       // local-memory Jacobi eigen-decomposition only when that is inconclusive.  Static indices everywhere: a
       // rolled loop over S or v here would force them into local memory for the whole function.
       const unsigned mask = O.dof_mask & ((1u << KD) - 1u);
-      T xo[KD];
-      bool done = false;
-      if (pd) {
-        T tr = T(0);
+      // This branch always runs in double precision, also for the fp32 kernels: the matrices that end up here have
+      // eigenvalue ratios down to 1e-8, where a float Cholesky breaks down (and the FP64 pipe is idle there anyway).
+      double Sd[KD][KD], Ld[KD][KD], Sid[KD], yd[KD], xd[KD];
+      double trd = 0.0;
+      ABRB_UNROLL
+      for (int a = 0; a < KD; ++a) trd += ((mask >> a) & 1u) ? double(S[a][a]) : 0.0;
+      ABRB_UNROLL
+      for (int a = 0; a < KD; ++a) {
+        yd[a] = double(v[a]);
         ABRB_UNROLL
-        for (int a = 0; a < KD; ++a) tr += ((mask >> a) & 1u) ? S[a][a] : T(0);
-        T Sb[KD][KD];  // inactive rows: diagonal >= lambda_max so that they are never counted as truncated
+        for (int b = 0; b < KD; ++b) {
+          // inactive rows: diagonal >= lambda_max so that they are never counted as truncated
+          Sd[a][b] = (a == b && !((mask >> a) & 1u)) ? trd : double(S[a][b]);
+          Ld[a][b] = Sd[a][b];
+        }
+      }
+      const bool pdd = chol<double, KD>(Ld, Sid);
+      bool done = pdd && pinv_solve_fast<double, KD>(Sd, Ld, Sid, mask, double(rcond), yd, xd);
+      if (!done) {
+        double Sf[KD * KD];
         ABRB_UNROLL
         for (int a = 0; a < KD; ++a)
           ABRB_UNROLL
-        for (int b = 0; b < KD; ++b) Sb[a][b] = (a == b && !((mask >> a) & 1u)) ? tr : S[a][b];
-        done = pinv_solve_fast<T, KD>(Sb, Sc, Si, mask, rcond, v, xo);
+        for (int b = 0; b < KD; ++b) Sf[a * KD + b] = double(S[a][b]);
+        pinv_apply_sym<double, KD>(Sf, mask, double(rcond), yd, xd);
       }
-      if (!done) {
-        T Sf[KD * KD], yi[KD];
-        ABRB_UNROLL
-        for (int a = 0; a < KD; ++a) {
-          yi[a] = v[a];
-          ABRB_UNROLL
-          for (int b = 0; b < KD; ++b) Sf[a * KD + b] = S[a][b];
-        }
-        pinv_apply_sym<T, KD>(Sf, mask, rcond, yi, xo);
-      }
+      T xo[KD];
+      ABRB_UNROLL
+      for (int a = 0; a < KD; ++a) xo[a] = T(xd[a]);
       ABRB_UNROLL
       for (int a = 0; a < KD; ++a) v[a] = xo[a];
     }

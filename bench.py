@@ -307,11 +307,13 @@ def run_ours(args):
     hbm_peak, peak_src = peaks()
     bytes_per_state = (6 + 6 + 6) * 8 + 6 * 8  # q, dq, target in; u out (fp64)
     kernel_s = t / args.steps if gather_buf is None else None
-    traffic = None
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         with open(tp) as fh:
-            traffic = json.load(fh).get("osc_kernel_ur5_f64_B65536")
+            for k, v in json.load(fh).items():
+                if k.startswith("osc:osc_kernel<double, 6"):
+                    traffic = {"bytes_per_launch": v["dram_mb_per_launch"] * 1e6, "source": f"profiles/{v['tag']}_osc.txt"}
 
     extra = {}
     if world == 1:
