@@ -30,7 +30,10 @@ constexpr int kBlock = 128;
 #endif
 template <typename T>
 struct MinBlocks {
-  static constexpr int value = sizeof(T) == 8 ? 2 : 4;
+#ifndef ABRB_MINBLOCKS_F32
+#define ABRB_MINBLOCKS_F32 4
+#endif
+  static constexpr int value = sizeof(T) == 8 ? 2 : ABRB_MINBLOCKS_F32;
 };
 constexpr int kWarps = kBlock / 32;
 
@@ -75,7 +78,7 @@ constexpr int kPitch = 33;
 // Records longer than kChunk elements go through the tile in slices of kChunk (the tile then needs only
 // kPitch * kChunk elements per warp, which is what lets three CTAs of the fp64 kernels share an SM); each slice is a
 // run of kChunk contiguous elements per record in global memory (>= 144 bytes for fp64).
-constexpr int kChunk = 18;
+constexpr int kChunk = 64;  // no slicing needed with 2 CTAs/SM (93 KB each); 18 would allow 3 CTAs/SM but measured slower
 template <typename T, int LEN>
 __device__ __forceinline__ void store_records(T *__restrict__ out, int64_t warp_b0, int nvalid, const T *rec,
                                               T *tile, int lane) {
@@ -349,7 +352,7 @@ int rbd_go(const ChainHost &h, const RbdCall &c, unsigned want) {
   a.frame = c.frame;
   a.want = want;
   for (int i = 0; i < 3; ++i) a.xoff[i] = c.xoff ? T(c.xoff[i]) : T(0);
-  constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32;
+  constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32 || ABRB_ROLLED;  // rolled loops index the scratch at run time
   const size_t smem = (size_t)kWarps * WarpSmem<T, N, ORTHO, KSMEM, MaxRecord<N>::value>::kElems * sizeof(T);
   auto kern = rbd_kernel<T, N, ORTHO, DYN, CMAT, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
@@ -399,7 +402,7 @@ int osc_go(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
   a.B = c.B;
   a.target_stride = c.target_stride;
   a.tv_stride = c.tv_stride;
-  constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32;
+  constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32 || ABRB_ROLLED;  // rolled loops index the scratch at run time
   const size_t smem = (size_t)kWarps * WarpSmem<T, N, ORTHO, KSMEM, N>::kElems * sizeof(T);
   auto kern = osc_kernel<T, N, ORTHO, KD, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
@@ -426,7 +429,7 @@ int rollout_go(const ChainHost &h, const abrb_osc_params &p, const RolloutCall &
   a.target_stride = c.target_stride;
   a.steps = c.steps;
   a.dt = T(c.dt);
-  constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32;
+  constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32 || ABRB_ROLLED;  // rolled loops index the scratch at run time
   const size_t smem = (size_t)kWarps * WarpSmem<T, N, ORTHO, KSMEM, N>::kElems * sizeof(T);
   auto kern = rollout_kernel<T, N, ORTHO, KD, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
