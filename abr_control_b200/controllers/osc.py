@@ -103,19 +103,6 @@ class OSC(Controller):
         except Exception:
             pass
 
-    # ------------------------------------------------------------------ pure-host helpers kept for parity
-    def _velocity_limiting(self, u_task):
-        """osc.py:198-215 for one 6-vector (host; the batched path fuses this into the kernel)."""
-        u_task = np.asarray(u_task, dtype=float)
-        norm_xyz = np.linalg.norm(u_task[:3])
-        norm_abg = np.linalg.norm(u_task[3:])
-        scale = np.ones(6)
-        if norm_xyz > self.sat_gain_xyz:
-            scale[:3] *= self.scale_xyz / norm_xyz
-        if norm_abg > self.sat_gain_abg:
-            scale[3:] *= self.scale_abg / norm_abg
-        return self.kv * scale * self.lamb * u_task
-
     # ------------------------------------------------------------------ generate
     def generate(self, q, dq, target, target_velocity=None, ref_frame="EE", xyz_offset=None):
         rc = self.robot_config

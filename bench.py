@@ -352,6 +352,32 @@ def run_ours(args):
         dt = time_kernel(lambda s: c3.generate_into(s[0], s[1], s[2], u3), 100, torch, s3)
         extra["osc_jaco2_cfg3_f32_B262144"] = {"evals_per_s": B3 / dt, "us_per_launch": dt * 1e6, "bytes_per_state": 96,
                                                "achieved_gbs": B3 * 96 / dt / 1e9, "frac_hbm": B3 * 96 / dt / 1e9 / hbm_peak}
+        # BASELINE config 5 (per-GPU share): Jaco2 OSC xyz + vmax + AvoidObstacles(1 obstacle) + Damping, fp32, B = 131072
+        from abr_control_b200.controllers import AvoidObstacles
+        B5 = 131072
+        c5 = OSC(rc3, kp=200, vmax=[0.5, 0], ctrlr_dof=[True, True, True, False, False, False],
+                 null_controllers=[AvoidObstacles(rc3, obstacles=[[0.09596, -0.2661, 0.64204, 0.05]], threshold=0.2),
+                                   Damping(rc3, kv=10)])
+        s5 = [tuple(t_[:B5].contiguous() for t_ in s) for s in s3[:8]]
+        u5 = torch.empty((B5, 6), dtype=torch.float32, device=dev)
+        dt = time_kernel(lambda s: c5.generate_into(s[0], s[1], s[2], u5), 50, torch, s5)
+        extra["osc_jaco2_cfg5_avoid_f32_B131072"] = {"evals_per_s": B5 / dt, "us_per_launch": dt * 1e6, "bytes_per_state": 96}
+        # BASELINE config 4: UR5 OSC(kp=10) closed-loop rollout, 4096 trajectories x 128 steps, dt = 1e-3 (one launch)
+        c4 = OSC(rc, kp=10.0)
+        q4, dq4, tg4 = (torch.as_tensor(a, device=dev) for a in synth(4096, 6, 4242))
+        dq4 = dq4 * 0.1
+        for _ in range(2):
+            c4.rollout(q4, dq4, tg4, steps=128, dt=1e-3, record=())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            c4.rollout(q4, dq4, tg4, steps=128, dt=1e-3, record=())
+        e1.record()
+        torch.cuda.synchronize()
+        dt = e0.elapsed_time(e1) * 1e-3 / 5
+        extra["rollout_ur5_cfg4_f64_4096x128"] = {"osc_evals_per_s": 4096 * 128 / dt, "ms_per_rollout": dt * 1e3,
+                                                   "us_per_step": dt / 128 * 1e6, "note": "latency bound: 32 warps per 148 SMs"}
         ctrl32 = OSC(ur5.Config(), **OSC_KW)
         s32 = [tuple(t_.float() for t_ in s) for s in sets[:24]]
         u32b = torch.empty((B, 6), dtype=torch.float32, device=dev)
