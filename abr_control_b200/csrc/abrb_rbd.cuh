@@ -23,19 +23,21 @@ enum { kOutTx = 0, kOutT, kOutR, kOutTinv, kOutQuat, kOutJ, kOutdJ, kOutM, kOutg
 // One state.  Every requested quantity is handed to `out.template put<LEN>(which, record)` as soon as it is complete,
 // so that no more than one or two output records are ever live in registers (the kernel's `put` stages the record
 // through shared memory and writes it out coalesced; the host test shim copies it into an array).
-// DYN: M and/or g requested; CMAT: C requested.  `want` is uniform over the launch.
+// DYN: M and/or g requested; CMAT: C requested; XTRA: any of Tx/T/R/T_inv/quaternion/dJ requested (compiled out of
+// the common {J, M, g, C} instantiations: less code to fetch, fewer live registers).  `want` is uniform over the launch.
 // `K` is the caller-provided kinematic scratch (register- or shared-memory-backed, see Kin in abrb_math.cuh).
-template <typename T, int N, bool DYN, bool CMAT, class K_, class Out>
+template <typename T, int N, bool DYN, bool CMAT, bool XTRA, class K_, class Out>
 ABRB_HD void rbd_state(const ChainK<T, N> &P, const T *q, const T *dq, int frame, const T *xoff, unsigned want,
                        K_ &K, Out &out) {
+  if (!XTRA) want &= (kWantJ | kWantM | kWantg | kWantC);
   K.sync();
   walk<T, N>(P, q, frame, K);
   K.sync();
   const int dep = frame_dep<N>(frame);
   T pF[3];
   frame_point(K.F, xoff, pF);
-  if (want & kWantTx) out.template put<3>(kOutTx, pF);
-  if (want & kWantT) {  // base_config.py:338-369
+  if (XTRA && (want & kWantTx)) out.template put<3>(kOutTx, pF);
+  if (XTRA && (want & kWantT)) {  // base_config.py:338-369
     T Tm[16];
     ABRB_UNROLL
     for (int i = 0; i < 12; ++i) Tm[i] = K.F[i];
@@ -43,7 +45,7 @@ ABRB_HD void rbd_state(const ChainK<T, N> &P, const T *q, const T *dq, int frame
     Tm[15] = T(1);
     out.template put<16>(kOutT, Tm);
   }
-  if (want & (kWantR | kWantQuat)) {  // base_config.py:647-676, :304-318
+  if (XTRA && (want & (kWantR | kWantQuat))) {  // base_config.py:647-676, :304-318
     T R[9];
     ABRB_UNROLL
     for (int r = 0; r < 3; ++r)
@@ -56,7 +58,7 @@ ABRB_HD void rbd_state(const ChainK<T, N> &P, const T *q, const T *dq, int frame
       out.template put<4>(kOutQuat, qt);
     }
   }
-  if (want & kWantTinv) {  // [[R^T, -R^T t],[0,1]] with the TRANSPOSE (base_config.py:820-824)
+  if (XTRA && (want & kWantTinv)) {  // [[R^T, -R^T t],[0,1]] with the TRANSPOSE (base_config.py:820-824)
     T Ti[16];
     ABRB_UNROLL
     for (int r = 0; r < 3; ++r) {
@@ -77,7 +79,7 @@ ABRB_HD void rbd_state(const ChainK<T, N> &P, const T *q, const T *dq, int frame
     T J[6][N];
     jacobian<T, N>(K, pF, dep, J);
     if (want & kWantJ) out.template put<6 * N>(kOutJ, &J[0][0]);
-    if (want & kWantdJ) {
+    if (XTRA && (want & kWantdJ)) {
       T dJ[6][N];
       jacobian_dot<T, N>(K, J, dq, dep, dJ);
       out.template put<6 * N>(kOutdJ, &dJ[0][0]);

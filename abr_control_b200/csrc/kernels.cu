@@ -135,7 +135,7 @@ struct WarpSmem {
   static constexpr int kElems = kKin + kTile;
 };
 
-template <typename T, int N, bool ORTHO, bool DYN, bool CMAT, bool KSMEM>
+template <typename T, int N, bool ORTHO, bool DYN, bool CMAT, bool XTRA, bool KSMEM>
 __global__ void __launch_bounds__(kBlock, MinBlocks<T>::value)
 rbd_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ RbdArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -173,7 +173,7 @@ rbd_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ RbdAr
     }
     sink.warp_b0 = warp_b0;
     sink.nvalid = nvalid;
-    rbd_state<T, N, DYN, CMAT>(P, q, dq, a.frame, a.xoff, a.want, K, sink);
+    rbd_state<T, N, DYN, CMAT, XTRA>(P, q, dq, a.frame, a.xoff, a.want, K, sink);
   }
 }
 
@@ -331,7 +331,7 @@ inline cudaError_t set_smem(K kernel, size_t bytes) {
   return cudaSuccess;
 }
 
-template <typename T, int N, bool ORTHO, bool DYN, bool CMAT>
+template <typename T, int N, bool ORTHO, bool DYN, bool CMAT, bool XTRA>
 int rbd_go(const ChainHost &h, const RbdCall &c, unsigned want) {
   ChainK<T, N> P;
   fill_chain<T, N>(h, P);
@@ -354,7 +354,7 @@ int rbd_go(const ChainHost &h, const RbdCall &c, unsigned want) {
   for (int i = 0; i < 3; ++i) a.xoff[i] = c.xoff ? T(c.xoff[i]) : T(0);
   constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32 || ABRB_ROLLED;  // rolled loops index the scratch at run time
   const size_t smem = (size_t)kWarps * WarpSmem<T, N, ORTHO, KSMEM, MaxRecord<N>::value>::kElems * sizeof(T);
-  auto kern = rbd_kernel<T, N, ORTHO, DYN, CMAT, KSMEM>;
+  auto kern = rbd_kernel<T, N, ORTHO, DYN, CMAT, XTRA, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, a);
@@ -376,14 +376,17 @@ int rbd_dispatch(const ChainHost &h, const RbdCall &c) {
   if (c.out.g) want |= kWantg;
   if (c.out.C) want |= kWantC;
   const bool cm = c.out.C != nullptr, dyn = c.out.M != nullptr || c.out.g != nullptr;
-  if (h.ortho) {
-    if (cm) return rbd_go<T, N, true, true, true>(h, c, want);
-    if (dyn) return rbd_go<T, N, true, true, false>(h, c, want);
-    return rbd_go<T, N, true, false, false>(h, c, want);
-  }
-  if (cm) return rbd_go<T, N, false, true, true>(h, c, want);
-  if (dyn) return rbd_go<T, N, false, true, false>(h, c, want);
-  return rbd_go<T, N, false, false, false>(h, c, want);
+  const bool xtra = (want & ~(kWantJ | kWantM | kWantg | kWantC)) != 0;
+  // instantiations: {frame-only (with extras)} + {dynamics / dynamics+C} x {with, without extras}
+#define ABRB_RBD_GO(O_)                                                                   \
+  do {                                                                                     \
+    if (cm) return xtra ? rbd_go<T, N, O_, true, true, true>(h, c, want) : rbd_go<T, N, O_, true, true, false>(h, c, want);   \
+    if (dyn) return xtra ? rbd_go<T, N, O_, true, false, true>(h, c, want) : rbd_go<T, N, O_, true, false, false>(h, c, want); \
+    return rbd_go<T, N, O_, false, false, true>(h, c, want);                               \
+  } while (0)
+  if (h.ortho) ABRB_RBD_GO(true);
+  ABRB_RBD_GO(false);
+#undef ABRB_RBD_GO
 }
 
 template <typename T, int N, bool ORTHO, int KD>

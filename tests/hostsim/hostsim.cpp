@@ -39,7 +39,7 @@ void rbd_loop(const ChainHost &h, int frame, const double *xoff, const double *q
     }
     Sink<T> sink{{Tx, Tm, R, Tinv, quat, J, dJ, M, g, C}, b};
     Kin<T, N, ORTHO> K;
-    rbd_state<T, N, true, true>(P, qq, dd, frame, xo, want, K, sink);
+    rbd_state<T, N, true, true, true>(P, qq, dd, frame, xo, want, K, sink);
   }
 }
 
