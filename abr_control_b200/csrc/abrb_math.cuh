@@ -1173,21 +1173,8 @@ ABRB_HD bool pinv_solve_fast(const T (*Sm)[S_], const T (*L)[S_], const T *invd,
   }
   if (delta < T(0) || m_lo < 0 || m_lo != m_hi || m_lo > 2) return false;
   const int m = m_lo;
-  // ---- 3. truncated eigenvectors by inverse subspace iteration (two vectors are carried, the second is only used
-  //         when m == 2).  S^-1 is formed explicitly first: its S_ columns are independent triangular solves (the
-  //         compiler interleaves them), after which every iteration is a matrix-vector product of depth S_ instead
-  //         of a forward/backward substitution of depth 2 S_^2 — this branch is latency bound.
-  T Sinv[S_][S_];
-  ABRB_UNROLL
-  for (int c = 0; c < S_; ++c) {
-    T e[S_];
-    ABRB_UNROLL
-    for (int i = 0; i < S_; ++i) e[i] = i == c ? T(1) : T(0);
-    fwd_solve<T, S_>(L, invd, e);
-    bwd_solve<T, S_>(L, invd, e);
-    ABRB_UNROLL
-    for (int i = 0; i < S_; ++i) Sinv[i][c] = e[i];
-  }
+  // ---- 3. truncated eigenvectors by inverse subspace iteration (two vectors are carried, the second is only
+  //         used when m == 2)
   T V0[S_], V1[S_];
   ABRB_UNROLL
   for (int i = 0; i < S_; ++i) {
@@ -1205,36 +1192,29 @@ ABRB_HD bool pinv_solve_fast(const T (*Sm)[S_], const T (*L)[S_], const T *invd,
     for (int blk = 0; blk < 6 && !converged; ++blk) {
       ABRB_NOUNROLL
       for (int it = 0; it < 3; ++it) {
-        T w0[S_], w1[S_], n0 = T(0);
+        fwd_solve<T, S_>(L, invd, V0);
+        bwd_solve<T, S_>(L, invd, V0);
+        T nn = T(0);
         ABRB_UNROLL
-        for (int i = 0; i < S_; ++i) {
-          T a0 = T(0), a1 = T(0);
-          ABRB_UNROLL
-          for (int j = 0; j < S_; ++j) {
-            a0 += Sinv[i][j] * V0[j];
-            a1 += Sinv[i][j] * V1[j];
-          }
-          w0[i] = a0;
-          w1[i] = a1;
-          n0 += a0 * a0;
-        }
-        const T sc0 = T(1) / sqrt_t(n0);
-        T d = T(0);
+        for (int i = 0; i < S_; ++i) nn += V0[i] * V0[i];
+        T sc = T(1) / sqrt_t(nn);
         ABRB_UNROLL
-        for (int i = 0; i < S_; ++i) {
-          V0[i] = w0[i] * sc0;
-          d += V0[i] * w1[i];
-        }
+        for (int i = 0; i < S_; ++i) V0[i] *= sc;
         if (m == 2) {
-          T n1 = T(0);
+          fwd_solve<T, S_>(L, invd, V1);
+          bwd_solve<T, S_>(L, invd, V1);
+          T d = T(0);
+          ABRB_UNROLL
+          for (int i = 0; i < S_; ++i) d += V0[i] * V1[i];
+          nn = T(0);
           ABRB_UNROLL
           for (int i = 0; i < S_; ++i) {
-            w1[i] -= d * V0[i];
-            n1 += w1[i] * w1[i];
+            V1[i] -= d * V0[i];
+            nn += V1[i] * V1[i];
           }
-          const T sc1 = T(1) / sqrt_t(n1);
+          sc = T(1) / sqrt_t(nn);
           ABRB_UNROLL
-          for (int i = 0; i < S_; ++i) V1[i] = w1[i] * sc1;
+          for (int i = 0; i < S_; ++i) V1[i] *= sc;
         }
       }
       T w0[S_], w1[S_], a00 = T(0), a01 = T(0), a11 = T(0);
@@ -1281,7 +1261,7 @@ ABRB_HD bool pinv_solve_fast(const T (*Sm)[S_], const T (*L)[S_], const T *invd,
       ABRB_UNROLL
       for (int i = 0; i < S_; ++i) b[i] -= d0 * V0[i] + d1 * V1[i];
     }
-    if (pass == 0) {  // the one solve that must be backward stable: substitutions, not the explicit inverse
+    if (pass == 0) {
       fwd_solve<T, S_>(L, invd, b);
       bwd_solve<T, S_>(L, invd, b);
     }
@@ -1291,7 +1271,8 @@ ABRB_HD bool pinv_solve_fast(const T (*Sm)[S_], const T (*L)[S_], const T *invd,
   return true;
 }
 
-// (An out-of-line entry — a real call with private register copies of the arguments — was measured slower on B200 than
-// the inlined form: 120 vs 99 us for the 6-DOF fp64 OSC kernel.)
+// (Measured and dropped on B200, 6-DOF fp64 OSC kernel at 99 us: an out-of-line entry with private register copies of the
+// arguments (120 us); forming S^-1 explicitly so that the inverse iteration becomes matrix-vector products (faster in
+// isolation, 13.7 k vs 16.7 k cycles, but 161 us in the kernel: the 36 extra live values spill).)
 
 }  // namespace abrb

@@ -294,7 +294,9 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) K.s.st(Aslot(r, k), row[k]);
   }
-  T S[KD][KD];
+  // S is built straight into the array that is then factorised in place; only its trace is kept.  The rare
+  // truncating branch re-forms S from A (shared memory) instead of keeping 36 more values live on the hot path.
+  T Sc[KD][KD], Si[KD], trS = T(0);
   ABRB_UNROLL
   for (int a = 0; a < KD; ++a) {
     T ra[N];
@@ -307,18 +309,13 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
         ABRB_UNROLL
         for (int k = 0; k < N; ++k) s += ra[k] * K.s.ld(Aslot(b, k));
         const bool on = ((O.dof_mask >> a) & 1u) && ((O.dof_mask >> b) & 1u);
-        S[a][b] = on ? s : (a == b ? T(1) : T(0));
-        S[b][a] = S[a][b];
+        Sc[a][b] = on ? s : (a == b ? T(1) : T(0));
+        Sc[b][a] = Sc[a][b];
+        if (a == b && on) trS += s;
       }
     }
   }
-  K.sync();  // last common point: from here on the rare truncating-pinv lanes diverge
   // ---- Mx: inverse if |det| >= threshold else pinv(rcond = threshold*0.1)   (osc.py:138-145)
-  T Sc[KD][KD], Si[KD];
-  ABRB_UNROLL
-  for (int a = 0; a < KD; ++a)
-    ABRB_UNROLL
-  for (int b = 0; b < KD; ++b) Sc[a][b] = S[a][b];
   const bool pd = chol<T, KD>(Sc, Si);
   T det = T(1);
   ABRB_UNROLL
@@ -328,11 +325,11 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
   if (pd && !fast) {
     // pinv == inv whenever no eigenvalue is truncated; certify that cheaply:
     // lambda_max <= trace(S_active), 1/lambda_min <= ||S^-1||_F  =>  no truncation if 1/||S^-1||_F > rcond*trace
-    T tr = T(0), fro = T(0);
+    const T tr = trS;
+    T fro = T(0);
     ABRB_UNROLL
     for (int a = 0; a < KD; ++a) {
       if ((O.dof_mask >> a) & 1u) {
-        tr += S[a][a];
         T e[KD];
         ABRB_UNROLL
         for (int b = 0; b < KD; ++b) e[b] = b == a ? T(1) : T(0);
@@ -357,19 +354,31 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
       // This branch always runs in double precision, also for the fp32 kernels: the matrices that end up here have
       // eigenvalue ratios down to 1e-8, where a float Cholesky breaks down (and the FP64 pipe is idle there anyway).
       double Sd[KD][KD], Ld[KD][KD], Sid[KD], yd[KD], xd[KD];
-      double trd = 0.0;
-      ABRB_UNROLL
-      for (int a = 0; a < KD; ++a) trd += ((mask >> a) & 1u) ? double(S[a][a]) : 0.0;
+      const double trd = double(trS);
       ABRB_UNROLL
       for (int a = 0; a < KD; ++a) {
         yd[a] = double(v[a]);
+        double ra[N];
+        ABRB_UNROLL
+        for (int k = 0; k < N; ++k) ra[k] = double(K.s.ld(Aslot(a, k)));
         ABRB_UNROLL
         for (int b = 0; b < KD; ++b) {
-          // inactive rows: diagonal >= lambda_max so that they are never counted as truncated
-          Sd[a][b] = (a == b && !((mask >> a) & 1u)) ? trd : double(S[a][b]);
-          Ld[a][b] = Sd[a][b];
+          if (b <= a) {
+            double acc = 0.0;
+            ABRB_UNROLL
+            for (int k = 0; k < N; ++k) acc += ra[k] * double(K.s.ld(Aslot(b, k)));
+            const bool on = ((mask >> a) & 1u) && ((mask >> b) & 1u);
+            // inactive rows: decoupled, diagonal >= lambda_max so that they are never counted as truncated
+            const double val = on ? acc : (a == b ? trd : 0.0);
+            Sd[a][b] = val;
+            Sd[b][a] = val;
+          }
         }
       }
+      ABRB_UNROLL
+      for (int a = 0; a < KD; ++a)
+        ABRB_UNROLL
+      for (int b = 0; b < KD; ++b) Ld[a][b] = Sd[a][b];
       const bool pdd = chol<double, KD>(Ld, Sid);
       bool done = pdd && pinv_solve_fast<double, KD>(Sd, Ld, Sid, mask, double(rcond), yd, xd);
       if (!done) {
@@ -377,7 +386,7 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
         ABRB_UNROLL
         for (int a = 0; a < KD; ++a)
           ABRB_UNROLL
-        for (int b = 0; b < KD; ++b) Sf[a * KD + b] = double(S[a][b]);
+        for (int b = 0; b < KD; ++b) Sf[a * KD + b] = (a == b && !((mask >> a) & 1u)) ? 1.0 : Sd[a][b];
         pinv_apply_sym<double, KD>(Sf, mask, double(rcond), yd, xd);
       }
       T xo[KD];

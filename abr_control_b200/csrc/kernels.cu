@@ -186,8 +186,9 @@ struct OscArgs {
 };
 
 // One pass: the few states that need the truncating pseudo-inverse take the register-resident inertia-count route
-// in line (about half the cost of the main path, so the divergence it causes is bounded); a block-level "defer and
-// re-run densely" scheme was measured slower on B200 because the other warps of the CTA idle at the barrier.
+// in line.  Deferring them was measured slower on B200 at B = 65536 both ways: re-running them densely in a second
+// pass of the same CTA (the other warps idle at the barrier: 269 us) and in a second launch fed by a global index
+// queue (the ~2.5 k deferred states are too few to fill the machine, so that launch is pure latency: 123 vs 103 us).
 template <typename T, int N, bool ORTHO, int KD, bool KSMEM>
 __global__ void __launch_bounds__(kBlock, MinBlocks<T>::value)
 osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,

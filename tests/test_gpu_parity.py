@@ -237,6 +237,38 @@ def test_singular_states_take_the_pinv_branch():
         assert np.abs(u - ref).max() < 1e-7 * np.abs(ref).max(), (arm, u, ref)
 
 
+def test_large_batch_deferred_pinv_states():
+    """Every state of a 4096-state UR5 6-DOF batch that takes the truncating-pinv branch (|det| < 1e-3, ~3.75 % of
+    uniformly random states) must match the oracle, fp64 and fp32, and must not depend on the batch it sits in."""
+    from oracle import osc_oracle, rbd_oracle
+
+    rng = np.random.default_rng(11)
+    B = 4096
+    q, dq, target = rng.uniform(0, 2 * np.pi, (B, 6)), rng.uniform(0, 5, (B, 6)), rng.uniform(-1, 1, (B, 6))
+    ch = rbd_oracle.ChainOracle("ur5")
+    J = ch.J("EE", q)
+    S = J @ np.linalg.inv(ch.M(q)) @ np.swapaxes(J, 1, 2)
+    slow = np.where(np.abs(np.linalg.det(S)) < 1e-3)[0]
+    assert 80 < len(slow) < 300  # ~3.75 % of uniformly random states
+    pick = np.concatenate([slow, np.arange(0, B, 97)])
+    case = dict(arm="ur5", osc=dict(kp=50, ctrlr_dof=[True] * 6, use_C=True), null=[("Damping", dict(kv=10))])
+    ref, _ = osc_oracle.run_case(case, q[pick], dq[pick], target[pick])
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    w = np.linalg.eigvalsh(S[pick])
+    # states with an eigenvalue within 0.1 % of the pinv cutoff are genuinely ambiguous: exclude them
+    clear = np.all(np.abs(w / (1e-4 * w[:, -1:]) - 1) > 1e-3, axis=1)
+    for dtype, tol in ((np.float64, 1e-6), (np.float32, 5e-2)):
+        rc = _cfg("ur5", dtype=dtype)
+        ctrlr = _build_ctrl(rc, case)
+        u = ctrlr.generate(q.astype(dtype), dq.astype(dtype), target.astype(dtype))
+        err = (np.abs(u[pick] - ref) / scale).max(axis=1)
+        assert err[clear].max() < tol, (dtype, err[clear].max())
+        assert np.median(err) < (1e-12 if dtype == np.float64 else 1e-5)
+        # and identical to evaluating the same rows in a small batch
+        small = ctrlr.generate(q[slow[:64]].astype(dtype), dq[slow[:64]].astype(dtype), target[slow[:64]].astype(dtype))
+        assert np.allclose(small, u[slow[:64]], rtol=1e-9 if dtype == np.float64 else 1e-4, atol=0)
+
+
 def test_full_size_properties():
     """BASELINE configs at full size, through size-independent properties (the oracle is too slow here):
     config 2 (UR5 {J,M,g,C}, B=65536, fp64) and config 3 (Jaco2 OSC, B=262144, fp32)."""
