@@ -61,7 +61,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                       "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "10", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             pass
 
@@ -313,7 +313,7 @@ def run_ours(args):
         with open(tp) as fh:
             for k, v in json.load(fh).items():
                 if k.startswith("osc:osc_kernel<double, 6"):
-                    traffic = {"bytes_per_launch": v["dram_mb_per_launch"] * 1e6, "source": f"profiles/{v['tag']}_osc.txt"}
+                    traffic = v["dram_mb_per_launch"] * 1e6  # bytes per launch (profiles/<tag>_osc.txt)
 
     extra = {}
     if world == 1:
@@ -438,7 +438,7 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--allgather", action="store_true", help="all-gather u across ranks every step (config 5 style)")
