@@ -48,6 +48,10 @@ SIGNATURES = {
     "abrb_osc_generate_host_f32": (_I, _gen),
     "abrb_null_generate_f64": (_I, [_VP, C.POINTER(_abi.NullParams), _VP, _VP, _VP, _I64, _VP]),
     "abrb_null_generate_f32": (_I, [_VP, C.POINTER(_abi.NullParams), _VP, _VP, _VP, _I64, _VP]),
+    "abrb_joint_generate_f64": (_I, [_VP, _D, _D, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I64, _VP]),
+    "abrb_joint_generate_f32": (_I, [_VP, _D, _D, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I64, _VP]),
+    "abrb_floating_generate_f64": (_I, [_VP, _I, _I, _VP, _VP, _VP, _I64, _VP]),
+    "abrb_floating_generate_f32": (_I, [_VP, _I, _I, _VP, _VP, _VP, _I64, _VP]),
     "abrb_osc_rollout_f64": (_I, _roll),
     "abrb_osc_rollout_f32": (_I, _roll),
     "abrb_launch_count": (_I64, []),

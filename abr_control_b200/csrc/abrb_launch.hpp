@@ -25,6 +25,7 @@ struct OscCall {
   int64_t B;
   bool f32;
   cudaStream_t stream;
+  int *queue = nullptr;  // device workspace of >= 4 + B ints, [0..3] zero: run the two-launch mode (6-row path only)
 };
 
 struct RolloutCall {
@@ -49,11 +50,25 @@ struct NullCall {
   cudaStream_t stream;
 };
 
+// Joint (kind 0) and Floating (kind 1) controllers
+struct CtrlCall {
+  int kind;
+  double kp, kv;
+  int flag_a, flag_b;              // Joint: account_for_gravity, -   Floating: task_space, dynamic
+  const void *q, *dq, *target, *tv;
+  int target_stride, tv_stride;
+  void *u;
+  int64_t B;
+  bool f32;
+  cudaStream_t stream;
+};
+
 // Each returns a cudaError_t (0 = success).  Defined once per joint count in kernels.cu (-DABRB_N=<n>).
 template <int N> int launch_rbd(const ChainHost &h, const RbdCall &c);
 template <int N> int launch_osc(const ChainHost &h, const abrb_osc_params &p, const OscCall &c);
 template <int N> int launch_rollout(const ChainHost &h, const abrb_osc_params &p, const RolloutCall &c);
 template <int N> int launch_null(const ChainHost &h, const abrb_null_params &z, const NullCall &c);
+template <int N> int launch_ctrl(const ChainHost &h, const CtrlCall &c);
 
 void count_launch();
 

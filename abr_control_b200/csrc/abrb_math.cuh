@@ -1088,9 +1088,12 @@ ABRB_HD void sym_square(const T (*A)[S_], T (*B)[S_]) {  // B = A A for symmetri
   }
 }
 
+#ifndef ABRB_PINV_BLOCKS
+#define ABRB_PINV_BLOCKS 40
+#endif
 template <typename T, int S_>
-ABRB_HD bool pinv_solve_fast(const T (*Sm)[S_], const T (*L)[S_], const T *invd, unsigned active, T rcond,
-                             const T *y, T *x) {
+ABRB_HD bool pinv_solve_fast2(const T (*Sm)[S_], const T (*L)[S_], const T *invd, unsigned active, T rcond,
+                              const T *y, T *x, const T *y2, T *x2, bool two) {
   // ---- 1. lambda_max of the active block
   T tr = T(0);
   ABRB_UNROLL
@@ -1171,104 +1174,130 @@ ABRB_HD bool pinv_solve_fast(const T (*Sm)[S_], const T (*L)[S_], const T *invd,
       m_hi = c;
     }
   }
-  if (delta < T(0) || m_lo < 0 || m_lo != m_hi || m_lo > 2) return false;
+  constexpr int MV = S_ >= 6 ? 3 : 2;  // truncated eigenvectors the register-resident route can carry
+  if (delta < T(0) || m_lo < 0 || m_lo != m_hi || m_lo > MV) return false;
   const int m = m_lo;
-  // ---- 3. truncated eigenvectors by inverse subspace iteration (two vectors are carried, the second is only
-  //         used when m == 2)
-  T V0[S_], V1[S_];
+  // ---- 3. truncated eigenvectors by inverse subspace iteration.  MV vectors are carried; vector j only takes part
+  //         when j < m (runtime guards around static indices: the vectors stay in registers).  Three truncated
+  //         eigenvalues are ~7e-4 of the UR5 6-DOF pinv states, i.e. more than one state per 65 536-state launch,
+  //         and each state that leaves this routine for the Jacobi route costs the whole launch ~80 us of tail.
+  T V[MV][S_];
   ABRB_UNROLL
   for (int i = 0; i < S_; ++i) {
     const bool on = (active >> i) & 1u;
-    V0[i] = on ? T(1) / T(1 + i) + T(0.1) : T(0);
-    V1[i] = on ? ((i & 1) ? T(-0.7) : T(0.45)) + T(0.05) * T(i) : T(0);
+    V[0][i] = on ? T(1) / T(1 + i) + T(0.1) : T(0);
+    V[1][i] = on ? ((i & 1) ? T(-0.7) : T(0.45)) + T(0.05) * T(i) : T(0);
+    if (MV > 2) V[MV - 1][i] = on ? ((i % 3) == 0 ? T(0.8) : ((i % 3) == 1 ? T(-0.35) : T(0.2))) - T(0.03) * T(i) : T(0);
   }
   if (m >= 1) {
     // Blocks of inverse iterations until the span is invariant (|| S v - span component || tiny relative to the
     // cutoff).  The loops over `blk`/`it` stay rolled (their bodies use static indices only): convergence normally
-    // takes one block because the truncated eigenvalues sit orders of magnitude below the kept ones.
-    const T tol = (sizeof(T) == 8 ? T(1e-9) : T(1e-4)) * rcond * rho;
+    // takes one block because the truncated eigenvalues sit orders of magnitude below the kept ones; the block limit is
+    // generous because a truncated eigenvalue within a factor ~2 of the next kept one converges at that ratio per
+    // iteration, and every state that runs out of blocks drops to the Jacobi route (with 6 blocks that was ~1 in 10^3
+    // of the pinv states: one or more per 65 536-state launch).
+    const T tol = (sizeof(T) == 8 ? T(1e-10) : T(1e-4)) * rcond * rho;
     bool converged = false;
     ABRB_NOUNROLL
-    for (int blk = 0; blk < 6 && !converged; ++blk) {
+    for (int blk = 0; blk < ABRB_PINV_BLOCKS && !converged; ++blk) {
       ABRB_NOUNROLL
       for (int it = 0; it < 3; ++it) {
-        fwd_solve<T, S_>(L, invd, V0);
-        bwd_solve<T, S_>(L, invd, V0);
-        T nn = T(0);
         ABRB_UNROLL
-        for (int i = 0; i < S_; ++i) nn += V0[i] * V0[i];
-        T sc = T(1) / sqrt_t(nn);
-        ABRB_UNROLL
-        for (int i = 0; i < S_; ++i) V0[i] *= sc;
-        if (m == 2) {
-          fwd_solve<T, S_>(L, invd, V1);
-          bwd_solve<T, S_>(L, invd, V1);
-          T d = T(0);
-          ABRB_UNROLL
-          for (int i = 0; i < S_; ++i) d += V0[i] * V1[i];
-          nn = T(0);
+        for (int j = 0; j < MV; ++j) {
+          if (j < m) {
+            fwd_solve<T, S_>(L, invd, V[j]);
+            bwd_solve<T, S_>(L, invd, V[j]);
+            ABRB_UNROLL
+            for (int k = 0; k < j; ++k) {  // Gram-Schmidt against the vectors already done in this sweep
+              T d = T(0);
+              ABRB_UNROLL
+              for (int i = 0; i < S_; ++i) d += V[k][i] * V[j][i];
+              ABRB_UNROLL
+              for (int i = 0; i < S_; ++i) V[j][i] -= d * V[k][i];
+            }
+            T nn = T(0);
+            ABRB_UNROLL
+            for (int i = 0; i < S_; ++i) nn += V[j][i] * V[j][i];
+            const T sc = T(1) / sqrt_t(nn);
+            ABRB_UNROLL
+            for (int i = 0; i < S_; ++i) V[j][i] *= sc;
+          }
+        }
+      }
+      // residual of every carried vector against the span: e_j = S v_j - sum_k (v_k^T S v_j) v_k
+      T rmax = T(0);
+      ABRB_UNROLL
+      for (int j = 0; j < MV; ++j) {
+        if (j < m) {
+          T w[S_];
           ABRB_UNROLL
           for (int i = 0; i < S_; ++i) {
-            V1[i] -= d * V0[i];
-            nn += V1[i] * V1[i];
+            T acc = T(0);
+            ABRB_UNROLL
+            for (int l = 0; l < S_; ++l) acc += Sm[i][l] * V[j][l];
+            w[i] = acc;
           }
-          sc = T(1) / sqrt_t(nn);
           ABRB_UNROLL
-          for (int i = 0; i < S_; ++i) V1[i] *= sc;
+          for (int k = 0; k < MV; ++k) {
+            if (k < m) {
+              T a = T(0);
+              ABRB_UNROLL
+              for (int i = 0; i < S_; ++i) a += V[k][i] * w[i];
+              // (w is updated in place: the v_k are orthonormal, so later coefficients are unaffected to rounding)
+              ABRB_UNROLL
+              for (int i = 0; i < S_; ++i) w[i] -= a * V[k][i];
+            }
+          }
+          T r = T(0);
+          ABRB_UNROLL
+          for (int i = 0; i < S_; ++i) r += w[i] * w[i];
+          rmax = (r <= rmax) ? rmax : r;  // a NaN residual propagates and fails the test below
         }
       }
-      T w0[S_], w1[S_], a00 = T(0), a01 = T(0), a11 = T(0);
-      ABRB_UNROLL
-      for (int i = 0; i < S_; ++i) {
-        T acc0 = T(0), acc1 = T(0);
-        ABRB_UNROLL
-        for (int j = 0; j < S_; ++j) {
-          acc0 += Sm[i][j] * V0[j];
-          acc1 += Sm[i][j] * V1[j];
-        }
-        w0[i] = acc0;
-        w1[i] = acc1;
-        a00 += V0[i] * acc0;
-        a01 += V1[i] * acc0;
-        a11 += V1[i] * acc1;
-      }
-      T r0 = T(0), r1 = T(0);
-      ABRB_UNROLL
-      for (int i = 0; i < S_; ++i) {
-        const T e0 = w0[i] - a00 * V0[i] - (m == 2 ? a01 * V1[i] : T(0));
-        const T e1 = w1[i] - a11 * V1[i] - a01 * V0[i];
-        r0 += e0 * e0;
-        r1 += e1 * e1;
-      }
-      converged = (r0 <= tol * tol) && (m < 2 || r1 <= tol * tol);  // NaNs compare false
+      // The result P S^-1 P y is off by O(theta) (theta = angle between the iterate and the true span, ~ r / gap to
+      // the kept eigenvalues), so the residual is held to 1e-10 of the cutoff.  NaNs compare false.
+      converged = rmax <= tol * tol;
     }
     if (!converged) return false;
   }
-  // ---- 4. x = P S^-1 P y
-  T b[S_];
-  ABRB_UNROLL
-  for (int i = 0; i < S_; ++i) b[i] = y[i];
+  // ---- 4. x = P S^-1 P y   (for one or two right-hand sides: the eigenvectors are the expensive part)
   ABRB_NOUNROLL
-  for (int pass = 0; pass < 2; ++pass) {
-    if (m >= 1) {
-      T d0 = T(0), d1 = T(0);
+  for (int rhs = 0; rhs < (two ? 2 : 1); ++rhs) {
+    T b[S_];
+    ABRB_UNROLL
+    for (int i = 0; i < S_; ++i) b[i] = rhs == 0 ? y[i] : y2[i];
+    ABRB_NOUNROLL
+    for (int pass = 0; pass < 2; ++pass) {
       ABRB_UNROLL
-      for (int i = 0; i < S_; ++i) {
-        d0 += V0[i] * b[i];
-        d1 += V1[i] * b[i];
+      for (int j = 0; j < MV; ++j) {
+        if (j < m) {
+          T d = T(0);
+          ABRB_UNROLL
+          for (int i = 0; i < S_; ++i) d += V[j][i] * b[i];
+          ABRB_UNROLL
+          for (int i = 0; i < S_; ++i) b[i] -= d * V[j][i];
+        }
       }
-      if (m < 2) d1 = T(0);
-      ABRB_UNROLL
-      for (int i = 0; i < S_; ++i) b[i] -= d0 * V0[i] + d1 * V1[i];
+      if (pass == 0) {
+        fwd_solve<T, S_>(L, invd, b);
+        bwd_solve<T, S_>(L, invd, b);
+      }
     }
-    if (pass == 0) {
-      fwd_solve<T, S_>(L, invd, b);
-      bwd_solve<T, S_>(L, invd, b);
+    ABRB_UNROLL
+    for (int i = 0; i < S_; ++i) {
+      if (rhs == 0)
+        x[i] = b[i];
+      else
+        x2[i] = b[i];
     }
   }
-  ABRB_UNROLL
-  for (int i = 0; i < S_; ++i) x[i] = b[i];
   return true;
+}
+
+template <typename T, int S_>
+ABRB_HD bool pinv_solve_fast(const T (*Sm)[S_], const T (*L)[S_], const T *invd, unsigned active, T rcond,
+                             const T *y, T *x) {
+  return pinv_solve_fast2<T, S_>(Sm, L, invd, active, rcond, y, x, y, x, false);
 }
 
 // (Measured and dropped on B200, 6-DOF fp64 OSC kernel at 99 us: an out-of-line entry with private register copies of the

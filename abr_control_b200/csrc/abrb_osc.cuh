@@ -123,15 +123,16 @@ ABRB_HD T wrap_pm_pi(T d) {
 
 // One OSC evaluation.  KD = 3: only (a subset of) x,y,z controlled; KD = 6: any mask.
 // PLANT: also return ddq = M^-1 (u + g - C dq) for the rollout kernel.
-// defer_slow: if the state needs the eigen-decomposition (truncating pinv) path, return true WITHOUT computing u;
-// the kernel re-runs such states densely packed in a second pass (they are a few % of random states but would
-// otherwise drag most warps through the divergent slow path).  Returns false when u has been produced.
+// DEFER: if the state needs the truncating-pinv path, return true WITHOUT computing u (and without that path's code
+// in the instantiation); the caller queues such states for a second, densely packed launch (they are a few % of
+// random UR5 states but would otherwise drag most warps through the divergent slow path).  Returns false when u has
+// been produced.
 // `K`: caller-provided kinematic scratch (registers or shared memory).  Once the dynamics are done its t_k / z_k
 // slots are overwritten IN PLACE by the task Jacobian (column k of J only needs t_k, z_k), which later becomes
 // A = (L^-1 J^T)^T; so J, A never occupy registers of their own.
-template <typename T, int N, int KD, bool PLANT, class K_>
+template <typename T, int N, int KD, bool PLANT, bool DEFER = false, class K_>
 ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, const T *dq, const T *target,
-                       const T *tv, T *u, T *train, T *ddq, K_ &K, bool defer_slow = false) {
+                       const T *tv, T *u, T *train, T *ddq, K_ &K) {
   constexpr bool ORTHO = K_::kOrtho;
   typedef typename K_::S SL;
   K.sync();
@@ -341,61 +342,113 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
     }
     fast = rcond * tr * sqrt_t(fro) < T(1);
   }
-  if (!fast && defer_slow) return true;
-  auto mx_apply = [&](T *v) {  // v <- Mx v
-    if (fast) {
-      fwd_solve<T, KD>(Sc, Si, v);
-      bwd_solve<T, KD>(Sc, Si, v);
-    } else {
-      // cheap register-resident route first (inertia counts + inverse iteration, abrb_math.cuh); the rolled,
-      // local-memory Jacobi eigen-decomposition only when that is inconclusive.  Static indices everywhere: a
-      // rolled loop over S or v here would force them into local memory for the whole function.
-      const unsigned mask = O.dof_mask & ((1u << KD) - 1u);
-      // This branch always runs in double precision, also for the fp32 kernels: the matrices that end up here have
-      // eigenvalue ratios down to 1e-8, where a float Cholesky breaks down (and the FP64 pipe is idle there anyway).
-      double Sd[KD][KD], Ld[KD][KD], Sid[KD], yd[KD], xd[KD];
-      const double trd = double(trS);
+  if (DEFER && !fast) return true;
+  // ---- secondary controllers that go through the null-space filter  I - J^T Mx J M^-1  (osc.py:310-318): their
+  //      task-space image z = J M^-1 u_null is formed here so that Mx is applied to y and z in ONE place (the
+  //      truncating branch computes its eigenvectors once for both right-hand sides)
+  T z[KD];
+  ABRB_UNROLL
+  for (int r = 0; r < KD; ++r) z[r] = T(0);
+  if (any_null) {
+    if (any_avoid) {
+      T Lf[N * N];
       ABRB_UNROLL
-      for (int a = 0; a < KD; ++a) {
-        yd[a] = double(v[a]);
-        double ra[N];
+      for (int a = 0; a < N; ++a)
         ABRB_UNROLL
-        for (int k = 0; k < N; ++k) ra[k] = double(K.s.ld(Aslot(a, k)));
-        ABRB_UNROLL
-        for (int b = 0; b < KD; ++b) {
-          if (b <= a) {
-            double acc = 0.0;
-            ABRB_UNROLL
-            for (int k = 0; k < N; ++k) acc += ra[k] * double(K.s.ld(Aslot(b, k)));
-            const bool on = ((mask >> a) & 1u) && ((mask >> b) & 1u);
-            // inactive rows: decoupled, diagonal >= lambda_max so that they are never counted as truncated
-            const double val = on ? acc : (a == b ? trd : 0.0);
-            Sd[a][b] = val;
-            Sd[b][a] = val;
-          }
+      for (int b = 0; b < N; ++b) Lf[a * N + b] = M[a][b];
+      for (int i = 0; i < O.n_null; ++i) {
+        if (O.nul[i].kind == kNullAvoid) {
+          T ua[N], qa[N];  // private copies: only these (not the caller's register arrays) have their address taken
+          ABRB_UNROLL
+          for (int k = 0; k < N; ++k) qa[k] = q[k];
+          avoid_generate<T, N, ORTHO>(P, O.nul[i], qa, Lf, ua);
+          ABRB_UNROLL
+          for (int k = 0; k < N; ++k) un[k] += ua[k];
         }
       }
+    }
+    T w[N];
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) w[k] = un[k];
+    fwd_solve<T, N>(M, Mi, w);  // L^-1 u_null
+    ABRB_UNROLL
+    for (int r = 0; r < KD; ++r) {
+      T s = T(0);
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) s += K.s.ld(Aslot(r, k)) * w[k];
+      z[r] = ((O.dof_mask >> r) & 1u) ? s : T(0);
+    }
+  }
+  // y <- Mx y,  z <- Mx z
+  if (DEFER || fast) {
+    fwd_solve<T, KD>(Sc, Si, y);
+    bwd_solve<T, KD>(Sc, Si, y);
+    if (any_null) {
+      fwd_solve<T, KD>(Sc, Si, z);
+      bwd_solve<T, KD>(Sc, Si, z);
+    }
+  } else {
+    // cheap register-resident route first (inertia counts + inverse iteration, abrb_math.cuh); the rolled,
+    // local-memory Jacobi eigen-decomposition only when that is inconclusive.  Static indices everywhere: a
+    // rolled loop over S or v here would force them into local memory for the whole function.
+    const unsigned mask = O.dof_mask & ((1u << KD) - 1u);
+    // This branch always runs in double precision, also for the fp32 kernels: the matrices that end up here have
+    // eigenvalue ratios down to 1e-8, where a float Cholesky breaks down (and the FP64 pipe is idle there anyway).
+    double Sd[KD][KD], Ld[KD][KD], Sid[KD], yd[KD], xd[KD], zd[KD], xz[KD];
+    const double trd = double(trS);
+    ABRB_UNROLL
+    for (int a = 0; a < KD; ++a) {
+      yd[a] = double(y[a]);
+      zd[a] = double(z[a]);
+      double ra[N];
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) ra[k] = double(K.s.ld(Aslot(a, k)));
+      ABRB_UNROLL
+      for (int b = 0; b < KD; ++b) {
+        if (b <= a) {
+          double acc = 0.0;
+          ABRB_UNROLL
+          for (int k = 0; k < N; ++k) acc += ra[k] * double(K.s.ld(Aslot(b, k)));
+          const bool on = ((mask >> a) & 1u) && ((mask >> b) & 1u);
+          // inactive rows: decoupled, diagonal >= lambda_max so that they are never counted as truncated
+          const double val = on ? acc : (a == b ? trd : 0.0);
+          Sd[a][b] = val;
+          Sd[b][a] = val;
+        }
+      }
+    }
+    ABRB_UNROLL
+    for (int a = 0; a < KD; ++a)
+      ABRB_UNROLL
+    for (int b = 0; b < KD; ++b) Ld[a][b] = Sd[a][b];
+    const bool pdd = chol<double, KD>(Ld, Sid);
+    bool done = pdd && pinv_solve_fast2<double, KD>(Sd, Ld, Sid, mask, double(rcond), yd, xd, zd, xz, any_null);
+    if (!done) {
+      double Sf[KD * KD], yf[KD], xf[KD];
       ABRB_UNROLL
       for (int a = 0; a < KD; ++a)
         ABRB_UNROLL
-      for (int b = 0; b < KD; ++b) Ld[a][b] = Sd[a][b];
-      const bool pdd = chol<double, KD>(Ld, Sid);
-      bool done = pdd && pinv_solve_fast<double, KD>(Sd, Ld, Sid, mask, double(rcond), yd, xd);
-      if (!done) {
-        double Sf[KD * KD];
+      for (int b = 0; b < KD; ++b) Sf[a * KD + b] = (a == b && !((mask >> a) & 1u)) ? 1.0 : Sd[a][b];
+      ABRB_NOUNROLL
+      for (int rhs = 0; rhs < (any_null ? 2 : 1); ++rhs) {
         ABRB_UNROLL
-        for (int a = 0; a < KD; ++a)
-          ABRB_UNROLL
-        for (int b = 0; b < KD; ++b) Sf[a * KD + b] = (a == b && !((mask >> a) & 1u)) ? 1.0 : Sd[a][b];
-        pinv_apply_sym<double, KD>(Sf, mask, double(rcond), yd, xd);
+        for (int a = 0; a < KD; ++a) yf[a] = rhs == 0 ? yd[a] : zd[a];
+        pinv_apply_sym<double, KD>(Sf, mask, double(rcond), yf, xf);
+        ABRB_UNROLL
+        for (int a = 0; a < KD; ++a) {
+          if (rhs == 0)
+            xd[a] = xf[a];
+          else
+            xz[a] = xf[a];
+        }
       }
-      T xo[KD];
-      ABRB_UNROLL
-      for (int a = 0; a < KD; ++a) xo[a] = T(xd[a]);
-      ABRB_UNROLL
-      for (int a = 0; a < KD; ++a) v[a] = xo[a];
     }
-  };
+    ABRB_UNROLL
+    for (int a = 0; a < KD; ++a) {
+      y[a] = T(xd[a]);
+      if (any_null) z[a] = T(xz[a]);
+    }
+  }
   // J^T x = L (A^T x)   (osc.py:285-288)
   auto JT_apply = [&](const T *x, T *out) {
     T w[N];
@@ -415,7 +468,6 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
       out[i] = s;
     }
   };
-  mx_apply(y);
   {
     T jt[N];
     JT_apply(y, jt);
@@ -434,37 +486,9 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) u[k] -= g[k];
   }
-  // ---- secondary controllers through the null-space filter  I - J^T Mx J M^-1   (osc.py:310-318)
+  // ---- secondary controllers, filtered:  u += u_null - J^T Mx J M^-1 u_null   (osc.py:310-318)
   if (any_null) {
-    if (any_avoid) {
-      T Lf[N * N];
-      ABRB_UNROLL
-      for (int a = 0; a < N; ++a)
-        ABRB_UNROLL
-      for (int b = 0; b < N; ++b) Lf[a * N + b] = M[a][b];
-      for (int i = 0; i < O.n_null; ++i) {
-        if (O.nul[i].kind == kNullAvoid) {
-          T ua[N], qa[N];  // private copies: only these (not the caller's register arrays) have their address taken
-          ABRB_UNROLL
-          for (int k = 0; k < N; ++k) qa[k] = q[k];
-          avoid_generate<T, N, ORTHO>(P, O.nul[i], qa, Lf, ua);
-          ABRB_UNROLL
-          for (int k = 0; k < N; ++k) un[k] += ua[k];
-        }
-      }
-    }
-    T w[N], z[KD], jt[N];
-    ABRB_UNROLL
-    for (int k = 0; k < N; ++k) w[k] = un[k];
-    fwd_solve<T, N>(M, Mi, w);  // L^-1 u_null
-    ABRB_UNROLL
-    for (int r = 0; r < KD; ++r) {
-      T s = T(0);
-      ABRB_UNROLL
-      for (int k = 0; k < N; ++k) s += K.s.ld(Aslot(r, k)) * w[k];
-      z[r] = ((O.dof_mask >> r) & 1u) ? s : T(0);
-    }
-    mx_apply(z);
+    T jt[N];
     JT_apply(z, jt);
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) u[k] += un[k] - jt[k];
@@ -526,6 +550,123 @@ ABRB_HD void null_state(const ChainK<T, N> &P, const NullK<T, N> &Z, const T *q,
     for (int b = 0; b < N; ++b) s += M[a][b] * w[b];
     u[a] = s;
   }
+}
+
+// Joint.generate (controllers/joint.py:104-131)
+template <typename T, int N, class K_>
+ABRB_HD void joint_state(const ChainK<T, N> &P, T kp, T kv, bool gravity, const T *q, const T *dq, const T *target,
+                         const T *tv, T *u, K_ &K) {
+  walk<T, N>(P, q, 0, K);
+  T M[N][N], g[N];
+  dynamics_Mg<T, N, false>(P, K, dq, M, g, nullptr);
+  T w[N];
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) w[k] = kp * wrap_pm_pi(target[k] - q[k]) + kv * ((tv != nullptr ? tv[k] : T(0)) - dq[k]);
+  ABRB_UNROLL
+  for (int a = 0; a < N; ++a) {
+    T s = T(0);
+    ABRB_UNROLL
+    for (int b = 0; b < N; ++b) s += (b >= a ? M[a][b] : M[b][a]) * w[b];
+    u[a] = gravity ? s - g[a] : s;
+  }
+}
+
+// Floating.generate (controllers/floating.py:27-71)
+template <typename T, int N, class K_>
+ABRB_HD void floating_state(const ChainK<T, N> &P, bool task_space, bool dynamic, const T *q, const T *dq, T *u,
+                            K_ &K) {
+  constexpr bool ORTHO = K_::kOrtho;
+  walk<T, N>(P, q, 2 * N + 1, K);
+  T M[N][N], g[N];
+  dynamics_Mg<T, N, false>(P, K, dq, M, g, nullptr);
+  ABRB_UNROLL
+  for (int a = 0; a < N; ++a)
+    ABRB_UNROLL
+  for (int b = 0; b < N; ++b)
+    if (b < a) M[a][b] = M[b][a];
+  T Mdq[N];
+  ABRB_UNROLL
+  for (int a = 0; a < N; ++a) {
+    T s = T(0);
+    ABRB_UNROLL
+    for (int b = 0; b < N; ++b) s += M[a][b] * dq[b];
+    Mdq[a] = s;
+  }
+  if (!task_space) {
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) u[k] = -g[k] - (dynamic ? Mdq[k] : T(0));
+    return;
+  }
+  // J = J("EE")[:3];  A = (L^-1 J^T)^T;  S = J M^-1 J^T;  u = J^T (-Mx^T J M^-1 g) = -L A^T Mx A (L^-1 g)
+  T pF[3] = {K.F[3], K.F[7], K.F[11]};
+  T J[6][N];
+  jacobian<T, N>(K, pF, N, J);
+  T Mi[N];
+  chol<T, N>(M, Mi);
+  T A[3][N];
+  ABRB_UNROLL
+  for (int r = 0; r < 3; ++r) {
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) A[r][k] = J[r][k];
+    fwd_solve<T, N>(M, Mi, A[r]);
+  }
+  T S[3][3], Sc[3][3], Si[3];
+  ABRB_UNROLL
+  for (int a = 0; a < 3; ++a)
+    ABRB_UNROLL
+  for (int b = 0; b < 3; ++b) {
+    T s = T(0);
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) s += A[a][k] * A[b][k];
+    S[a][b] = s;
+    Sc[a][b] = s;
+  }
+  const bool pd = chol<T, 3>(Sc, Si);
+  T det = T(1);
+  ABRB_UNROLL
+  for (int a = 0; a < 3; ++a) det *= Sc[a][a] * Sc[a][a];
+  T w[N], z[3];
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) w[k] = g[k];
+  fwd_solve<T, N>(M, Mi, w);
+  ABRB_UNROLL
+  for (int r = 0; r < 3; ++r) {
+    T s = T(0);
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) s += A[r][k] * w[k];
+    z[r] = s;
+  }
+  if (pd && det > T(1e-3)) {  // note the strict '>' of floating.py:52 (osc.py uses '>=')
+    fwd_solve<T, 3>(Sc, Si, z);
+    bwd_solve<T, 3>(Sc, Si, z);
+  } else {
+    T Sf[9], zi[3], zo[3];
+    ABRB_UNROLL
+    for (int a = 0; a < 3; ++a) {
+      zi[a] = z[a];
+      ABRB_UNROLL
+      for (int b = 0; b < 3; ++b) Sf[a * 3 + b] = S[a][b];
+    }
+    pinv_apply_sym<T, 3>(Sf, 7u, T(1e-4), zi, zo);
+    ABRB_UNROLL
+    for (int a = 0; a < 3; ++a) z[a] = zo[a];
+  }
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) {
+    T s = T(0);
+    ABRB_UNROLL
+    for (int r = 0; r < 3; ++r) s += A[r][k] * z[r];
+    w[k] = s;
+  }
+  ABRB_UNROLL
+  for (int i = 0; i < N; ++i) {
+    T s = T(0);
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k)
+      if (k <= i) s += M[i][k] * w[k];
+    u[i] = -s - (dynamic ? Mdq[i] : T(0));
+  }
+  (void)ORTHO;
 }
 
 }  // namespace abrb

@@ -4,9 +4,13 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
+#include <utility>
 
 #include "abrb_launch.hpp"
 
@@ -17,9 +21,17 @@ struct abrb_model {
   ChainHost host;
 };
 
+// Index queue of the two-launch OSC mode (kernels.cu): one per (device, stream) the controller has been used on.
+struct SlowQueue {
+  int *buf = nullptr;
+  int64_t cap = 0;
+};
+
 struct abrb_osc {
   const abrb_model *model;
   abrb_osc_params params;
+  mutable std::mutex mu;
+  mutable std::map<std::pair<int, cudaStream_t>, SlowQueue> queues;
 };
 
 namespace {
@@ -233,8 +245,51 @@ int abrb_osc_create(const abrb_model *m, const abrb_osc_params *p, abrb_osc **ou
 }
 
 int abrb_osc_destroy(abrb_osc *c) {
+  if (c) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto &kv : c->queues) {
+      cudaSetDevice(kv.first.first);
+      cudaFree(kv.second.buf);
+    }
+    cudaSetDevice(cur);
+  }
   delete c;
   return ABRB_OK;
+}
+
+// Two-launch mode (kernels.cu, osc_kernel<DEFER> + osc_slow_kernel): used for the 6-row task space from
+// ABRB_OSC_DEFER_MIN states up (default 16384; ABRB_OSC_DEFER=0 turns it off).  Returns the queue for this
+// (device, stream), growing it on demand, or nullptr for the single-launch mode.
+static int *slow_queue_for(const abrb_osc *c, int64_t B, cudaStream_t stream, int *err) {
+  static const int64_t min_b = [] {
+    const char *off = std::getenv("ABRB_OSC_DEFER");
+    if (off && off[0] == '0') return (int64_t)-1;
+    const char *m = std::getenv("ABRB_OSC_DEFER_MIN");
+    return m ? (int64_t)std::atoll(m) : (int64_t)16384;
+  }();
+  *err = 0;
+  const abrb_osc_params &p = c->params;
+  if (min_b < 0 || B < min_b || B > (int64_t)0x7fffffff - 8) return nullptr;
+  if (!(p.ctrlr_dof[3] || p.ctrlr_dof[4] || p.ctrlr_dof[5])) return nullptr;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(c->mu);
+  SlowQueue &sq = c->queues[std::make_pair(dev, stream)];
+  if (sq.cap < B) {
+    cudaError_t e = cudaSuccess;
+    if (sq.buf) e = cudaFree(sq.buf);  // synchronises with any launch still using it
+    sq.buf = nullptr;
+    sq.cap = 0;
+    if (e == cudaSuccess) e = cudaMalloc(&sq.buf, (size_t)(B + 4) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(sq.buf, 0, 4 * sizeof(int), stream);
+    if (e != cudaSuccess) {
+      *err = (int)e;
+      return nullptr;
+    }
+    sq.cap = B;
+  }
+  return sq.buf;
 }
 
 static int osc_generate(const abrb_osc *c, int frame_id, const double *x_off, const void *q, const void *dq,
@@ -254,6 +309,9 @@ static int osc_generate(const abrb_osc *c, int frame_id, const double *x_off, co
   int rc = ensure_device();
   if (rc) return rc;
   OscCall k{frame_id, x_off, q, dq, target, tv, target_stride, tv_stride, u, train, B, f32, (cudaStream_t)stream};
+  int qe = 0;
+  k.queue = slow_queue_for(c, B, (cudaStream_t)stream, &qe);
+  if (qe) return cuda_fail(qe, "abrb_osc_generate (index queue)");
   int e = cudaErrorInvalidValue;
   switch (n) {
 #define X(j) case j: e = launch_osc<j>(c->model->host, c->params, k); break;
@@ -372,6 +430,55 @@ int abrb_null_generate_f64(const abrb_model *m, const abrb_null_params *p, const
 int abrb_null_generate_f32(const abrb_model *m, const abrb_null_params *p, const float *q, const float *dq, float *u,
                            int64_t B, void *stream) {
   return null_generate(m, p, q, dq, u, B, stream, true);
+}
+
+// ------------------------------------------------------------------------------------------------ joint / floating
+static int ctrl_generate(const abrb_model *m, int kind, double kp, double kv, int fa, int fb, const void *q,
+                         const void *dq, const void *target, int target_stride, const void *tv, int tv_stride, void *u,
+                         int64_t B, void *stream, bool f32, const char *who) {
+  if (!m) return fail(ABRB_EINVAL, std::string(who) + ": NULL model");
+  if (B < 0) return fail(ABRB_EINVAL, std::string(who) + ": B < 0");
+  const int n = m->host.n;
+  if (kind == 0 && ((target_stride != 0 && target_stride != n) || (tv && tv_stride != 0 && tv_stride != n)))
+    return fail(ABRB_EINVAL, std::string(who) + ": stride must be 0 (broadcast) or n_joints");
+  if (B == 0) return ABRB_OK;
+  if (!q || !u || (kind == 0 && (!dq || !target)) || (kind == 1 && fb && !dq))
+    return fail(ABRB_EINVAL, std::string(who) + ": NULL q/dq/target/u");
+  if (!aligned16(q) || !aligned16(u) || (dq && !aligned16(dq)))
+    return fail(ABRB_EINVAL, std::string(who) + ": pointers must be 16-byte aligned");
+  int rc = ensure_device();
+  if (rc) return rc;
+  CtrlCall k{kind, kp, kv, fa, fb, q, dq, target, tv, target_stride, tv_stride, u, B, f32, (cudaStream_t)stream};
+  int e = cudaErrorInvalidValue;
+  switch (n) {
+#define X(j) case j: e = launch_ctrl<j>(m->host, k); break;
+    ABRB_N_LIST(X)
+#undef X
+  }
+  return e ? cuda_fail(e, who) : ABRB_OK;
+}
+
+int abrb_joint_generate_f64(const abrb_model *m, double kp, double kv, int account_for_gravity, const double *q,
+                            const double *dq, const double *target, int target_stride, const double *target_velocity,
+                            int tv_stride, double *u, int64_t B, void *stream) {
+  return ctrl_generate(m, 0, kp, kv, account_for_gravity, 0, q, dq, target, target_stride, target_velocity, tv_stride, u,
+                       B, stream, false, "abrb_joint_generate");
+}
+int abrb_joint_generate_f32(const abrb_model *m, double kp, double kv, int account_for_gravity, const float *q,
+                            const float *dq, const float *target, int target_stride, const float *target_velocity,
+                            int tv_stride, float *u, int64_t B, void *stream) {
+  return ctrl_generate(m, 0, kp, kv, account_for_gravity, 0, q, dq, target, target_stride, target_velocity, tv_stride, u,
+                       B, stream, true, "abrb_joint_generate");
+}
+int abrb_floating_generate_f64(const abrb_model *m, int task_space, int dynamic, const double *q, const double *dq,
+                               double *u, int64_t B, void *stream) {
+  return ctrl_generate(m, 1, 0, 0, task_space, dynamic, q, dq, nullptr, 0, nullptr, 0, u, B, stream, false,
+                       "abrb_floating_generate");
+}
+int abrb_floating_generate_f32(const abrb_model *m, int task_space, int dynamic, const float *q, const float *dq, float *u,
+                               int64_t B, void *stream) {
+  return ctrl_generate(m, 1, 0, 0, task_space, dynamic, q, dq, nullptr, 0, nullptr, 0, u, B, stream, true,
+                       "abrb_floating_generate");
 }
 
 // ------------------------------------------------------------------------------------------------ rollout

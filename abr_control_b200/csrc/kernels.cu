@@ -183,13 +183,15 @@ struct OscArgs {
   T *u, *train;
   int64_t B;
   int target_stride, tv_stride;
+  int *queue;  // two-launch mode: queue[0] = number of deferred states, queue[1] = CTA ticket, queue[4..] = their indices
 };
 
-// One pass: the few states that need the truncating pseudo-inverse take the register-resident inertia-count route
-// in line.  Deferring them was measured slower on B200 at B = 65536 both ways: re-running them densely in a second
-// pass of the same CTA (the other warps idle at the barrier: 269 us) and in a second launch fed by a global index
-// queue (the ~2.5 k deferred states are too few to fill the machine, so that launch is pure latency: 123 vs 103 us).
-template <typename T, int N, bool ORTHO, int KD, bool KSMEM>
+// DEFER = false: one pass, the states that need the truncating pseudo-inverse take that route in line.  For random
+// UR5 6-DOF states that is 3.8 % of the states but 70 % of the warps, each of which then serialises a long divergent
+// path for one or two lanes (39 us without those states, ~100 us with them at B = 65 536).
+// DEFER = true: the instantiation has no truncating code at all; such states are appended to a global index queue
+// (one warp-aggregated atomic) and osc_slow_kernel re-runs them densely packed.
+template <typename T, int N, bool ORTHO, int KD, bool KSMEM, bool DEFER>
 __global__ void __launch_bounds__(kBlock, MinBlocks<T>::value)
 osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
            const __grid_constant__ OscArgs<T> a) {
@@ -213,15 +215,79 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
     for (int k = 0; k < N; ++k) {
       q[k] = a.q[b * N + k];
       dq[k] = a.dq[b * N + k];
+      u[k] = T(0);
+      tr[k] = T(0);
     }
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       tg[c] = a.target[b * a.target_stride + c];
       tv[c] = a.tv != nullptr ? a.tv[b * a.tv_stride + c] : T(0);
     }
-    osc_state<T, N, KD, false>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, u, tr, nullptr, K);
-    store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);
+    const bool slow =
+        osc_state<T, N, KD, false, DEFER>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, u, tr, nullptr, K);
+    if (DEFER) {
+      const bool push = slow && lane < nvalid;
+      const unsigned m = __ballot_sync(0xffffffffu, push);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        int pos = 0;
+        if (lane == leader) pos = atomicAdd(a.queue, __popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, leader);
+        if (push) a.queue[4 + pos + __popc(m & ((1u << lane) - 1u))] = (int)b;
+      }
+    }
+    store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);  // deferred states: placeholder, rewritten below
     if (a.train) store_records<T, N>(a.train, warp_b0, nvalid, tr, stage, lane);
+  }
+}
+
+// Second launch of the two-launch mode: one warp per CTA so that the ~2.5 k deferred states of a 65 536-state batch
+// spread over as many SMs as possible (the launch is latency bound).  The last CTA to finish re-arms the queue.
+constexpr int kSlowBlock = 32;
+template <typename T, int N, bool ORTHO, int KD, bool KSMEM>
+__global__ void __launch_bounds__(kSlowBlock)
+osc_slow_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
+                const __grid_constant__ OscArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef KinSel<T, N, ORTHO, KSMEM> KS;
+  const int lane = threadIdx.x;
+  T *region = reinterpret_cast<T *>(smem_raw);
+  typename KS::type K;
+  KS::bind(K, region, lane);
+  const int count = *static_cast<volatile int *>(a.queue);
+  for (int base = blockIdx.x * kSlowBlock; base < count; base += gridDim.x * kSlowBlock) {
+    const int i = base + lane;
+    const bool valid = i < count;
+    const int64_t b = a.queue[4 + (valid ? i : count - 1)];
+    T q[N], dq[N], tg[6], tv[6], u[N], tr[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      q[k] = a.q[b * N + k];
+      dq[k] = a.dq[b * N + k];
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      tg[c] = a.target[b * a.target_stride + c];
+      tv[c] = a.tv != nullptr ? a.tv[b * a.tv_stride + c] : T(0);
+    }
+    osc_state<T, N, KD, false, false>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, u, tr, nullptr, K);
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        a.u[b * N + k] = u[k];
+        if (a.train) a.train[b * N + k] = tr[k];
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(reinterpret_cast<unsigned *>(a.queue + 1), 1u);
+    if (t == gridDim.x - 1) {  // every CTA has read `count` before it took its ticket
+      a.queue[0] = 0;
+      a.queue[1] = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -312,8 +378,47 @@ null_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ Null
   }
 }
 
+template <typename T>
+struct CtrlArgs {
+  const T *q, *dq, *target, *tv;
+  T *u;
+  int64_t B;
+  int target_stride, tv_stride, kind, flag_a, flag_b;
+  T kp, kv;
+};
+
+// Joint.generate / Floating.generate: small relatives of the kernels above (M, g, one product or one 3x3 solve)
+template <typename T, int N, bool ORTHO>
+__global__ void __launch_bounds__(kBlock)
+ctrl_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ CtrlArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T *stage = reinterpret_cast<T *>(smem_raw) + warp * kPitch * N;
+  for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
+    const int64_t warp_b0 = base + warp * 32;
+    if (warp_b0 >= a.B) break;
+    const int64_t rem = a.B - warp_b0;
+    const int nvalid = rem < 32 ? (int)rem : 32;
+    const int64_t b = warp_b0 + (lane < nvalid ? lane : nvalid - 1);
+    T q[N], dq[N], tg[N], tv[N], u[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      q[k] = a.q[b * N + k];
+      dq[k] = a.dq != nullptr ? a.dq[b * N + k] : T(0);
+      tg[k] = a.target != nullptr ? a.target[b * a.target_stride + k] : T(0);
+      tv[k] = a.tv != nullptr ? a.tv[b * a.tv_stride + k] : T(0);
+    }
+    Kin<T, N, ORTHO> K;
+    if (a.kind == 0)
+      joint_state<T, N>(P, a.kp, a.kv, a.flag_a != 0, q, dq, tg, a.tv != nullptr ? tv : nullptr, u, K);
+    else
+      floating_state<T, N>(P, a.flag_a != 0, a.flag_b != 0, q, dq, u, K);
+    store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ launch
-inline int grid_for(int64_t B, int blocks_per_sm) {
+inline int num_sms() {
   static int sm_count = 0;
   if (sm_count == 0) {
     int dev = 0;
@@ -321,8 +426,12 @@ inline int grid_for(int64_t B, int blocks_per_sm) {
     if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
       sm_count = 148;
   }
+  return sm_count;
+}
+
+inline int grid_for(int64_t B, int blocks_per_sm) {
   const int64_t tiles = (B + kBlock - 1) / kBlock;
-  const int64_t cap = (int64_t)sm_count * blocks_per_sm;
+  const int64_t cap = (int64_t)num_sms() * blocks_per_sm;
   return (int)(tiles < cap ? tiles : cap);
 }
 
@@ -406,9 +515,30 @@ int osc_go(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
   a.B = c.B;
   a.target_stride = c.target_stride;
   a.tv_stride = c.tv_stride;
+  a.queue = c.queue;
   constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32 || ABRB_ROLLED;  // rolled loops index the scratch at run time
   const size_t smem = (size_t)kWarps * WarpSmem<T, N, ORTHO, KSMEM, N>::kElems * sizeof(T);
-  auto kern = osc_kernel<T, N, ORTHO, KD, KSMEM>;
+  if constexpr (KD == 6) {
+    if (c.queue != nullptr) {
+      // two launches: everything but the truncating-pinv states, then those states densely packed
+      auto k1 = osc_kernel<T, N, ORTHO, 6, KSMEM, true>;
+      auto k2 = osc_slow_kernel<T, N, ORTHO, 6, KSMEM>;
+      const size_t smem2 = (size_t)WarpSmem<T, N, ORTHO, KSMEM, N>::kElems * sizeof(T);
+      cudaError_t e = set_smem(k1, smem);
+      if (e == cudaSuccess) e = set_smem(k2, smem2);
+      if (e != cudaSuccess) return (int)e;
+      k1<<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, O, a);
+      count_launch();
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return (int)e;
+      const int64_t want = (c.B + kSlowBlock - 1) / kSlowBlock;
+      const int64_t cap = (int64_t)num_sms() * 8;
+      k2<<<(unsigned)(want < cap ? want : cap), kSlowBlock, smem2, c.stream>>>(P, O, a);
+      count_launch();
+      return (int)cudaGetLastError();
+    }
+  }
+  auto kern = osc_kernel<T, N, ORTHO, KD, KSMEM, false>;
   cudaError_t e = set_smem(kern, smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, O, a);
@@ -464,6 +594,30 @@ inline bool needs_kd6(const abrb_osc_params &p) { return p.ctrlr_dof[3] || p.ctr
 
 }  // namespace
 
+template <typename T, int N, bool ORTHO>
+int ctrl_go(const ChainHost &h, const CtrlCall &c) {
+  ChainK<T, N> P;
+  fill_chain<T, N>(h, P);
+  CtrlArgs<T> a;
+  a.q = static_cast<const T *>(c.q);
+  a.dq = static_cast<const T *>(c.dq);
+  a.target = static_cast<const T *>(c.target);
+  a.tv = static_cast<const T *>(c.tv);
+  a.u = static_cast<T *>(c.u);
+  a.B = c.B;
+  a.target_stride = c.target_stride;
+  a.tv_stride = c.tv_stride;
+  a.kind = c.kind;
+  a.flag_a = c.flag_a;
+  a.flag_b = c.flag_b;
+  a.kp = T(c.kp);
+  a.kv = T(c.kv);
+  const size_t smem = (size_t)kWarps * kPitch * N * sizeof(T);
+  ctrl_kernel<T, N, ORTHO><<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, a);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 template <>
 int launch_rbd<ABRB_N>(const ChainHost &h, const RbdCall &c) {
   return c.f32 ? rbd_dispatch<float, ABRB_N>(h, c) : rbd_dispatch<double, ABRB_N>(h, c);
@@ -494,6 +648,12 @@ template <>
 int launch_null<ABRB_N>(const ChainHost &h, const abrb_null_params &z, const NullCall &c) {
   if (c.f32) return h.ortho ? null_go<float, ABRB_N, true>(h, z, c) : null_go<float, ABRB_N, false>(h, z, c);
   return h.ortho ? null_go<double, ABRB_N, true>(h, z, c) : null_go<double, ABRB_N, false>(h, z, c);
+}
+
+template <>
+int launch_ctrl<ABRB_N>(const ChainHost &h, const CtrlCall &c) {
+  if (c.f32) return h.ortho ? ctrl_go<float, ABRB_N, true>(h, c) : ctrl_go<float, ABRB_N, false>(h, c);
+  return h.ortho ? ctrl_go<double, ABRB_N, true>(h, c) : ctrl_go<double, ABRB_N, false>(h, c);
 }
 
 }  // namespace abrb

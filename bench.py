@@ -59,9 +59,12 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        period = os.environ.get("ABRB_BENCH_CLOCK_MS", "10")  # tuning knob: "off" disables the sampler (A/B only)
+        if period == "off":
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                       "10", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       period, "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             pass
 
@@ -316,7 +319,8 @@ def run_ours(args):
                     traffic = v["dram_mb_per_launch"] * 1e6  # bytes per launch (profiles/<tag>_osc.txt)
 
     extra = {}
-    if world == 1:
+    quick = bool(os.environ.get("ABRB_BENCH_QUICK"))  # tuning knob: headline + e2e only
+    if world == 1 and not quick:
         # the other single-GPU kernels, same timing discipline (explain the headline; not bench lines themselves)
         def rbd_sets(want, dtype):
             out = []
@@ -385,7 +389,7 @@ def run_ours(args):
         extra["osc_ur5_6dof_f32_B65536"] = {"evals_per_s": B / dt, "us_per_launch": dt * 1e6, "bytes_per_state": 96}
 
     cpu = None
-    if world == 1:
+    if world == 1 and not quick:
         cpu, u_cpu, (cq, cdq, ctg) = cpu_reference_run(4_000_000 if ref_lib() is not None else 300)
         # parity spot check in the same run: first 4096 states of the CPU sample against the GPU path
         m = min(4096, len(cq))

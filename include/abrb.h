@@ -178,6 +178,25 @@ int abrb_null_generate_f64(const abrb_model *m, const abrb_null_params *p, const
 int abrb_null_generate_f32(const abrb_model *m, const abrb_null_params *p, const float *q,
                            const float *dq, float *u, int64_t B, void *stream);
 
+/* Joint-space PD controller  Joint.generate(q, dq, target, target_velocity=None)
+ * (controllers/joint.py:104-131):  u = M (kp q_tilde + kv (target_velocity - dq)) [- g],
+ * q_tilde = ((target - q + pi) mod 2 pi) - pi  (joint.py:42-46; the ball-joint/quaternion branch is MuJoCo-only).
+ *   target (B,n) if target_stride == n, one (n,) row if 0;  target_velocity NULL or per tv_stride. */
+int abrb_joint_generate_f64(const abrb_model *m, double kp, double kv, int account_for_gravity, const double *q,
+                            const double *dq, const double *target, int target_stride,
+                            const double *target_velocity, int tv_stride, double *u, int64_t B, void *stream);
+int abrb_joint_generate_f32(const abrb_model *m, double kp, double kv, int account_for_gravity, const float *q,
+                            const float *dq, const float *target, int target_stride,
+                            const float *target_velocity, int tv_stride, float *u, int64_t B, void *stream);
+
+/* Gravity compensation  Floating.generate(q, dq)  (controllers/floating.py:27-71):
+ *   joint space:  u = -g;   task space:  u = J^T (-(M^-1 J^T Mx)^T g) with J = J("EE")[:3] and the reference's
+ *   inv / pinv(rcond=1e-4) switch at |det| > 1e-3;   dynamic: u -= M dq.   dq may be NULL unless dynamic. */
+int abrb_floating_generate_f64(const abrb_model *m, int task_space, int dynamic, const double *q, const double *dq,
+                               double *u, int64_t B, void *stream);
+int abrb_floating_generate_f32(const abrb_model *m, int task_space, int dynamic, const float *q, const float *dq,
+                               float *u, int64_t B, void *stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Closed-loop rollout: `steps` iterations of
  *     u = OSC.generate(q, dq, target);  ddq = M^-1 (u + g - C dq);  dq += ddq dt;  q += dq dt

@@ -85,6 +85,44 @@ class RestingConfig:
         return np.dot(self.rc.M(q), self.kp * q_tilde + self.kv * (0.0 - dq))
 
 
+class Joint:
+    """controllers/joint.py:104-131 (angle joints only)"""
+
+    def __init__(self, rc, kp=1, kv=None, account_for_gravity=True):
+        self.rc, self.kp, self.kv, self.grav = rc, kp, (np.sqrt(kp) if kv is None else kv), account_for_gravity
+
+    def generate(self, q, dq, target, target_velocity=None):
+        tvel = np.zeros(len(q)) if target_velocity is None else target_velocity
+        q_tilde = ((target - q + np.pi) % (np.pi * 2)) - np.pi
+        u = np.dot(self.rc.M(q), self.kp * q_tilde + self.kv * (tvel - dq))
+        return u - self.rc.g(q) if self.grav else u
+
+
+class Floating:
+    """controllers/floating.py:27-71"""
+
+    def __init__(self, rc, dynamic=False, task_space=False):
+        self.rc, self.dynamic, self.task_space = rc, dynamic, task_space
+
+    def generate(self, q, dq=None):
+        g = self.rc.g(q)
+        M = None
+        if self.task_space:
+            J = self.rc.J("EE", q)[:3]
+            M = self.rc.M(q)
+            M_inv = np.linalg.inv(M)
+            Mx_inv = np.dot(J, np.dot(M_inv, J.T))
+            Mx = np.linalg.inv(Mx_inv) if abs(np.linalg.det(Mx_inv)) > 1e-3 else np.linalg.pinv(Mx_inv, rcond=1e-4)
+            Jbar = np.dot(M_inv, np.dot(J.T, Mx))
+            u = np.dot(J.T, -1 * np.dot(Jbar.T, g))
+        else:
+            u = -g
+        if self.dynamic:
+            M = self.rc.M(q) if M is None else M
+            u = u - np.dot(M, dq)
+        return u
+
+
 def _segment_closest(p_a, p_b, centre):
     """closest point of segment [p_a, p_b] to ``centre`` (avoid_obstacles.py:69-83)."""
     seg = p_b - p_a
@@ -231,6 +269,20 @@ def run_case(case, q, dq, target, target_velocity=None, mode="fp64"):
         us.append(np.asarray(ctrlr.generate(q[i], dq[i], target[i], **kw), dtype=np.float64))
         ts.append(np.asarray(ctrlr.training_signal, dtype=np.float64))
     return np.array(us), np.array(ts)
+
+
+def run_ctrl_case(case, q, dq, target_q, target_dq, mode="fp64"):
+    """tests/cases.py::CTRL_CASES -> (B, n)"""
+    rc = RobotOracle(case["arm"], mode)
+    kind, kw = case["ctrl"]
+    out = []
+    for i in range(len(q)):
+        if kind == "Joint":
+            c = Joint(rc, **kw)
+            out.append(c.generate(q[i], dq[i], target_q[i], target_dq[i] if case.get("tv") else None))
+        else:
+            out.append(Floating(rc, **kw).generate(q[i], dq[i]))
+    return np.array(out, dtype=np.float64)
 
 
 def run_null_case(case, q, dq, mode="fp64"):

@@ -129,6 +129,23 @@ def main(arm, phase):
         osc_out[f"{name}__null64"] = stack(lambda i: ctrl.generate(q[i], dq[i]))
         print(f"[{arm}] null case {name} done {time.time()-t0:.0f}s", flush=True)
 
+    tq, tdq = cases.joint_targets(arm)
+    osc_out["joint_target"], osc_out["joint_target_velocity"] = tq, tdq
+    from abr_control.controllers import Floating, Joint
+
+    for name, c in cases.CTRL_CASES.items():
+        if c["arm"] != arm:
+            continue
+        kind, kw = c["ctrl"]
+        if kind == "Joint":
+            ctrl = Joint(rc, **kw)
+            osc_out[f"{name}__ctrl64"] = stack(
+                lambda i: ctrl.generate(q[i], dq[i], tq[i], tdq[i] if c.get("tv") else None))
+        else:
+            ctrl = Floating(rc, **kw)
+            osc_out[f"{name}__ctrl64"] = stack(lambda i: ctrl.generate(q[i], dq[i]))
+        print(f"[{arm}] ctrl case {name} done {time.time()-t0:.0f}s", flush=True)
+
     # the reference's own pinned quantities for OSC helpers (controllers/tests/test_osc.py:19-59)
     if phase == "eval":
         gdir = os.path.join(REPO, "tests", "golden")

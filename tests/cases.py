@@ -131,3 +131,19 @@ NULL_CASES = {
         arm="threejoint", ctrl=("RestingConfig", dict(kp=50, kv=float(np.sqrt(50)), rest_angles=[PI / 4, PI, None]))
     ),
 }
+
+# joint-space controllers: Joint.generate(q, dq, target, target_velocity) and Floating.generate(q, dq)
+CTRL_CASES = {
+    "ur5_joint": dict(arm="ur5", ctrl=("Joint", dict(kp=25, kv=7)), tv=True),
+    "jaco2_joint_nograv": dict(arm="jaco2", ctrl=("Joint", dict(kp=10, account_for_gravity=False))),
+    "ur5_floating": dict(arm="ur5", ctrl=("Floating", dict())),
+    "ur5_floating_task_dyn": dict(arm="ur5", ctrl=("Floating", dict(task_space=True, dynamic=True))),
+    "jaco2_floating_task": dict(arm="jaco2", ctrl=("Floating", dict(task_space=True))),
+    "threejoint_joint": dict(arm="threejoint", ctrl=("Joint", dict(kp=50))),
+}
+
+
+def joint_targets(arm, count=N_GOLDEN):
+    n = ARMS[arm]["n"]
+    rng = np.random.default_rng(hash_name(arm) + 17)
+    return rng.uniform(-2 * np.pi, 4 * np.pi, (count, n)), rng.uniform(-1, 1, (count, n))

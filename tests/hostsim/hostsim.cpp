@@ -93,6 +93,28 @@ void null_loop(const ChainHost &h, const abrb_null_params &z, const double *q, c
   }
 }
 
+template <typename T, int N, bool ORTHO>
+void ctrl_loop(const ChainHost &h, int kind, double kp, double kv, int fa, int fb, const double *q, const double *dq,
+               const double *target, const double *tv, int64_t B, double *u) {
+  ChainK<T, N> P;
+  fill_chain<T, N>(h, P);
+  for (int64_t b = 0; b < B; ++b) {
+    T qq[N], dd[N], tg[N], tvv[N], uu[N];
+    for (int k = 0; k < N; ++k) {
+      qq[k] = T(q[b * N + k]);
+      dd[k] = dq ? T(dq[b * N + k]) : T(0);
+      tg[k] = target ? T(target[b * N + k]) : T(0);
+      tvv[k] = tv ? T(tv[b * N + k]) : T(0);
+    }
+    Kin<T, N, ORTHO> K;
+    if (kind == 0)
+      joint_state<T, N>(P, T(kp), T(kv), fa != 0, qq, dd, tg, tv ? tvv : nullptr, uu, K);
+    else
+      floating_state<T, N>(P, fa != 0, fb != 0, qq, dd, uu, K);
+    for (int k = 0; k < N; ++k) u[b * N + k] = double(uu[k]);
+  }
+}
+
 }  // namespace
 
 #define DISPATCH_N(FN, ...)                                       \
@@ -150,6 +172,15 @@ int hs_null(const abrb_chain_desc *d, const abrb_null_params *z, int f32, int fo
   if (!chain_from_desc(*d, h).empty()) return ABRB_EINVAL;
   const bool ortho = h.ortho && !force_general;
   DISPATCH_N(null_loop, h, *z, q, dq, B, u);
+  return 0;
+}
+
+int hs_ctrl(const abrb_chain_desc *d, int f32, int force_general, int kind, double kp, double kv, int fa, int fb,
+            const double *q, const double *dq, const double *target, const double *tv, int64_t B, double *u) {
+  ChainHost h;
+  if (!chain_from_desc(*d, h).empty()) return ABRB_EINVAL;
+  const bool ortho = h.ortho && !force_general;
+  DISPATCH_N(ctrl_loop, h, kind, kp, kv, fa, fb, q, dq, target, tv, B, u);
   return 0;
 }
 

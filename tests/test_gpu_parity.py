@@ -161,6 +161,43 @@ def test_null_controllers_vs_reference_golden(name):
     _close(u, ref, 1e-8, 1e-9 * max(1.0, np.abs(ref).max()), name)
 
 
+@pytest.mark.parametrize("name", list(cases.CTRL_CASES))
+def test_joint_and_floating_vs_reference_golden(name):
+    import torch
+
+    from abr_control_b200 import controllers
+
+    cs = cases.CTRL_CASES[name]
+    o = np.load(f"{GOLD}/{cs['arm']}_osc.npz")
+    q, dq, tq, tdq = o["q"], o["dq"], o["joint_target"], o["joint_target_velocity"]
+    ref = o[f"{name}__ctrl64"]
+    kind, kw = cs["ctrl"]
+    for dtype, tol in ((np.float64, 1e-9), (np.float32, 2e-3)):
+        rc = _cfg(cs["arm"], dtype=dtype)
+        ctrl = getattr(controllers, kind)(rc, **kw)
+        cast = lambda a: a.astype(dtype)  # noqa: E731
+        if kind == "Joint":
+            u = ctrl.generate(cast(q), cast(dq), cast(tq), cast(tdq) if cs.get("tv") else None)
+            one = ctrl.generate(q[0], dq[0], tq[0], tdq[0] if cs.get("tv") else None)
+        else:
+            u = ctrl.generate(cast(q), cast(dq))
+            one = ctrl.generate(q[0], dq[0])
+        assert u.dtype == dtype and u.shape == ref.shape
+        scale = np.abs(ref).max(axis=1, keepdims=True) + 1e-12
+        assert (np.abs(u - ref) / scale).max() < tol, (name, dtype)
+        assert one.shape == ref[0].shape and one.dtype == np.float64
+        assert np.abs(one - ref[0]).max() < 1e-9 * max(1.0, np.abs(ref[0]).max())
+    # CUDA tensors in -> CUDA tensor out
+    rc = _cfg(cs["arm"])
+    ctrl = getattr(controllers, kind)(rc, **kw)
+    tq_, tdq_ = torch.as_tensor(q, device="cuda"), torch.as_tensor(dq, device="cuda")
+    if kind == "Joint":
+        ud = ctrl.generate(tq_, tdq_, torch.as_tensor(tq, device="cuda"))
+    else:
+        ud = ctrl.generate(tq_, tdq_)
+    assert ud.is_cuda and ud.shape == ref.shape
+
+
 def test_single_state_contract():
     """One state in -> the reference's shapes/dtypes out (float32 J/M/g/C/R, float64 Tx/T/T_inv, fresh arrays)."""
     from abr_control_b200.controllers import OSC
@@ -267,6 +304,42 @@ def test_large_batch_deferred_pinv_states():
         # and identical to evaluating the same rows in a small batch
         small = ctrlr.generate(q[slow[:64]].astype(dtype), dq[slow[:64]].astype(dtype), target[slow[:64]].astype(dtype))
         assert np.allclose(small, u[slow[:64]], rtol=1e-9 if dtype == np.float64 else 1e-4, atol=0)
+
+
+def test_two_launch_mode_matches_single_launch():
+    """From 16384 states up the 6-row OSC path runs as two launches (everything but the truncating-pinv states, then
+    those states from an index queue; abr_control_b200/csrc/kernels.cu).  It must agree with the single-launch mode
+    (the same rows in chunks below the threshold) for every row, repeatedly (the queue re-arms itself), for batch
+    sizes that grow, shrink and are not multiples of the warp size, with and without the training-signal output."""
+    import torch
+
+    rng = np.random.default_rng(23)
+    case = dict(arm="ur5", osc=dict(kp=50, ctrlr_dof=[True] * 6, use_C=True), null=[("Damping", dict(kv=10))])
+    for dtype, tol in ((np.float64, 1e-9), (np.float32, 2e-3)):
+        rc = _cfg("ur5", dtype=dtype)
+        ctrlr = _build_ctrl(rc, case)
+        for B in (20000, 40003, 16384):
+            q = rng.uniform(0, 2 * np.pi, (B, 6)).astype(dtype)
+            dq = rng.uniform(0, 5, (B, 6)).astype(dtype)
+            target = rng.uniform(-1, 1, (B, 6)).astype(dtype)
+            tv = rng.uniform(-0.5, 0.5, (B, 6)).astype(dtype)
+            for kw in ({}, {"target_velocity": tv}):
+                tq, tdq, tt = (torch.as_tensor(a, device="cuda") for a in (q, dq, target))
+                kwd = {k: torch.as_tensor(v, device="cuda") for k, v in kw.items()}
+                big = ctrlr.generate(tq, tdq, tt, **kwd)
+                big_train = ctrlr.training_signal.clone()
+                again = ctrlr.generate(tq, tdq, tt, **kwd)
+                assert torch.equal(big, again)  # deterministic, and the queue was re-armed
+                parts, parts_train = [], []
+                for s0 in range(0, B, 4096):
+                    sl = slice(s0, min(B, s0 + 4096))
+                    parts.append(ctrlr.generate(tq[sl], tdq[sl], tt[sl], **{k: v[sl] for k, v in kwd.items()}))
+                    parts_train.append(ctrlr.training_signal.clone())
+                ref, ref_train = torch.cat(parts), torch.cat(parts_train)
+                scale = ref.abs().amax(dim=1, keepdim=True)
+                assert float(((big - ref).abs() / scale).max()) < tol
+                assert float(((big_train - ref_train).abs() / scale).max()) < tol
+                assert bool(torch.isfinite(big).all())
 
 
 def test_full_size_properties():

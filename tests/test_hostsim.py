@@ -120,6 +120,29 @@ def test_null_math_vs_oracle(hostsim, name):
     assert _err(u, ref) < 1e-8 * max(1, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("name", list(cases.CTRL_CASES))
+def test_joint_floating_math_vs_oracle(hostsim, name):
+    cs = cases.CTRL_CASES[name]
+    q, dq, _, _ = cases.states(cs["arm"], 32)
+    tq, tdq = cases.joint_targets(cs["arm"], 32)
+    cd = _abi.chain_desc_from_dict(_abi.load_arm_json(cs["arm"]))
+    kind, kw = cs["ctrl"]
+    u = np.zeros((len(q), cd.n_joints))
+    if kind == "Joint":
+        kp = kw.get("kp", 1)
+        kv = kw.get("kv", np.sqrt(kp))
+        rc = hostsim.hs_ctrl(C.byref(cd), 0, 0, 0, C.c_double(kp), C.c_double(kv), int(kw.get("account_for_gravity", True)), 0,
+                             P(np.ascontiguousarray(q)), P(np.ascontiguousarray(dq)), P(np.ascontiguousarray(tq)),
+                             P(np.ascontiguousarray(tdq)) if cs.get("tv") else None, C.c_int64(len(q)), P(u))
+    else:
+        rc = hostsim.hs_ctrl(C.byref(cd), 0, 0, 1, C.c_double(0), C.c_double(0), int(kw.get("task_space", False)),
+                             int(kw.get("dynamic", False)), P(np.ascontiguousarray(q)), P(np.ascontiguousarray(dq)), None, None,
+                             C.c_int64(len(q)), P(u))
+    assert rc == 0
+    ref = oo.run_ctrl_case(cs, q, dq, tq, tdq)
+    assert _err(u, ref) < 1e-9 * max(1, np.abs(ref).max())
+
+
 def test_singular_states_pinv_branch(hostsim):
     """rank-deficient J M^-1 J^T -> the reference's pinv(rcond=1e-4) branch (osc.py:143-145), incl. truncation."""
     for arm, qs in (("twojoint", [[0.3, 0.0], [1.0, np.pi], [2.0, 1e-9]]),

@@ -2,6 +2,10 @@
 """Turn the scratch ncu artefacts in gpurun_out/ into the tracked summaries under profiles/.
 
 usage: tools/make_profiles.py <round-tag> [--launches gpurun_out/launches.csv] [--rep name=gpurun_out/x.ncu-rep ...]
+                                            [--summary name=gpurun_out/ncu_x.txt,gpurun_out/ncu_x.json ...]
+
+--summary takes what `tools/ncu_summary.py <rep> --json <json> > <txt>` wrote ON THE GPU BOX (the .ncu-rep files are
+too big for gpurun_out's merge-back limit, so they are condensed there).
 """
 import collections
 import csv
@@ -35,6 +39,19 @@ def launches(path, out):
             fh.write(f"{sum(v)/tot*100:6.2f}%  n={len(v):4d}  avg {sum(v)/len(v)/1e3:9.2f} us  {k}\n")
 
 
+def _mb(v):
+    return float(v[0].replace(",", "")) * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1, "Gbyte": 1e3}[v[1]]
+
+
+def record_traffic(traffic, name, tag, json_path):
+    for d in json.load(open(json_path)):
+        if "dram__bytes_read.sum" in d:
+            key = re.sub(r"void |unnamed>::|\(.*", "", d["kernel"]).strip()
+            traffic[f"{name}:{key}"] = {
+                "dram_mb_per_launch": round(_mb(d["dram__bytes_read.sum"]) + _mb(d["dram__bytes_write.sum"]), 3),
+                "ncu_us": float(d["gpu__time_duration.sum"][0]), "tag": tag}
+
+
 def main():
     tag = sys.argv[1]
     args = sys.argv[2:]
@@ -59,13 +76,16 @@ def main():
             with open(os.path.join(ROOT, "profiles", f"{tag}_{name}.txt"), "w") as fh:
                 fh.write(f"# condensed from {os.path.basename(rep)} (ncu --set full --clock-control none --import-source on)\n")
                 fh.write(buf.getvalue())
-            for d in json.load(open("/tmp/_ncu.json")):
-                def mb(v):
-                    return float(v[0].replace(",", "")) * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1, "Gbyte": 1e3}[v[1]]
-                if "dram__bytes_read.sum" in d:
-                    key = re.sub(r"void |unnamed>::|\(.*", "", d["kernel"]).strip()
-                    traffic[f"{name}:{key}"] = {"dram_mb_per_launch": round(mb(d["dram__bytes_read.sum"]) + mb(d["dram__bytes_write.sum"]), 3),
-                                               "ncu_us": float(d["gpu__time_duration.sum"][0]), "tag": tag}
+            record_traffic(traffic, name, tag, "/tmp/_ncu.json")
+            i += 2
+        elif args[i] == "--summary":
+            name, paths = args[i + 1].split("=")
+            txt, js = paths.split(",")
+            with open(os.path.join(ROOT, "profiles", f"{tag}_{name}.txt"), "w") as fh:
+                fh.write("# condensed on the GPU box by tools/ncu_summary.py from one ncu --set full --clock-control none "
+                         "--import-source on capture\n")
+                fh.write(open(txt).read())
+            record_traffic(traffic, name, tag, js)
             i += 2
         else:
             raise SystemExit(f"bad arg {args[i]}")
