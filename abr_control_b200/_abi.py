@@ -1,5 +1,6 @@
 """ctypes mirror of include/abrb.h (struct layouts and constants only; no library loading here)."""
 import ctypes as C
+import math
 import json
 import os
 
@@ -8,7 +9,7 @@ MAX_NULL = 4
 MAX_OBSTACLES = 16
 
 OK, EINVAL, EFRAME, ESHAPE, EUNSUP, ECUDA, ENOMEM = 0, -1, -2, -3, -4, -5, -6
-NULL_DAMPING, NULL_RESTING, NULL_AVOID = 1, 2, 3
+NULL_DAMPING, NULL_RESTING, NULL_AVOID, NULL_JOINT_LIMITS = 1, 2, 3, 4
 
 
 class ChainDesc(C.Structure):
@@ -41,6 +42,11 @@ class NullParams(C.Structure):
         ("gain", C.c_double),
         ("maximum", C.c_double),
         ("obstacles", (C.c_double * 4) * MAX_OBSTACLES),
+        ("limit_min", C.c_double * MAX_JOINTS),
+        ("limit_max", C.c_double * MAX_JOINTS),
+        ("limit_torque", C.c_double * MAX_JOINTS),
+        ("limit_cross_zero", C.c_int32 * MAX_JOINTS),
+        ("limit_gradient", C.c_int32 * MAX_JOINTS),
     ]
 
 
@@ -100,9 +106,11 @@ def chain_desc_from_dict(d):
 
 
 def null_params(kind, n_joints, kv=None, kp=1.0, rest_angles=None, obstacles=None, threshold=0.2, gain=1.0,
-                maximum=500.0):
+                maximum=500.0, min_joint_angles=None, max_joint_angles=None, max_torque=None, cross_zero=None,
+                gradient=None):
     """Build a NullParams with the reference's constructor defaults
-    (damping.py:15-19, joint.py:29-36 + resting_config.py:18-23, avoid_obstacles.py:25-36)."""
+    (damping.py:15-19, joint.py:29-36 + resting_config.py:18-23, avoid_obstacles.py:25-36,
+    avoid_joint_limits.py:36-86)."""
     z = NullParams()
     if kind == "Damping":
         z.kind = NULL_DAMPING
@@ -126,6 +134,22 @@ def null_params(kind, n_joints, kv=None, kp=1.0, rest_angles=None, obstacles=Non
             for c in range(4):
                 z.obstacles[i][c] = float(ob[c])
         z.threshold, z.gain, z.maximum = float(threshold), float(gain), float(maximum)
+    elif kind == "AvoidJointLimits":
+        z.kind = NULL_JOINT_LIMITS
+        if len(min_joint_angles) != n_joints or len(max_joint_angles) != n_joints:
+            raise Exception("joint angles vector incorrect size")  # avoid_joint_limits.py:68-72
+        nan = float("nan")
+        # the constructor shifts the limits to the -pi..pi range (:46-51) and swaps them where the working range
+        # crosses zero (:62-66); None (or NaN) = no limit on that side
+        lo = [nan if v is None else float(v) - math.pi for v in min_joint_angles]
+        hi = [nan if v is None else float(v) - math.pi for v in max_joint_angles]
+        cz = [False] * n_joints if cross_zero is None else [bool(v) for v in cross_zero]
+        gr = [False] * n_joints if gradient is None else [bool(v) for v in gradient]
+        tq = [1.0] * n_joints if max_torque is None else [float(v) for v in max_torque]
+        for k in range(n_joints):
+            z.limit_min[k], z.limit_max[k] = (hi[k], lo[k]) if cz[k] else (lo[k], hi[k])
+            z.limit_torque[k] = tq[k]
+            z.limit_cross_zero[k], z.limit_gradient[k] = int(cz[k]), int(gr[k])
     else:
         raise ValueError(f"unknown secondary controller {kind}")
     return z

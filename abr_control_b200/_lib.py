@@ -42,6 +42,7 @@ SIGNATURES = {
     "abrb_rbd_eval_host_f32": (_I, [_VP, _I, _VP, _VP, _VP, _I64, C.POINTER(_abi.RbdOut)]),
     "abrb_osc_create": (_I, [_VP, C.POINTER(_abi.OscParams), C.POINTER(_VP)]),
     "abrb_osc_destroy": (_I, [_VP]),
+    "abrb_osc_set_option": (_I, [_VP, C.c_char_p, C.c_double]),
     "abrb_osc_generate_f64": (_I, _gen + [_VP]),
     "abrb_osc_generate_f32": (_I, _gen + [_VP]),
     "abrb_osc_generate_host_f64": (_I, _gen),
@@ -52,6 +53,8 @@ SIGNATURES = {
     "abrb_joint_generate_f32": (_I, [_VP, _D, _D, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I64, _VP]),
     "abrb_floating_generate_f64": (_I, [_VP, _I, _I, _VP, _VP, _VP, _I64, _VP]),
     "abrb_floating_generate_f32": (_I, [_VP, _I, _I, _VP, _VP, _VP, _I64, _VP]),
+    "abrb_sliding_generate_f64": (_I, [_VP, _D, _D, _I, _I, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _VP, _VP, _I64, _VP]),
+    "abrb_sliding_generate_f32": (_I, [_VP, _D, _D, _I, _I, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _VP, _VP, _I64, _VP]),
     "abrb_osc_rollout_f64": (_I, _roll),
     "abrb_osc_rollout_f32": (_I, _roll),
     "abrb_launch_count": (_I64, []),

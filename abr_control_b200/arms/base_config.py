@@ -22,6 +22,7 @@ import ctypes as C
 import numpy as np
 
 from .. import _abi, _lib
+from ..controllers._batch import host_out as _host_out
 
 try:  # torch is only needed when the caller hands in CUDA tensors
     import torch
@@ -160,7 +161,7 @@ class BaseConfig:
         else:
             f32 = qa.dtype == np.float32
             for k in want:
-                res[k] = np.empty((B,) + shapes[k], dtype=qa.dtype)
+                res[k] = _host_out((B,) + shapes[k], qa.dtype)
                 setattr(out, k, res[k].ctypes.data)
             fn = L.abrb_rbd_eval_host_f32 if f32 else L.abrb_rbd_eval_host_f64
             _lib.check(fn(self._handle, fid, xo, qa.ctypes.data, dqa.ctypes.data if dqa is not None else None, B,

@@ -44,3 +44,18 @@ def ptr(a):
     if a is None:
         return None
     return a.data_ptr() if is_torch(a) else a.ctypes.data
+
+
+def host_out(shape, dtype):
+    """NumPy result buffer for the host-pointer entry points.  From 64 KiB up it is page-locked (torch's caching host
+    allocator: cheap after the first call, returned to the cache when the array is dropped) so that the library's
+    device->host copy is a plain DMA instead of a staged copy through the driver's bounce buffer."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    if nbytes >= (1 << 16):
+        import torch
+
+        t = torch.empty(tuple(int(s) for s in shape), dtype=torch.float32 if np.dtype(dtype) == np.float32 else torch.float64,
+                        pin_memory=True)
+        return t.numpy()  # keeps `t` alive
+    return np.empty(shape, dtype=dtype)
+

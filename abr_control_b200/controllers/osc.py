@@ -76,6 +76,7 @@ class OSC(Controller):
         # the reference stores `training_signal` on every call (osc.py:297); for large host batches it doubles the
         # device-to-host traffic, so throughput-minded callers may switch it off
         self.record_training_signal = True
+        self._options = {}
         self._handle = None
 
     # ------------------------------------------------------------------ native handle
@@ -95,7 +96,16 @@ class OSC(Controller):
             h = C.c_void_p()
             _lib.check(_lib.lib().abrb_osc_create(self.robot_config.handle, C.byref(p), C.byref(h)))
             self._handle = h
+            for name, value in self._options.items():
+                _lib.check(_lib.lib().abrb_osc_set_option(h, name.encode(), value))
         return self._handle
+
+    def set_option(self, name, value):
+        """Execution option of the native controller (include/abrb.h, abrb_osc_set_option), e.g.
+        ``set_option("two_launch_min", 131072)``.  Kept across parameter changes."""
+        self._options[name] = float(value)
+        if self._handle is not None:
+            _lib.check(_lib.lib().abrb_osc_set_option(self._handle, name.encode(), float(value)))
 
     def __del__(self):
         try:
@@ -129,8 +139,8 @@ class OSC(Controller):
                               tvstride, u.data_ptr(), tr.data_ptr(), B,
                               torch.cuda.current_stream(qa.device).cuda_stream))
         else:
-            u = np.empty_like(qa)
-            tr = np.empty_like(qa) if (self.record_training_signal or single) else None
+            u = _batch.host_out(qa.shape, qa.dtype)
+            tr = _batch.host_out(qa.shape, qa.dtype) if (self.record_training_signal or single) else None
             fn = L.abrb_osc_generate_host_f32 if f32 else L.abrb_osc_generate_host_f64
             _lib.check(fn(h, fid, xo, qa.ctypes.data, dqa.ctypes.data, tgt.ctypes.data, tstride, _batch.ptr(tv),
                           tvstride, u.ctypes.data, _batch.ptr(tr), B))

@@ -111,7 +111,8 @@ inline int parse_frame(int n, const char *name) {
 }
 
 inline std::string check_null(int n, const abrb_null_params &z) {
-  if (z.kind != ABRB_NULL_DAMPING && z.kind != ABRB_NULL_RESTING && z.kind != ABRB_NULL_AVOID)
+  if (z.kind != ABRB_NULL_DAMPING && z.kind != ABRB_NULL_RESTING && z.kind != ABRB_NULL_AVOID &&
+      z.kind != ABRB_NULL_JOINT_LIMITS)
     return "unknown secondary controller kind";
   if (z.kind == ABRB_NULL_AVOID && (z.n_obstacles < 0 || z.n_obstacles > ABRB_MAX_OBSTACLES))
     return "n_obstacles out of range";
@@ -136,6 +137,19 @@ inline void fill_null(const abrb_null_params &z, NullK<T, N> &Z) {
   Z.maximum = T(z.maximum);
   for (int o = 0; o < kMaxObstacles; ++o)
     for (int c = 0; c < 4; ++c) Z.obs[o][c] = o < Z.n_obs ? T(z.obstacles[o][c]) : T(0);
+  if (z.kind == ABRB_NULL_JOINT_LIMITS) {  // shares rest[] / obs[] / rest_mask (NullK, abrb_osc.cuh)
+    Z.rest_mask = 0;
+    for (int k = 0; k < N; ++k) {
+      const bool no_lo = z.limit_min[k] != z.limit_min[k], no_hi = z.limit_max[k] != z.limit_max[k];  // NaN
+      Z.rest[k] = T(z.limit_min[k]);
+      Z.obs[k >> 2][k & 3] = T(z.limit_max[k]);
+      Z.obs[2 + (k >> 2)][k & 3] = T(z.limit_torque[k]);
+      if (z.limit_cross_zero[k]) Z.rest_mask |= 1u << k;
+      if (z.limit_gradient[k]) Z.rest_mask |= 1u << (8 + k);
+      if (no_lo) Z.rest_mask |= 1u << (16 + k);
+      if (no_hi) Z.rest_mask |= 1u << (24 + k);
+    }
+  }
 }
 
 inline std::string check_osc(int n, const abrb_osc_params &p) {

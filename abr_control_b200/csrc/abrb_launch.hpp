@@ -25,8 +25,15 @@ struct OscCall {
   int64_t B;
   bool f32;
   cudaStream_t stream;
-  int *queue = nullptr;  // device workspace of >= 4 + B ints, [0..3] zero: run the two-launch mode (6-row path only)
+  // two-launch mode (6-row path only): queue = 4 + B ints with [0..3] zero; records = osc_record_len(n) * rec_stride
+  // values of the compute type, rec_stride >= B
+  int *queue = nullptr;
+  void *records = nullptr;
+  int64_t rec_stride = 0;
 };
+
+// values per deferred state (OscRecord<N, 6>::kLen in abrb_osc.cuh)
+inline int osc_record_len(int n) { return 12 + 4 * n + n * (n + 1) / 2 + n + 6 * n; }
 
 struct RolloutCall {
   int frame;
@@ -63,12 +70,25 @@ struct CtrlCall {
   cudaStream_t stream;
 };
 
+struct SlidingCall {
+  double kd, lamb;
+  int cartesian, frame;
+  const double *xoff;  // host, 3 values or nullptr
+  const void *q, *dq, *target, *tv, *ta;
+  int target_stride, tv_stride, ta_stride;
+  void *u, *s;
+  int64_t B;
+  bool f32;
+  cudaStream_t stream;
+};
+
 // Each returns a cudaError_t (0 = success).  Defined once per joint count in kernels.cu (-DABRB_N=<n>).
 template <int N> int launch_rbd(const ChainHost &h, const RbdCall &c);
 template <int N> int launch_osc(const ChainHost &h, const abrb_osc_params &p, const OscCall &c);
 template <int N> int launch_rollout(const ChainHost &h, const abrb_osc_params &p, const RolloutCall &c);
 template <int N> int launch_null(const ChainHost &h, const abrb_null_params &z, const NullCall &c);
 template <int N> int launch_ctrl(const ChainHost &h, const CtrlCall &c);
+template <int N> int launch_sliding(const ChainHost &h, const SlidingCall &c);
 
 void count_launch();
 

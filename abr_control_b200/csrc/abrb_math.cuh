@@ -48,6 +48,8 @@ ABRB_HD double abs_t(double x) { return ::fabs(x); }
 ABRB_HD float abs_t(float x) { return ::fabsf(x); }
 ABRB_HD double fmod_t(double x, double y) { return ::fmod(x, y); }
 ABRB_HD float fmod_t(float x, float y) { return ::fmodf(x, y); }
+ABRB_HD double exp_t(double x) { return ::exp(x); }
+ABRB_HD float exp_t(float x) { return ::expf(x); }
 ABRB_HD double pow_t(double x, double y) { return ::pow(x, y); }
 ABRB_HD float pow_t(float x, float y) { return ::powf(x, y); }
 

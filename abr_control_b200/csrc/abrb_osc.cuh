@@ -7,7 +7,7 @@
 
 namespace abrb {
 
-enum { kNullDamping = 1, kNullResting = 2, kNullAvoid = 3 };
+enum { kNullDamping = 1, kNullResting = 2, kNullAvoid = 3, kNullLimits = 4 };
 
 template <typename T, int N>
 struct NullK {
@@ -19,7 +19,42 @@ struct NullK {
   T rest[N];
   T threshold, gain, maximum;
   T obs[kMaxObstacles][4];
+  // AvoidJointLimits shares the storage: rest[] = lower limits, obs[0..1] = upper limits, obs[2..3] = max torque,
+  // rest_mask bits 0-7 cross_zero, 8-15 gradient, 16-23 no lower limit, 24-31 no upper limit (abrb_host.hpp)
+  ABRB_HD T lim_hi(int k) const { return obs[k >> 2][k & 3]; }
+  ABRB_HD T lim_torque(int k) const { return obs[2 + (k >> 2)][k & 3]; }
 };
+
+// AvoidJointLimits.generate (controllers/avoid_joint_limits.py:83-142): a function of q alone
+template <typename T, int N>
+ABRB_HD void joint_limits_generate(const NullK<T, N> &Z, const T *q, T *u) {
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) {
+    const T x = q[k] - T(3.14159265358979323846);  // :91
+    const T lo = Z.rest[k], hi = Z.lim_hi(k), tq = Z.lim_torque(k);
+    const bool cross = (Z.rest_mask >> k) & 1u, grad = (Z.rest_mask >> (8 + k)) & 1u;
+    const bool no_lo = (Z.rest_mask >> (16 + k)) & 1u, no_hi = (Z.rest_mask >> (24 + k)) & 1u;
+    const T dlo = x - lo, dhi = x - hi;
+    const bool nearer_hi = abs_t(dlo) >= abs_t(dhi);  // the reference's `closer_to_min_index` (:94-96)
+    const bool nearer_lo = abs_t(dlo) <= abs_t(dhi);  // the reference's `closer_to_max_index` (:97-99)
+    T a_lo = T(0), a_hi = T(0);
+    if (grad) {  // :108-115
+      const T e_lo = exp_t(T(1) / dlo), e_hi = exp_t(T(-1) / dhi);
+      a_lo = e_lo < tq ? e_lo : tq;
+      a_hi = -(e_hi < tq ? e_hi : tq);
+    }
+    bool below = dlo < T(0), above = dhi > T(0);  // :118-119
+    if (cross) {                                 // :124-134
+      below = below && (dhi > T(0)) && nearer_lo;
+      above = above && (dlo < T(0)) && nearer_hi;
+    }
+    if (below) a_lo = tq;
+    if (no_lo) a_lo = T(0);
+    if (above) a_hi = -tq;
+    if (no_hi) a_hi = T(0);
+    u[k] = a_lo + a_hi;
+  }
+}
 
 template <typename T, int N>
 struct OscK {
@@ -123,18 +158,41 @@ ABRB_HD T wrap_pm_pi(T d) {
 
 // One OSC evaluation.  KD = 3: only (a subset of) x,y,z controlled; KD = 6: any mask.
 // PLANT: also return ddq = M^-1 (u + g - C dq) for the rollout kernel.
-// DEFER: if the state needs the truncating-pinv path, return true WITHOUT computing u (and without that path's code
-// in the instantiation); the caller queues such states for a second, densely packed launch (they are a few % of
-// random UR5 states but would otherwise drag most warps through the divergent slow path).  Returns false when u has
-// been produced.
+// Returns true only in MODE 1 (below) for a state left to the second launch; false when u has been produced.
 // `K`: caller-provided kinematic scratch (registers or shared memory).  Once the dynamics are done its t_k / z_k
 // slots are overwritten IN PLACE by the task Jacobian (column k of J only needs t_k, z_k), which later becomes
 // A = (L^-1 J^T)^T; so J, A never occupy registers of their own.
-template <typename T, int N, int KD, bool PLANT, bool DEFER = false, class K_>
-ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, const T *dq, const T *target,
-                       const T *tv, T *u, T *train, T *ddq, K_ &K) {
+//
+// MODE 0: everything in line.  MODE 1 / MODE 2 are the two halves of the two-launch mode: MODE 1 stops at a state that
+// needs the truncating route, writes what the rest of the evaluation needs (y, z, the partial u, C dq, g, u_null,
+// chol(M), A: OscRecord<N,KD>::kLen values) through `rec` and returns true; MODE 2 starts from such a record (q, dq,
+// target are not read), runs the truncating route and finishes u.  `Rec`: begin() reserves a record,
+// put(i, v) / get(i) access value i of it.
+struct NoRecord {
+  ABRB_HD void begin() {}
+  template <typename V> ABRB_HD void put(int, V) {}
+  ABRB_HD double get(int) const { return 0.0; }
+};
+
+template <int N, int KD>
+struct OscRecord {
+  static constexpr int kY = 0, kZ = KD, kU = 2 * KD, kCdq = kU + N, kG = kCdq + N, kUn = kG + N, kL = kUn + N,
+                       kMi = kL + N * (N + 1) / 2, kA = kMi + N, kLen = kA + KD * N;
+};
+
+template <typename T, int N, int KD, bool PLANT, int MODE, class K_, class Rec>
+ABRB_HD bool osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, const T *dq, const T *target,
+                      const T *tv, T *u, T *train, T *ddq, K_ &K, Rec &rec) {
   constexpr bool ORTHO = K_::kOrtho;
   typedef typename K_::S SL;
+  typedef OscRecord<N, KD> RC;
+  // A(r,k): r<3 -> slot kT+3k+r,  r>=3 -> slot kZ+3k+r-3
+  auto Aslot = [](int r, int k) { return r < 3 ? SL::kT + 3 * k + r : SL::kZ + 3 * k + (r - 3); };
+  T M[N][N], Mi[N], g[N], cdq[N], un[N], y[KD], z[KD];
+  const bool any_null = O.n_null > 0;
+  const T rcond = O.thr * T(0.1);
+  bool fast = true;
+  if constexpr (MODE != 2) {
   K.sync();
   walk<T, N>(P, q, O.frame, K);
   K.sync();
@@ -200,7 +258,6 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
 
   // ---- joint-space dynamics
   K.sync();
-  T M[N][N], g[N], cdq[N];
   if (PLANT || O.use_C)
     dynamics_Mg<T, N, true>(P, K, dq, M, g, cdq);
   else
@@ -212,13 +269,15 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
     if (b < a) M[a][b] = M[b][a];
 
   // secondary controllers that are M.(something): accumulate the something
-  T wn[N];
-  bool any_null = false, any_avoid = false;
+  T wn[N], ud[N];  // ud: secondary controllers that are plain joint torques (AvoidJointLimits)
+  bool any_avoid = false;
   ABRB_UNROLL
-  for (int k = 0; k < N; ++k) wn[k] = T(0);
+  for (int k = 0; k < N; ++k) {
+    wn[k] = T(0);
+    ud[k] = T(0);
+  }
   for (int i = 0; i < O.n_null; ++i) {
     const NullK<T, N> &Z = O.nul[i];
-    any_null = true;
     if (Z.kind == kNullDamping) {
       ABRB_UNROLL
       for (int k = 0; k < N; ++k) wn[k] -= Z.kv * dq[k];
@@ -228,6 +287,11 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
         const T qt = ((Z.rest_mask >> k) & 1u) ? wrap_pm_pi(Z.rest[k] - q[k]) : T(0);
         wn[k] += Z.kp * qt - Z.kv * dq[k];
       }
+    } else if (Z.kind == kNullLimits) {
+      T ul[N];
+      joint_limits_generate<T, N>(Z, q, ul);
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) ud[k] += ul[k];
     } else {
       any_avoid = true;
     }
@@ -238,7 +302,6 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
     ABRB_UNROLL
     for (int c = 0; c < 6; ++c) tv_zero = tv_zero && (tv[c] == T(0));
   }
-  T un[N];
   ABRB_UNROLL
   for (int a = 0; a < N; ++a) {
     T s1 = T(0), s2 = T(0);
@@ -248,13 +311,12 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
       s2 += M[a][b] * wn[b];
     }
     u[a] = tv_zero ? -O.kv * s1 : T(0);
-    un[a] = s2;
+    un[a] = s2 + ud[a];
   }
 
   K.sync();
   // ---- task Jacobian rows of the controlled DOF written in place over t_k / z_k (osc.py:242-244):
-  //      A(r,k): r<3 -> slot kT+3k+r,  r>=3 -> slot kZ+3k+r-3.  Uncontrolled rows are zero.
-  auto Aslot = [](int r, int k) { return r < 3 ? SL::kT + 3 * k + r : SL::kZ + 3 * k + (r - 3); };
+  //      Uncontrolled rows are zero.
   T xdot[KD];
   ABRB_UNROLL
   for (int r = 0; r < KD; ++r) xdot[r] = T(0);
@@ -278,13 +340,11 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
     ABRB_UNROLL
     for (int r = 0; r < KD; ++r) err[r] += O.kv * (xdot[r] - tv[r]);
   }
-  T y[KD];
   ABRB_UNROLL
   for (int r = 0; r < KD; ++r) y[r] = ((O.dof_mask >> r) & 1u) ? err[r] : T(0);
 
   K.sync();
   // ---- M = L L^T ;  A <- rows of (L^-1 J^T)^T ;  S = J M^-1 J^T = A A^T   (osc.py:136-137)
-  T Mi[N];
   chol<T, N>(M, Mi);
   ABRB_UNROLL
   for (int r = 0; r < KD; ++r) {
@@ -321,8 +381,7 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
   T det = T(1);
   ABRB_UNROLL
   for (int a = 0; a < KD; ++a) det *= Sc[a][a] * Sc[a][a];
-  bool fast = pd && (det >= O.thr);
-  const T rcond = O.thr * T(0.1);
+  fast = pd && (det >= O.thr);
   if (pd && !fast) {
     // pinv == inv whenever no eigenvalue is truncated; certify that cheaply:
     // lambda_max <= trace(S_active), 1/lambda_min <= ||S^-1||_F  =>  no truncation if 1/||S^-1||_F > rcond*trace
@@ -342,11 +401,9 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
     }
     fast = rcond * tr * sqrt_t(fro) < T(1);
   }
-  if (DEFER && !fast) return true;
   // ---- secondary controllers that go through the null-space filter  I - J^T Mx J M^-1  (osc.py:310-318): their
   //      task-space image z = J M^-1 u_null is formed here so that Mx is applied to y and z in ONE place (the
   //      truncating branch computes its eigenvectors once for both right-hand sides)
-  T z[KD];
   ABRB_UNROLL
   for (int r = 0; r < KD; ++r) z[r] = T(0);
   if (any_null) {
@@ -379,15 +436,63 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
       z[r] = ((O.dof_mask >> r) & 1u) ? s : T(0);
     }
   }
-  // y <- Mx y,  z <- Mx z
-  if (DEFER || fast) {
+  // y <- Mx y,  z <- Mx z   (regular case; the truncating case follows below, possibly in another launch)
+  if (fast) {
     fwd_solve<T, KD>(Sc, Si, y);
     bwd_solve<T, KD>(Sc, Si, y);
     if (any_null) {
       fwd_solve<T, KD>(Sc, Si, z);
       bwd_solve<T, KD>(Sc, Si, z);
     }
-  } else {
+  }
+  }  // MODE != 2
+  if constexpr (MODE == 1) {
+    if (!fast) {
+      rec.begin();
+      ABRB_UNROLL
+      for (int r = 0; r < KD; ++r) {
+        rec.put(RC::kY + r, y[r]);
+        rec.put(RC::kZ + r, z[r]);
+        ABRB_UNROLL
+        for (int k = 0; k < N; ++k) rec.put(RC::kA + r * N + k, K.s.ld(Aslot(r, k)));
+      }
+      int li = 0;
+      ABRB_UNROLL
+      for (int a = 0; a < N; ++a) {
+        rec.put(RC::kU + a, u[a]);
+        rec.put(RC::kCdq + a, (PLANT || O.use_C) ? cdq[a] : T(0));
+        rec.put(RC::kG + a, g[a]);
+        rec.put(RC::kUn + a, un[a]);
+        rec.put(RC::kMi + a, Mi[a]);
+        ABRB_UNROLL
+        for (int b = 0; b < N; ++b)
+          if (b <= a) rec.put(RC::kL + li++, M[a][b]);
+      }
+      return true;
+    }
+  }
+  if constexpr (MODE == 2) {
+    fast = false;
+    ABRB_UNROLL
+    for (int r = 0; r < KD; ++r) {
+      y[r] = T(rec.get(RC::kY + r));
+      z[r] = T(rec.get(RC::kZ + r));
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) K.s.st(Aslot(r, k), T(rec.get(RC::kA + r * N + k)));
+    }
+    int li = 0;
+    ABRB_UNROLL
+    for (int a = 0; a < N; ++a) {
+      u[a] = T(rec.get(RC::kU + a));
+      cdq[a] = T(rec.get(RC::kCdq + a));
+      g[a] = T(rec.get(RC::kG + a));
+      un[a] = T(rec.get(RC::kUn + a));
+      Mi[a] = T(rec.get(RC::kMi + a));
+      ABRB_UNROLL
+      for (int b = 0; b < N; ++b) M[a][b] = b <= a ? T(rec.get(RC::kL + li++)) : T(0);
+    }
+  }
+  if (!fast) {
     // cheap register-resident route first (inertia counts + inverse iteration, abrb_math.cuh); the rolled,
     // local-memory Jacobi eigen-decomposition only when that is inconclusive.  Static indices everywhere: a
     // rolled loop over S or v here would force them into local memory for the whole function.
@@ -395,7 +500,6 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
     // This branch always runs in double precision, also for the fp32 kernels: the matrices that end up here have
     // eigenvalue ratios down to 1e-8, where a float Cholesky breaks down (and the FP64 pipe is idle there anyway).
     double Sd[KD][KD], Ld[KD][KD], Sid[KD], yd[KD], xd[KD], zd[KD], xz[KD];
-    const double trd = double(trS);
     ABRB_UNROLL
     for (int a = 0; a < KD; ++a) {
       yd[a] = double(y[a]);
@@ -410,13 +514,19 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
           ABRB_UNROLL
           for (int k = 0; k < N; ++k) acc += ra[k] * double(K.s.ld(Aslot(b, k)));
           const bool on = ((mask >> a) & 1u) && ((mask >> b) & 1u);
-          // inactive rows: decoupled, diagonal >= lambda_max so that they are never counted as truncated
-          const double val = on ? acc : (a == b ? trd : 0.0);
+          const double val = on ? acc : 0.0;
           Sd[a][b] = val;
           Sd[b][a] = val;
         }
       }
     }
+    // inactive rows: decoupled, diagonal = trace >= lambda_max so that they are never counted as truncated
+    double trd = 0.0;
+    ABRB_UNROLL
+    for (int a = 0; a < KD; ++a) trd += Sd[a][a];
+    ABRB_UNROLL
+    for (int a = 0; a < KD; ++a)
+      if (!((mask >> a) & 1u)) Sd[a][a] = trd;
     ABRB_UNROLL
     for (int a = 0; a < KD; ++a)
       ABRB_UNROLL
@@ -505,10 +615,21 @@ ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, c
   return false;
 }
 
+template <typename T, int N, int KD, bool PLANT, class K_>
+ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, const T *dq, const T *target,
+                       const T *tv, T *u, T *train, T *ddq, K_ &K) {
+  NoRecord none;
+  return osc_eval<T, N, KD, PLANT, 0>(P, O, q, dq, target, tv, u, train, ddq, K, none);
+}
+
 // Standalone secondary controller (`Damping/RestingConfig/AvoidObstacles.generate`)
 template <typename T, int N, class K_>
 ABRB_HD void null_state(const ChainK<T, N> &P, const NullK<T, N> &Z, const T *q, const T *dq, T *u, K_ &K) {
   constexpr bool ORTHO = K_::kOrtho;
+  if (Z.kind == kNullLimits) {
+    joint_limits_generate<T, N>(Z, q, u);
+    return;
+  }
   walk<T, N>(P, q, 0, K);
   T M[N][N], g[N];
   dynamics_Mg<T, N, false>(P, K, dq, M, g, nullptr);
@@ -667,6 +788,115 @@ ABRB_HD void floating_state(const ChainK<T, N> &P, bool task_space, bool dynamic
     u[i] = -s - (dynamic ? Mdq[i] : T(0));
   }
   (void)ORTHO;
+}
+
+// Sliding.generate (controllers/sliding.py:34-99).  pinv(J) for the 3 x N position Jacobian is applied through a
+// one-sided (Hestenes) Jacobi SVD of its rows: rotations of row pairs until they are mutually orthogonal give
+// J = V diag(sigma) U^T with sigma_i u_i = rotated row i, so pinv(J) y = sum_i row_i (v_i . y) / sigma_i^2 over the
+// sigma_i > 1e-15 sigma_max that numpy.linalg.pinv keeps.  (Going through J J^T would square the condition number.)
+template <typename T, int N, class K_>
+ABRB_HD void sliding_state(const ChainK<T, N> &P, T kd, T lamb, bool cartesian, int frame, const T *xoff, const T *q,
+                           const T *dq, const T *target, const T *tv, const T *ta, T *u, T *s_out, K_ &K) {
+  walk<T, N>(P, q, cartesian ? frame : 0, K);
+  T dq_ref[N], ddq_ref[N];
+  if (cartesian) {
+    const int dep = frame_dep<N>(frame);
+    T pF[3];
+    frame_point(K.F, xoff, pF);
+    T J[6][N], dJ[6][N];
+    jacobian<T, N>(K, pF, dep, J);
+    T b0[N], b1[N], b2[N], v0[3] = {T(1), T(0), T(0)}, v1[3] = {T(0), T(1), T(0)}, v2[3] = {T(0), T(0), T(1)};
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) {
+      b0[k] = J[0][k];
+      b1[k] = J[1][k];
+      b2[k] = J[2][k];
+    }
+    auto rotate = [](T *bi, T *bj, T *vi, T *vj) {
+      T al = T(0), be = T(0), ga = T(0);
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) {
+        al += bi[k] * bi[k];
+        be += bj[k] * bj[k];
+        ga += bi[k] * bj[k];
+      }
+      if (ga * ga > (sizeof(T) == 8 ? T(1e-32) : T(1e-14)) * al * be && ga != T(0)) {
+        const T zeta = (be - al) / (T(2) * ga);
+        const T t = (zeta >= T(0) ? T(1) : T(-1)) / (abs_t(zeta) + sqrt_t(T(1) + zeta * zeta));
+        const T c = T(1) / sqrt_t(T(1) + t * t), sn = c * t;
+        ABRB_UNROLL
+        for (int k = 0; k < N; ++k) {
+          const T x = bi[k], y = bj[k];
+          bi[k] = c * x - sn * y;
+          bj[k] = sn * x + c * y;
+        }
+        ABRB_UNROLL
+        for (int k = 0; k < 3; ++k) {
+          const T x = vi[k], y = vj[k];
+          vi[k] = c * x - sn * y;
+          vj[k] = sn * x + c * y;
+        }
+      }
+    };
+    ABRB_NOUNROLL
+    for (int sweep = 0; sweep < 8; ++sweep) {
+      rotate(b0, b1, v0, v1);
+      rotate(b0, b2, v0, v2);
+      rotate(b1, b2, v1, v2);
+    }
+    T s0 = T(0), s1 = T(0), s2 = T(0);
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) {
+      s0 += b0[k] * b0[k];
+      s1 += b1[k] * b1[k];
+      s2 += b2[k] * b2[k];
+    }
+    const T smax = s0 > s1 ? (s0 > s2 ? s0 : s2) : (s1 > s2 ? s1 : s2);
+    const T cut = T(1e-30) * smax;  // (rcond = 1e-15)^2 on the squared singular values
+    const T i0 = s0 > cut ? T(1) / s0 : T(0), i1 = s1 > cut ? T(1) / s1 : T(0), i2 = s2 > cut ? T(1) / s2 : T(0);
+    auto pinv_J = [&](const T *y, T *out) {
+      const T c0 = (v0[0] * y[0] + v0[1] * y[1] + v0[2] * y[2]) * i0;
+      const T c1 = (v1[0] * y[0] + v1[1] * y[1] + v1[2] * y[2]) * i1;
+      const T c2 = (v2[0] * y[0] + v2[1] * y[1] + v2[2] * y[2]) * i2;
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) out[k] = b0[k] * c0 + b1[k] * c1 + b2[k] * c2;
+    };
+    T r1[3], r2[3];
+    ABRB_UNROLL
+    for (int c = 0; c < 3; ++c) r1[c] = (tv != nullptr ? tv[c] : T(0)) + lamb * (target[c] - pF[c]);
+    pinv_J(r1, dq_ref);
+    jacobian_dot<T, N>(K, J, dq, dep, dJ);
+    ABRB_UNROLL
+    for (int c = 0; c < 3; ++c) {
+      T dx = T(0), dj = T(0);
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) {
+        dx += J[c][k] * dq[k];
+        dj += dJ[c][k] * dq_ref[k];
+      }
+      r2[c] = (ta != nullptr ? ta[c] : T(0)) + lamb * ((tv != nullptr ? tv[c] : T(0)) - dx) - dj;
+    }
+    pinv_J(r2, ddq_ref);
+  } else {
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) {
+      const T tvk = tv != nullptr ? tv[k] : T(0);
+      dq_ref[k] = tvk - lamb * (q[k] - target[k]);
+      ddq_ref[k] = (ta != nullptr ? ta[k] : T(0)) - lamb * (dq[k] - tvk);
+    }
+  }
+  T M[N][N], g[N], Cm[N][N];
+  dynamics_Mg<T, N, false>(P, K, dq, M, g, nullptr);
+  dynamics_C<T, N>(P, K, dq, Cm);
+  ABRB_UNROLL
+  for (int a = 0; a < N; ++a) {
+    T acc = T(0);
+    ABRB_UNROLL
+    for (int b = 0; b < N; ++b) acc += (b >= a ? M[a][b] : M[b][a]) * ddq_ref[b] + Cm[a][b] * dq_ref[b];
+    const T sa = dq[a] - dq_ref[a];
+    if (s_out != nullptr) s_out[a] = sa;
+    u[a] = acc + g[a] - kd * sa;
+  }
 }
 
 }  // namespace abrb

@@ -23,13 +23,15 @@ struct abrb_model {
 
 // Index queue of the two-launch OSC mode (kernels.cu): one per (device, stream) the controller has been used on.
 struct SlowQueue {
-  int *buf = nullptr;
+  int *buf = nullptr;       // 4 + cap ints
+  void *records = nullptr;  // osc_record_len(n) * cap doubles (also used by the float kernels)
   int64_t cap = 0;
 };
 
 struct abrb_osc {
   const abrb_model *model;
   abrb_osc_params params;
+  int64_t two_launch_min = 0;  // 0: single launch always
   mutable std::mutex mu;
   mutable std::map<std::pair<int, cudaStream_t>, SlowQueue> queues;
 };
@@ -240,8 +242,18 @@ int abrb_osc_create(const abrb_model *m, const abrb_osc_params *p, abrb_osc **ou
   if (!c) return fail(ABRB_ENOMEM, "abrb_osc_create: out of memory");
   c->model = m;
   c->params = *p;
+  if (const char *v = std::getenv("ABRB_OSC_DEFER_MIN")) c->two_launch_min = (int64_t)std::atoll(v);
   *out = c;
   return ABRB_OK;
+}
+
+int abrb_osc_set_option(abrb_osc *c, const char *name, double value) {
+  if (!c || !name) return fail(ABRB_EINVAL, "abrb_osc_set_option: NULL argument");
+  if (std::strcmp(name, "two_launch_min") == 0) {
+    c->two_launch_min = value > 0 ? (int64_t)value : 0;
+    return ABRB_OK;
+  }
+  return fail(ABRB_EINVAL, std::string("abrb_osc_set_option: unknown option ") + name);
 }
 
 int abrb_osc_destroy(abrb_osc *c) {
@@ -251,6 +263,7 @@ int abrb_osc_destroy(abrb_osc *c) {
     for (auto &kv : c->queues) {
       cudaSetDevice(kv.first.first);
       cudaFree(kv.second.buf);
+      cudaFree(kv.second.records);
     }
     cudaSetDevice(cur);
   }
@@ -258,20 +271,15 @@ int abrb_osc_destroy(abrb_osc *c) {
   return ABRB_OK;
 }
 
-// Two-launch mode (kernels.cu, osc_kernel<DEFER> + osc_slow_kernel): used for the 6-row task space from
-// ABRB_OSC_DEFER_MIN states up (default 16384; ABRB_OSC_DEFER=0 turns it off).  Returns the queue for this
-// (device, stream), growing it on demand, or nullptr for the single-launch mode.
-static int *slow_queue_for(const abrb_osc *c, int64_t B, cudaStream_t stream, int *err) {
-  static const int64_t min_b = [] {
-    const char *off = std::getenv("ABRB_OSC_DEFER");
-    if (off && off[0] == '0') return (int64_t)-1;
-    const char *m = std::getenv("ABRB_OSC_DEFER_MIN");
-    return m ? (int64_t)std::atoll(m) : (int64_t)16384;
-  }();
+// Two-launch mode (kernels.cu, osc_kernel<DEFER> + osc_slow_kernel) for the 6-row task space, from
+// `two_launch_min` states up.  Returns the queue for this (device, stream), growing it on demand, or nullptr for the
+// single-launch mode.
+static SlowQueue slow_queue_for(const abrb_osc *c, int64_t B, cudaStream_t stream, int *err) {
+  const int64_t min_b = c->two_launch_min > 0 ? c->two_launch_min : -1;
   *err = 0;
   const abrb_osc_params &p = c->params;
-  if (min_b < 0 || B < min_b || B > (int64_t)0x7fffffff - 8) return nullptr;
-  if (!(p.ctrlr_dof[3] || p.ctrlr_dof[4] || p.ctrlr_dof[5])) return nullptr;
+  if (min_b < 0 || B < min_b || B > (int64_t)0x7fffffff - 8) return SlowQueue();
+  if (!(p.ctrlr_dof[3] || p.ctrlr_dof[4] || p.ctrlr_dof[5])) return SlowQueue();
   int dev = 0;
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lock(c->mu);
@@ -279,17 +287,22 @@ static int *slow_queue_for(const abrb_osc *c, int64_t B, cudaStream_t stream, in
   if (sq.cap < B) {
     cudaError_t e = cudaSuccess;
     if (sq.buf) e = cudaFree(sq.buf);  // synchronises with any launch still using it
-    sq.buf = nullptr;
-    sq.cap = 0;
+    if (sq.records) cudaFree(sq.records);
+    sq = SlowQueue();
     if (e == cudaSuccess) e = cudaMalloc(&sq.buf, (size_t)(B + 4) * sizeof(int));
+    if (e == cudaSuccess)
+      e = cudaMalloc(&sq.records, (size_t)osc_record_len(c->model->host.n) * (size_t)B * sizeof(double));
     if (e == cudaSuccess) e = cudaMemsetAsync(sq.buf, 0, 4 * sizeof(int), stream);
     if (e != cudaSuccess) {
+      cudaFree(sq.buf);
+      cudaFree(sq.records);
+      sq = SlowQueue();
       *err = (int)e;
-      return nullptr;
+      return SlowQueue();
     }
     sq.cap = B;
   }
-  return sq.buf;
+  return sq;
 }
 
 static int osc_generate(const abrb_osc *c, int frame_id, const double *x_off, const void *q, const void *dq,
@@ -310,8 +323,11 @@ static int osc_generate(const abrb_osc *c, int frame_id, const double *x_off, co
   if (rc) return rc;
   OscCall k{frame_id, x_off, q, dq, target, tv, target_stride, tv_stride, u, train, B, f32, (cudaStream_t)stream};
   int qe = 0;
-  k.queue = slow_queue_for(c, B, (cudaStream_t)stream, &qe);
-  if (qe) return cuda_fail(qe, "abrb_osc_generate (index queue)");
+  const SlowQueue sq = slow_queue_for(c, B, (cudaStream_t)stream, &qe);
+  if (qe) return cuda_fail(qe, "abrb_osc_generate (two-launch workspace)");
+  k.queue = sq.buf;
+  k.records = sq.records;
+  k.rec_stride = sq.cap;
   int e = cudaErrorInvalidValue;
   switch (n) {
 #define X(j) case j: e = launch_osc<j>(c->model->host, c->params, k); break;
@@ -357,7 +373,13 @@ static int osc_generate_host(const abrb_osc *c, int frame_id, const double *x_of
   // D2H copy of chunk c-1 (the copy engines are full duplex), so a large batch costs ~max(H2D, kernel, D2H).
   const size_t row = n * es;
   // chunks stay large: a launch is latency bound below ~64k states, so splitting smaller batches only adds latency
-  const int64_t chunk = B <= 131072 ? B : ((B + 3) / 4 + 127) / 128 * 128;
+  static const int64_t chunk_env = [] {  // tuning knob: states per pipeline chunk
+    const char *v = std::getenv("ABRB_HOST_CHUNK");
+    return v ? (int64_t)std::atoll(v) : (int64_t)0;
+  }();
+  int64_t chunk = B <= 131072 ? B : ((B + 3) / 4 + 127) / 128 * 128;
+  if (chunk_env > 0) chunk = (chunk_env < B ? chunk_env : B + 127) / 128 * 128;
+  if (chunk <= 0) chunk = B;
   if (!target_stride) cudaMemcpyAsync(d_t, target, sz_t, cudaMemcpyHostToDevice, g_ws.stream);
   if (tv && !tv_stride) cudaMemcpyAsync(d_tv, tv, sz_tv, cudaMemcpyHostToDevice, g_ws.stream);
   cudaError_t ce = cudaStreamSynchronize(g_ws.stream);
@@ -430,6 +452,50 @@ int abrb_null_generate_f64(const abrb_model *m, const abrb_null_params *p, const
 int abrb_null_generate_f32(const abrb_model *m, const abrb_null_params *p, const float *q, const float *dq, float *u,
                            int64_t B, void *stream) {
   return null_generate(m, p, q, dq, u, B, stream, true);
+}
+
+// ------------------------------------------------------------------------------------------------ sliding
+static int sliding_generate(const abrb_model *m, double kd, double lamb, int cartesian, int frame_id,
+                            const double *x_off, const void *q, const void *dq, const void *target, int target_stride,
+                            const void *tv, int tv_stride, const void *ta, int ta_stride, void *u, void *s, int64_t B,
+                            void *stream, bool f32) {
+  if (!m) return fail(ABRB_EINVAL, "abrb_sliding_generate: NULL model");
+  if (B < 0) return fail(ABRB_EINVAL, "abrb_sliding_generate: B < 0");
+  const int n = m->host.n, w = cartesian ? 3 : n;
+  if (frame_id < 0 || frame_id > 2 * n + 1) return fail(ABRB_EFRAME, "abrb_sliding_generate: invalid frame id");
+  if ((target_stride != 0 && target_stride != w) || (tv && tv_stride != 0 && tv_stride != w) ||
+      (ta && ta_stride != 0 && ta_stride != w))
+    return fail(ABRB_EINVAL, "abrb_sliding_generate: stride must be 0 (broadcast) or the row width (3 or n_joints)");
+  if (B == 0) return ABRB_OK;
+  if (!q || !dq || !target || !u) return fail(ABRB_EINVAL, "abrb_sliding_generate: NULL q/dq/target/u");
+  if (!aligned16(q) || !aligned16(dq) || !aligned16(u) || (s && !aligned16(s)))
+    return fail(ABRB_EINVAL, "abrb_sliding_generate: pointers must be 16-byte aligned");
+  int rc = ensure_device();
+  if (rc) return rc;
+  SlidingCall k{kd, lamb, cartesian, frame_id, x_off, q, dq, target, tv, ta, target_stride, tv_stride, ta_stride,
+                u, s, B, f32, (cudaStream_t)stream};
+  int e = cudaErrorInvalidValue;
+  switch (n) {
+#define X(j) case j: e = launch_sliding<j>(m->host, k); break;
+    ABRB_N_LIST(X)
+#undef X
+  }
+  return e ? cuda_fail(e, "abrb_sliding_generate") : ABRB_OK;
+}
+
+int abrb_sliding_generate_f64(const abrb_model *m, double kd, double lamb, int cartesian, int frame_id,
+                              const double *x_off, const double *q, const double *dq, const double *target,
+                              int target_stride, const double *target_velocity, int tv_stride,
+                              const double *target_acc, int ta_stride, double *u, double *s, int64_t B, void *stream) {
+  return sliding_generate(m, kd, lamb, cartesian, frame_id, x_off, q, dq, target, target_stride, target_velocity,
+                          tv_stride, target_acc, ta_stride, u, s, B, stream, false);
+}
+int abrb_sliding_generate_f32(const abrb_model *m, double kd, double lamb, int cartesian, int frame_id,
+                              const double *x_off, const float *q, const float *dq, const float *target,
+                              int target_stride, const float *target_velocity, int tv_stride, const float *target_acc,
+                              int ta_stride, float *u, float *s, int64_t B, void *stream) {
+  return sliding_generate(m, kd, lamb, cartesian, frame_id, x_off, q, dq, target, target_stride, target_velocity,
+                          tv_stride, target_acc, ta_stride, u, s, B, stream, true);
 }
 
 // ------------------------------------------------------------------------------------------------ joint / floating

@@ -183,14 +183,33 @@ struct OscArgs {
   T *u, *train;
   int64_t B;
   int target_stride, tv_stride;
-  int *queue;  // two-launch mode: queue[0] = number of deferred states, queue[1] = CTA ticket, queue[4..] = their indices
+  // two-launch mode: queue[0] = number of deferred states, queue[1] = CTA ticket, queue[4 + i] = state index of
+  // record i; records[f * rec_stride + i] = value f of record i (OscRecord<N,KD> layout, abrb_osc.cuh)
+  int *queue;
+  T *records;
+  int64_t rec_stride;
+};
+
+template <typename T>
+struct DevRecord {
+  int *queue;
+  T *store;
+  int64_t stride, state;
+  int pos;
+  __device__ void begin() {
+    pos = atomicAdd(queue, 1);
+    queue[4 + pos] = (int)state;
+  }
+  template <typename V>
+  __device__ void put(int i, V v) { store[(int64_t)i * stride + pos] = T(v); }
+  __device__ T get(int i) const { return store[(int64_t)i * stride + pos]; }
 };
 
 // DEFER = false: one pass, the states that need the truncating pseudo-inverse take that route in line.  For random
 // UR5 6-DOF states that is 3.8 % of the states but 70 % of the warps, each of which then serialises a long divergent
-// path for one or two lanes (39 us without those states, ~100 us with them at B = 65 536).
-// DEFER = true: the instantiation has no truncating code at all; such states are appended to a global index queue
-// (one warp-aggregated atomic) and osc_slow_kernel re-runs them densely packed.
+// path for one or two lanes (41 us without those states, 77 us with them at B = 65 536).
+// DEFER = true (first launch of the two-launch mode): the instantiation has no truncating code at all; such a state
+// writes a record of its intermediate results (osc_eval MODE 1) and osc_finish_kernel completes it.
 template <typename T, int N, bool ORTHO, int KD, bool KSMEM, bool DEFER>
 __global__ void __launch_bounds__(kBlock, MinBlocks<T>::value)
 osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
@@ -215,39 +234,34 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
     for (int k = 0; k < N; ++k) {
       q[k] = a.q[b * N + k];
       dq[k] = a.dq[b * N + k];
-      u[k] = T(0);
-      tr[k] = T(0);
     }
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       tg[c] = a.target[b * a.target_stride + c];
       tv[c] = a.tv != nullptr ? a.tv[b * a.tv_stride + c] : T(0);
     }
-    const bool slow =
-        osc_state<T, N, KD, false, DEFER>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, u, tr, nullptr, K);
     if (DEFER) {
-      const bool push = slow && lane < nvalid;
-      const unsigned m = __ballot_sync(0xffffffffu, push);
-      if (m) {
-        const int leader = __ffs(m) - 1;
-        int pos = 0;
-        if (lane == leader) pos = atomicAdd(a.queue, __popc(m));
-        pos = __shfl_sync(0xffffffffu, pos, leader);
-        if (push) a.queue[4 + pos + __popc(m & ((1u << lane) - 1u))] = (int)b;
-      }
+      // lanes that only duplicate a valid state (ragged last warp) must not queue it a second time: they get a
+      // state index of -1 and are skipped by the finishing kernel
+      DevRecord<T> rec{a.queue, a.records, a.rec_stride, lane < nvalid ? b : (int64_t)-1, 0};
+      osc_eval<T, N, KD, false, 1>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, u, tr, (T *)nullptr, K, rec);
+    } else {
+      osc_state<T, N, KD, false>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, u, tr, nullptr, K);
     }
     store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);  // deferred states: placeholder, rewritten below
     if (a.train) store_records<T, N>(a.train, warp_b0, nvalid, tr, stage, lane);
   }
 }
 
-// Second launch of the two-launch mode: one warp per CTA so that the ~2.5 k deferred states of a 65 536-state batch
-// spread over as many SMs as possible (the launch is latency bound).  The last CTA to finish re-arms the queue.
-constexpr int kSlowBlock = 32;
+// Second launch of the two-launch mode: finishes the deferred states from their records (osc_eval MODE 2: truncating
+// pseudo-inverse, J^T, the null-space filter).  One warp per CTA so that the ~2.5 k deferred states of a 65 536-state
+// UR5 batch spread over as many SMs as possible (the launch is latency bound).  The last CTA to finish re-arms the
+// queue for the next call.
+constexpr int kFinishBlock = 32;
 template <typename T, int N, bool ORTHO, int KD, bool KSMEM>
-__global__ void __launch_bounds__(kSlowBlock)
-osc_slow_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
-                const __grid_constant__ OscArgs<T> a) {
+__global__ void __launch_bounds__(kFinishBlock)
+osc_finish_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
+                  const __grid_constant__ OscArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef KinSel<T, N, ORTHO, KSMEM> KS;
   const int lane = threadIdx.x;
@@ -255,23 +269,16 @@ osc_slow_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ 
   typename KS::type K;
   KS::bind(K, region, lane);
   const int count = *static_cast<volatile int *>(a.queue);
-  for (int base = blockIdx.x * kSlowBlock; base < count; base += gridDim.x * kSlowBlock) {
+  for (int base = blockIdx.x * kFinishBlock; base < count; base += gridDim.x * kFinishBlock) {
     const int i = base + lane;
-    const bool valid = i < count;
-    const int64_t b = a.queue[4 + (valid ? i : count - 1)];
-    T q[N], dq[N], tg[6], tv[6], u[N], tr[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      q[k] = a.q[b * N + k];
-      dq[k] = a.dq[b * N + k];
-    }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      tg[c] = a.target[b * a.target_stride + c];
-      tv[c] = a.tv != nullptr ? a.tv[b * a.tv_stride + c] : T(0);
-    }
-    osc_state<T, N, KD, false, false>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, u, tr, nullptr, K);
-    if (valid) {
+    const bool in_range = i < count;
+    const int pos = in_range ? i : count - 1;
+    const int64_t b = a.queue[4 + pos];
+    T u[N], tr[N];
+    DevRecord<T> rec{a.queue, a.records, a.rec_stride, b, pos};
+    osc_eval<T, N, KD, false, 2>(P, O, (const T *)nullptr, (const T *)nullptr, (const T *)nullptr, (const T *)nullptr, u,
+                                 tr, (T *)nullptr, K, rec);
+    if (in_range && b >= 0) {
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         a.u[b * N + k] = u[k];
@@ -417,6 +424,47 @@ ctrl_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ Ctrl
   }
 }
 
+template <typename T>
+struct SlidingArgs {
+  const T *q, *dq, *target, *tv, *ta;
+  T *u, *s;
+  int64_t B;
+  int target_stride, tv_stride, ta_stride, cartesian, frame;
+  T kd, lamb;
+  T xoff[3];
+};
+
+// Sliding.generate: J, dJ, M, C, g of one state and two applications of pinv(J) (abrb_osc.cuh, sliding_state)
+template <typename T, int N, bool ORTHO>
+__global__ void __launch_bounds__(kBlock)
+sliding_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ SlidingArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T *stage = reinterpret_cast<T *>(smem_raw) + warp * kPitch * N;
+  const int w = a.cartesian ? 3 : N;
+  for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
+    const int64_t warp_b0 = base + warp * 32;
+    if (warp_b0 >= a.B) break;
+    const int64_t rem = a.B - warp_b0;
+    const int nvalid = rem < 32 ? (int)rem : 32;
+    const int64_t b = warp_b0 + (lane < nvalid ? lane : nvalid - 1);
+    T q[N], dq[N], tg[N], tv[N], ta[N], u[N], sv[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      q[k] = a.q[b * N + k];
+      dq[k] = a.dq[b * N + k];
+      const bool on = k < w;
+      tg[k] = on ? a.target[b * a.target_stride + k] : T(0);
+      tv[k] = (on && a.tv != nullptr) ? a.tv[b * a.tv_stride + k] : T(0);
+      ta[k] = (on && a.ta != nullptr) ? a.ta[b * a.ta_stride + k] : T(0);
+    }
+    Kin<T, N, ORTHO> K;
+    sliding_state<T, N>(P, a.kd, a.lamb, a.cartesian != 0, a.frame, a.xoff, q, dq, tg, tv, ta, u, sv, K);
+    store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);
+    if (a.s != nullptr) store_records<T, N>(a.s, warp_b0, nvalid, sv, stage, lane);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ launch
 inline int num_sms() {
   static int sm_count = 0;
@@ -516,13 +564,15 @@ int osc_go(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
   a.target_stride = c.target_stride;
   a.tv_stride = c.tv_stride;
   a.queue = c.queue;
+  a.records = static_cast<T *>(c.records);
+  a.rec_stride = c.rec_stride;
   constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32 || ABRB_ROLLED;  // rolled loops index the scratch at run time
   const size_t smem = (size_t)kWarps * WarpSmem<T, N, ORTHO, KSMEM, N>::kElems * sizeof(T);
   if constexpr (KD == 6) {
-    if (c.queue != nullptr) {
+    if (c.queue != nullptr && c.records != nullptr) {
       // two launches: everything but the truncating-pinv states, then those states densely packed
       auto k1 = osc_kernel<T, N, ORTHO, 6, KSMEM, true>;
-      auto k2 = osc_slow_kernel<T, N, ORTHO, 6, KSMEM>;
+      auto k2 = osc_finish_kernel<T, N, ORTHO, 6, KSMEM>;
       const size_t smem2 = (size_t)WarpSmem<T, N, ORTHO, KSMEM, N>::kElems * sizeof(T);
       cudaError_t e = set_smem(k1, smem);
       if (e == cudaSuccess) e = set_smem(k2, smem2);
@@ -531,9 +581,9 @@ int osc_go(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
       count_launch();
       e = cudaGetLastError();
       if (e != cudaSuccess) return (int)e;
-      const int64_t want = (c.B + kSlowBlock - 1) / kSlowBlock;
+      const int64_t want = (c.B + kFinishBlock - 1) / kFinishBlock;
       const int64_t cap = (int64_t)num_sms() * 8;
-      k2<<<(unsigned)(want < cap ? want : cap), kSlowBlock, smem2, c.stream>>>(P, O, a);
+      k2<<<(unsigned)(want < cap ? want : cap), kFinishBlock, smem2, c.stream>>>(P, O, a);
       count_launch();
       return (int)cudaGetLastError();
     }
@@ -648,6 +698,39 @@ template <>
 int launch_null<ABRB_N>(const ChainHost &h, const abrb_null_params &z, const NullCall &c) {
   if (c.f32) return h.ortho ? null_go<float, ABRB_N, true>(h, z, c) : null_go<float, ABRB_N, false>(h, z, c);
   return h.ortho ? null_go<double, ABRB_N, true>(h, z, c) : null_go<double, ABRB_N, false>(h, z, c);
+}
+
+template <typename T, int N, bool ORTHO>
+int sliding_go(const ChainHost &h, const SlidingCall &c) {
+  ChainK<T, N> P;
+  fill_chain<T, N>(h, P);
+  SlidingArgs<T> a;
+  a.q = static_cast<const T *>(c.q);
+  a.dq = static_cast<const T *>(c.dq);
+  a.target = static_cast<const T *>(c.target);
+  a.tv = static_cast<const T *>(c.tv);
+  a.ta = static_cast<const T *>(c.ta);
+  a.u = static_cast<T *>(c.u);
+  a.s = static_cast<T *>(c.s);
+  a.B = c.B;
+  a.target_stride = c.target_stride;
+  a.tv_stride = c.tv_stride;
+  a.ta_stride = c.ta_stride;
+  a.cartesian = c.cartesian;
+  a.frame = c.frame;
+  a.kd = T(c.kd);
+  a.lamb = T(c.lamb);
+  for (int i = 0; i < 3; ++i) a.xoff[i] = c.xoff ? T(c.xoff[i]) : T(0);
+  const size_t smem = (size_t)kWarps * kPitch * N * sizeof(T);
+  sliding_kernel<T, N, ORTHO><<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, a);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+template <>
+int launch_sliding<ABRB_N>(const ChainHost &h, const SlidingCall &c) {
+  if (c.f32) return h.ortho ? sliding_go<float, ABRB_N, true>(h, c) : sliding_go<float, ABRB_N, false>(h, c);
+  return h.ortho ? sliding_go<double, ABRB_N, true>(h, c) : sliding_go<double, ABRB_N, false>(h, c);
 }
 
 template <>

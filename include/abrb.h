@@ -116,7 +116,7 @@ int abrb_rbd_eval_host_f32(const abrb_model *m, int frame_id, const double *x_of
  *   ABRB_NULL_AVOID          controllers/avoid_obstacles.py:38-120
  * abrb_osc_generate_* evaluates OSC.generate (controllers/osc.py:217-320) for B states.
  * ------------------------------------------------------------------------------------------------- */
-enum { ABRB_NULL_DAMPING = 1, ABRB_NULL_RESTING = 2, ABRB_NULL_AVOID = 3 };
+enum { ABRB_NULL_DAMPING = 1, ABRB_NULL_RESTING = 2, ABRB_NULL_AVOID = 3, ABRB_NULL_JOINT_LIMITS = 4 };
 
 typedef struct abrb_null_params {
   int32_t kind;
@@ -127,6 +127,10 @@ typedef struct abrb_null_params {
   int32_t _pad;
   double threshold, gain, maximum;                /* AVOID (avoid_obstacles.py:25-36) */
   double obstacles[ABRB_MAX_OBSTACLES][4];        /* AVOID: x, y, z, radius */
+  /* JOINT_LIMITS (avoid_joint_limits.py:36-86): the controller's attributes AFTER its constructor, i.e. limits
+   * shifted by -pi and swapped where cross_zero is set; NaN = no limit on that side; max_torque default 1 */
+  double limit_min[ABRB_MAX_JOINTS], limit_max[ABRB_MAX_JOINTS], limit_torque[ABRB_MAX_JOINTS];
+  int32_t limit_cross_zero[ABRB_MAX_JOINTS], limit_gradient[ABRB_MAX_JOINTS];
 } abrb_null_params;
 
 typedef struct abrb_osc_params {
@@ -147,6 +151,13 @@ typedef struct abrb_osc abrb_osc;
 /* ki != 0 needs per-state integrator memory and is reported as ABRB_EUNSUP in this version. */
 int abrb_osc_create(const abrb_model *m, const abrb_osc_params *p, abrb_osc **out);
 int abrb_osc_destroy(abrb_osc *c);
+
+/* Execution options of one controller (no effect on results beyond rounding).  Names:
+ *   "two_launch_min"  batch size from which abrb_osc_generate_* runs the 6-row task space as two launches (all
+ *                     states but those on the truncating pinv route, then those from an index queue); 0 = never
+ *                     (default; the environment variable ABRB_OSC_DEFER_MIN sets another default).
+ * Returns ABRB_EINVAL for an unknown name. */
+int abrb_osc_set_option(abrb_osc *c, const char *name, double value);
 
 /* OSC.generate(q, dq, target, target_velocity=None, ref_frame="EE", xyz_offset=None) for B states.
  *   target          (B,6) if target_stride == 6, or one (6,) row broadcast to all states if target_stride == 0
@@ -172,7 +183,8 @@ int abrb_osc_generate_host_f32(const abrb_osc *c, int frame_id, const double *x_
                                const float *target_velocity, int tv_stride, float *u,
                                float *training_signal, int64_t B);
 
-/* Standalone secondary controller: Damping / RestingConfig / AvoidObstacles `.generate(q, dq)` -> (B,n). */
+/* Standalone secondary controller: Damping / RestingConfig / AvoidObstacles / AvoidJointLimits
+ * `.generate(q, dq)` -> (B,n). */
 int abrb_null_generate_f64(const abrb_model *m, const abrb_null_params *p, const double *q,
                            const double *dq, double *u, int64_t B, void *stream);
 int abrb_null_generate_f32(const abrb_model *m, const abrb_null_params *p, const float *q,
@@ -214,6 +226,24 @@ int abrb_osc_rollout_f32(const abrb_osc *c, int frame_id, const double *x_off, f
 
 /* Kernel launch counter for this process (every launch of a libabrb kernel increments it). */
 int64_t abrb_launch_count(void);
+
+/* Sliding-mode controller  Sliding.generate(q, dq, target, target_velocity=0, target_acc=0, ref_frame="EE",
+ * offset=None)  (controllers/sliding.py:34-99):
+ *   cartesian != 0:  J = J(frame, x_off)[:3], dq_ref = pinv(J)(tv + lamb (target - Tx)),
+ *                    ddq_ref = pinv(J)(ta + lamb (tv - J dq) - dJ[:3] dq_ref);   target/tv/ta rows have 3 values
+ *   cartesian == 0:  dq_ref = tv - lamb (q - target), ddq_ref = ta - lamb (dq - tv);   rows have n values
+ *   s = dq - dq_ref,  u = M ddq_ref + C dq_ref + g - kd s.
+ * target: one row per state (stride = row width) or one broadcast row (stride 0); target_velocity / target_acc
+ * likewise or NULL (zero).  s (B,n) receives the reference's `self.s` (the adaptation signal) or may be NULL. */
+int abrb_sliding_generate_f64(const abrb_model *m, double kd, double lamb, int cartesian, int frame_id,
+                              const double *x_off, const double *q, const double *dq, const double *target,
+                              int target_stride, const double *target_velocity, int tv_stride,
+                              const double *target_acc, int ta_stride, double *u, double *s, int64_t B,
+                              void *stream);
+int abrb_sliding_generate_f32(const abrb_model *m, double kd, double lamb, int cartesian, int frame_id,
+                              const double *x_off, const float *q, const float *dq, const float *target,
+                              int target_stride, const float *target_velocity, int tv_stride,
+                              const float *target_acc, int ta_stride, float *u, float *s, int64_t B, void *stream);
 
 #ifdef __cplusplus
 }

@@ -123,6 +123,69 @@ class Floating:
         return u
 
 
+class AvoidJointLimits:
+    """controllers/avoid_joint_limits.py:36-142.  NaN marks a joint without a limit (the reference's `None`
+    placeholder does not survive its own `np.isnan`, avoid_joint_limits.py:74-75)."""
+
+    def __init__(self, rc, min_joint_angles, max_joint_angles, max_torque=None, cross_zero=None, gradient=None):
+        n = rc.N_JOINTS
+        lo = np.array([np.nan if v is None else v - np.pi for v in min_joint_angles], dtype=float)  # :46-51
+        hi = np.array([np.nan if v is None else v - np.pi for v in max_joint_angles], dtype=float)
+        self.cross = np.array([False] * n if cross_zero is None else cross_zero)
+        self.grad = np.array([False] * n if gradient is None else gradient)
+        self.lo, self.hi = lo.copy(), hi.copy()
+        self.hi[self.cross] = lo[self.cross]  # :62-66 (flipped so that the maths matches the normal case)
+        self.lo[self.cross] = hi[self.cross]
+        self.no_lo, self.no_hi = np.isnan(self.lo), np.isnan(self.hi)
+        self.tmax = np.ones(n) if max_torque is None else np.asarray(max_torque, dtype=float)
+        self.n = n
+
+    def generate(self, q, dq=None):
+        q = np.asarray(q, dtype=float) - np.pi  # :91
+        with np.errstate(all="ignore"):
+            nearer_hi = abs(q - self.lo) >= abs(q - self.hi)  # the reference's `closer_to_min_index`, :94-96
+            nearer_lo = abs(q - self.lo) <= abs(q - self.hi)  # the reference's `closer_to_max_index`, :97-99
+            a_lo, a_hi = np.zeros(self.n), np.zeros(self.n)
+            gr = self.grad
+            a_lo[gr] = np.minimum(np.exp(1.0 / (q[gr] - self.lo[gr])), self.tmax[gr])  # :108-111
+            a_hi[gr] = -np.minimum(np.exp(-1.0 / (q[gr] - self.hi[gr])), self.tmax[gr])  # :112-115
+            below = (q - self.lo) < 0  # :118-119
+            above = (q - self.hi) > 0
+            cz = self.cross
+            below[cz] = below[cz] * ((q[cz] - self.hi[cz]) > 0) * nearer_lo[cz]  # :124-128
+            above[cz] = above[cz] * ((q[cz] - self.lo[cz]) < 0) * nearer_hi[cz]  # :130-134
+        a_lo[below] = self.tmax[below]
+        a_lo[self.no_lo] = 0.0
+        a_hi[above] = -self.tmax[above]
+        a_hi[self.no_hi] = 0.0
+        return a_lo + a_hi
+
+
+class Sliding:
+    """controllers/sliding.py:27-99 (Slotine & Li sliding control); `s` is the reference's training signal."""
+
+    def __init__(self, rc, kd=160.0, lamb=30.0, cartesian=True):
+        self.rc, self.kd, self.lamb, self.cartesian = rc, kd, lamb, cartesian
+        self.s = None
+
+    def generate(self, q, dq, target, target_velocity=0, target_acc=0, ref_frame="EE", offset=None):
+        rc = self.rc
+        offset = np.zeros(3) if offset is None else offset
+        if self.cartesian:
+            J = rc.J(ref_frame, q, x=offset)[:3]
+            xyz = rc.Tx(ref_frame, q, x=offset)
+            dxyz = np.dot(J, dq)
+            J_inv = np.linalg.pinv(J)
+            dJ = rc.dJ(ref_frame, q, dq, x=offset)[:3]
+            dq_ref = np.dot(J_inv, target_velocity + self.lamb * (target - xyz))
+            ddq_ref = np.dot(J_inv, target_acc + self.lamb * (target_velocity - dxyz) - np.dot(dJ, dq_ref))
+        else:
+            dq_ref = target_velocity - self.lamb * (q - target)
+            ddq_ref = target_acc - self.lamb * (dq - target_velocity)
+        self.s = dq - dq_ref
+        return np.dot(rc.M(q), ddq_ref) + np.dot(rc.C(q, dq), dq_ref) + rc.g(q) - self.kd * self.s
+
+
 def _segment_closest(p_a, p_b, centre):
     """closest point of segment [p_a, p_b] to ``centre`` (avoid_obstacles.py:69-83)."""
     seg = p_b - p_a
@@ -166,7 +229,8 @@ class AvoidObstacles:
         return np.clip(total * self.gain, -self.maximum, self.maximum)  # :120
 
 
-NULL_KINDS = {"Damping": Damping, "RestingConfig": RestingConfig, "AvoidObstacles": AvoidObstacles}
+NULL_KINDS = {"Damping": Damping, "RestingConfig": RestingConfig, "AvoidObstacles": AvoidObstacles,
+              "AvoidJointLimits": AvoidJointLimits}
 
 
 class OSC:
@@ -283,6 +347,23 @@ def run_ctrl_case(case, q, dq, target_q, target_dq, mode="fp64"):
         else:
             out.append(Floating(rc, **kw).generate(q[i], dq[i]))
     return np.array(out, dtype=np.float64)
+
+
+def run_sliding_case(case, q, dq, target, tv, ta, mode="fp64"):
+    """tests/cases.py::SLIDING_CASES -> (u, s), both (B, n)"""
+    rc = RobotOracle(case["arm"], mode)
+    ctrl = Sliding(rc, **case["ctrl"])
+    kw = {}
+    if case.get("ref_frame"):
+        kw["ref_frame"] = case["ref_frame"]
+    if case.get("offset") is not None:
+        kw["offset"] = np.array(case["offset"], dtype=float)
+    us, ss = [], []
+    for i in range(len(q)):
+        us.append(ctrl.generate(q[i], dq[i], target[i], target_velocity=0 if tv is None else tv[i],
+                                target_acc=0 if ta is None else ta[i], **kw))
+        ss.append(ctrl.s)
+    return np.array(us, dtype=np.float64), np.array(ss, dtype=np.float64)
 
 
 def run_null_case(case, q, dq, mode="fp64"):

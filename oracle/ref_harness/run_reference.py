@@ -52,10 +52,13 @@ def set_mode(fp64):
 
 
 def build_null(rc, kind, kw):
-    from abr_control.controllers import AvoidObstacles, Damping, RestingConfig
+    import copy
 
-    cls = {"Damping": Damping, "RestingConfig": RestingConfig, "AvoidObstacles": AvoidObstacles}[kind]
-    return cls(rc, **kw)
+    from abr_control.controllers import AvoidJointLimits, AvoidObstacles, Damping, RestingConfig
+
+    cls = {"Damping": Damping, "RestingConfig": RestingConfig, "AvoidObstacles": AvoidObstacles,
+           "AvoidJointLimits": AvoidJointLimits}[kind]
+    return cls(rc, **copy.deepcopy(kw))  # AvoidJointLimits shifts the lists it is given in place
 
 
 def main(arm, phase):
@@ -145,6 +148,28 @@ def main(arm, phase):
             ctrl = Floating(rc, **kw)
             osc_out[f"{name}__ctrl64"] = stack(lambda i: ctrl.generate(q[i], dq[i]))
         print(f"[{arm}] ctrl case {name} done {time.time()-t0:.0f}s", flush=True)
+
+    from abr_control.controllers import Sliding
+
+    for name, c in cases.SLIDING_CASES.items():
+        if c["arm"] != arm:
+            continue
+        tgt, tv, ta = cases.sliding_inputs(c)
+        ctrl = Sliding(rc, **c["ctrl"])
+        kw = {}
+        if c.get("ref_frame"):
+            kw["ref_frame"] = c["ref_frame"]
+        if c.get("offset") is not None:
+            kw["offset"] = np.array(c["offset"])
+        us, ss = [], []
+        for i in range(N):
+            u = ctrl.generate(q[i], dq[i], tgt[i], target_velocity=0 if tv is None else tv[i],
+                              target_acc=0 if ta is None else ta[i], **kw)
+            us.append(np.array(u, dtype=np.float64))
+            ss.append(np.array(ctrl.s, dtype=np.float64))
+        osc_out[f"{name}__sliding64"] = np.array(us)
+        osc_out[f"{name}__s64"] = np.array(ss)
+        print(f"[{arm}] sliding case {name} done {time.time()-t0:.0f}s", flush=True)
 
     # the reference's own pinned quantities for OSC helpers (controllers/tests/test_osc.py:19-59)
     if phase == "eval":

@@ -47,6 +47,7 @@ def hash_name(s):
 
 T, F = True, False
 PI = float(np.pi)
+NAN = float("nan")  # AvoidJointLimits: no limit on that side (the reference's None placeholder fails its own isnan)
 
 # name -> dict(arm, osc=<OSC kwargs>, null=[(kind, kwargs)...], tv=<use target_velocity>,
 #              ref_frame, xyz_offset)
@@ -112,6 +113,22 @@ OSC_CASES = {
         ],
     ),
     "twojoint_xy": dict(arm="twojoint", osc=dict(kp=15, use_C=True, ctrlr_dof=[T, T, F, F, F, F])),
+    # examples/PyGame/force_osc_xy_avoid_joint_limits.py:21-38
+    "threejoint_limits": dict(
+        arm="threejoint",
+        osc=dict(kp=100, ctrlr_dof=[T, T, F, F, F, F]),
+        null=[
+            ("AvoidJointLimits", dict(min_joint_angles=[PI / 5.0] * 3, max_joint_angles=[PI / 2.0] * 3, max_torque=[100.0] * 3)),
+            ("Damping", dict(kv=10)),
+        ],
+    ),
+    "ur5_limits_grad": dict(
+        arm="ur5",
+        osc=dict(kp=40, ko=30, ctrlr_dof=[T] * 6),
+        null=[("AvoidJointLimits", dict(
+            min_joint_angles=[0.5, NAN, 1.0, 5.5, NAN, 2.0], max_joint_angles=[2.0, 3.0, NAN, 1.0, NAN, 4.0],
+            max_torque=[3.0, 4.0, 5.0, 6.0, 7.0, 8.0], cross_zero=[F, F, F, T, F, F], gradient=[T, F, F, T, F, T]))],
+    ),
 }
 
 # standalone secondary controllers
@@ -130,6 +147,12 @@ NULL_CASES = {
     "threejoint_resting": dict(
         arm="threejoint", ctrl=("RestingConfig", dict(kp=50, kv=float(np.sqrt(50)), rest_angles=[PI / 4, PI, None]))
     ),
+    "ur5_limits": dict(arm="ur5", ctrl=("AvoidJointLimits", dict(
+        min_joint_angles=[0.5, NAN, 1.0, 5.5, NAN, 2.0], max_joint_angles=[2.0, 3.0, NAN, 1.0, NAN, 4.0],
+        max_torque=[3.0, 4.0, 5.0, 6.0, 7.0, 8.0], cross_zero=[F, F, F, T, F, F], gradient=[T, F, F, T, F, T]))),
+    "jaco2_limits_wall": dict(arm="jaco2", ctrl=("AvoidJointLimits", dict(
+        min_joint_angles=[1.0, 0.8, 0.3, NAN, 5.0, 1.5], max_joint_angles=[5.0, 5.4, 6.0, NAN, 1.2, 4.5],
+        cross_zero=[F, F, F, F, T, F]))),
 }
 
 # joint-space controllers: Joint.generate(q, dq, target, target_velocity) and Floating.generate(q, dq)
@@ -141,6 +164,30 @@ CTRL_CASES = {
     "jaco2_floating_task": dict(arm="jaco2", ctrl=("Floating", dict(task_space=True))),
     "threejoint_joint": dict(arm="threejoint", ctrl=("Joint", dict(kp=50))),
 }
+
+
+# Sliding.generate(q, dq, target, target_velocity, target_acc, ref_frame, offset)  
+#   cartesian: target/velocity/acc are the first 3 columns of states()'s target / target_velocity / joint_targets()[1];
+#   joint space: joint_targets() and dq-like rows
+SLIDING_CASES = {
+    "ur5_sliding_xyz": dict(arm="ur5", ctrl=dict(kd=10.0, lamb=30.0)),
+    "ur5_sliding_xyz_full": dict(arm="ur5", ctrl=dict(kd=160.0, lamb=30.0), tv=True, ta=True, ref_frame="EE", offset=XOFF),
+    "ur5_sliding_joint": dict(arm="ur5", ctrl=dict(kd=20.0, lamb=5.0, cartesian=False), tv=True, ta=True),
+    "threejoint_sliding_xyz": dict(arm="threejoint", ctrl=dict(kd=160.0, lamb=30.0), tv=True),
+}
+
+
+def sliding_inputs(case, count=N_GOLDEN):
+    """-> (target, target_velocity or None, target_acc or None) rows for one SLIDING_CASES entry"""
+    arm = case["arm"]
+    _, _, target, tvel = states(arm, count)
+    tq, tdq = joint_targets(arm, count)
+    if case["ctrl"].get("cartesian", True):
+        tgt, tv, ta = target[:, :3], tvel[:, :3], 0.3 * tdq[:, :1] + tvel[:, 3:6]
+    else:
+        tgt, tv, ta = tq, tdq, 0.5 * tdq[:, ::-1]
+    return (np.ascontiguousarray(tgt), np.ascontiguousarray(tv) if case.get("tv") else None,
+            np.ascontiguousarray(ta) if case.get("ta") else None)
 
 
 def joint_targets(arm, count=N_GOLDEN):

@@ -75,6 +75,55 @@ void osc_loop(const ChainHost &h, const abrb_osc_params &p, int frame, const dou
   }
 }
 
+// The two halves of the two-launch mode (osc_eval MODE 1 -> record -> MODE 2 on a FRESH scratch), state by state.
+template <typename T>
+struct HostRecord {
+  std::vector<T> v;
+  bool used = false;
+  void begin() { used = true; }
+  void put(int i, T x) {
+    if ((size_t)i >= v.size()) v.resize(i + 1);
+    v[i] = x;
+  }
+  T get(int i) const { return v[i]; }
+};
+
+template <typename T, int N, bool ORTHO>
+void osc_split_loop(const ChainHost &h, const abrb_osc_params &p, int frame, const double *xoff, const double *q,
+                    const double *dq, const double *target, int tstride, const double *tv, int tvstride, int64_t B,
+                    double *u, double *train, int64_t *n_deferred) {
+  ChainK<T, N> P;
+  fill_chain<T, N>(h, P);
+  OscK<T, N> O;
+  fill_osc<T, N>(p, frame, xoff, O);
+  *n_deferred = 0;
+  for (int64_t b = 0; b < B; ++b) {
+    T qq[N], dd[N], tg[6], tvv[6], uu[N], tr[N];
+    for (int k = 0; k < N; ++k) {
+      qq[k] = T(q[b * N + k]);
+      dd[k] = T(dq[b * N + k]);
+    }
+    for (int c = 0; c < 6; ++c) {
+      tg[c] = T(target[b * tstride + c]);
+      tvv[c] = tv ? T(tv[b * tvstride + c]) : T(0);
+    }
+    HostRecord<T> rec;
+    Kin<T, N, ORTHO> K;
+    if (osc_eval<T, N, 6, false, 1>(P, O, qq, dd, tg, tv ? tvv : nullptr, uu, tr, (T *)nullptr, K, rec)) {
+      ++*n_deferred;
+      if ((int)rec.v.size() != OscRecord<N, 6>::kLen) std::abort();
+      Kin<T, N, ORTHO> K2;
+      for (int k = 0; k < N; ++k) uu[k] = tr[k] = T(-777);
+      osc_eval<T, N, 6, false, 2>(P, O, (const T *)nullptr, (const T *)nullptr, (const T *)nullptr, (const T *)nullptr,
+                                  uu, tr, (T *)nullptr, K2, rec);
+    }
+    for (int k = 0; k < N; ++k) {
+      u[b * N + k] = double(uu[k]);
+      if (train) train[b * N + k] = double(tr[k]);
+    }
+  }
+}
+
 template <typename T, int N, bool ORTHO>
 void null_loop(const ChainHost &h, const abrb_null_params &z, const double *q, const double *dq, int64_t B, double *u) {
   ChainK<T, N> P;
@@ -90,6 +139,32 @@ void null_loop(const ChainHost &h, const abrb_null_params &z, const double *q, c
     Kin<T, N, ORTHO> K;
     null_state<T, N>(P, Z, qq, dd, uu, K);
     for (int k = 0; k < N; ++k) u[b * N + k] = double(uu[k]);
+  }
+}
+
+template <typename T, int N, bool ORTHO>
+void sliding_loop(const ChainHost &h, double kd, double lamb, int cartesian, int frame, const double *xoff,
+                  const double *q, const double *dq, const double *target, const double *tv, const double *ta,
+                  int64_t B, double *u, double *s) {
+  ChainK<T, N> P;
+  fill_chain<T, N>(h, P);
+  const int w = cartesian ? 3 : N;
+  T xo[3] = {T(xoff ? xoff[0] : 0), T(xoff ? xoff[1] : 0), T(xoff ? xoff[2] : 0)};
+  for (int64_t b = 0; b < B; ++b) {
+    T qq[N], dd[N], tg[N], tvv[N], taa[N], uu[N], ss[N];
+    for (int k = 0; k < N; ++k) {
+      qq[k] = T(q[b * N + k]);
+      dd[k] = T(dq[b * N + k]);
+      tg[k] = k < w ? T(target[b * w + k]) : T(0);
+      tvv[k] = (k < w && tv) ? T(tv[b * w + k]) : T(0);
+      taa[k] = (k < w && ta) ? T(ta[b * w + k]) : T(0);
+    }
+    Kin<T, N, ORTHO> K;
+    sliding_state<T, N>(P, T(kd), T(lamb), cartesian != 0, frame, xo, qq, dd, tg, tvv, taa, uu, ss, K);
+    for (int k = 0; k < N; ++k) {
+      u[b * N + k] = double(uu[k]);
+      if (s) s[b * N + k] = double(ss[k]);
+    }
   }
 }
 
@@ -166,6 +241,17 @@ int hs_osc(const abrb_chain_desc *d, const abrb_osc_params *p, int f32, int forc
   return 0;
 }
 
+int hs_osc_split(const abrb_chain_desc *d, const abrb_osc_params *p, int f32, int force_general, int frame,
+                 const double *xoff, const double *q, const double *dq, const double *target, int tstride,
+                 const double *tv, int tvstride, int64_t B, double *u, double *train, int64_t *n_deferred) {
+  ChainHost h;
+  if (!chain_from_desc(*d, h).empty()) return ABRB_EINVAL;
+  if (!check_osc(h.n, *p).empty()) return ABRB_EUNSUP;
+  const bool ortho = h.ortho && !force_general;
+  DISPATCH_N(osc_split_loop, h, *p, frame, xoff, q, dq, target, tstride, tv, tvstride, B, u, train, n_deferred);
+  return 0;
+}
+
 int hs_null(const abrb_chain_desc *d, const abrb_null_params *z, int f32, int force_general, const double *q,
             const double *dq, int64_t B, double *u) {
   ChainHost h;
@@ -181,6 +267,16 @@ int hs_ctrl(const abrb_chain_desc *d, int f32, int force_general, int kind, doub
   if (!chain_from_desc(*d, h).empty()) return ABRB_EINVAL;
   const bool ortho = h.ortho && !force_general;
   DISPATCH_N(ctrl_loop, h, kind, kp, kv, fa, fb, q, dq, target, tv, B, u);
+  return 0;
+}
+
+int hs_sliding(const abrb_chain_desc *d, int f32, int force_general, double kd, double lamb, int cartesian, int frame,
+               const double *xoff, const double *q, const double *dq, const double *target, const double *tv,
+               const double *ta, int64_t B, double *u, double *s) {
+  ChainHost h;
+  if (!chain_from_desc(*d, h).empty()) return ABRB_EINVAL;
+  const bool ortho = h.ortho && !force_general;
+  DISPATCH_N(sliding_loop, h, kd, lamb, cartesian, frame, xoff, q, dq, target, tv, ta, B, u, s);
   return 0;
 }
 

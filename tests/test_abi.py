@@ -87,6 +87,8 @@ def test_model_handles_and_error_codes_without_compute():
     assert lib.abrb_rbd_eval_f64(h, 13, None, None, None, 0, C.byref(out), None) == 0  # empty batch is a no-op
     assert lib.abrb_osc_generate_f64(hc, 13, None, None, None, None, 6, None, 0, None, None, 0, None) == 0
     assert lib.abrb_osc_generate_f64(hc, 13, None, None, None, None, 5, None, 0, None, None, 8, None) == _abi.EINVAL
+    assert lib.abrb_osc_set_option(hc, b"two_launch_min", 65536.0) == 0
+    assert lib.abrb_osc_set_option(hc, b"no_such_option", 1.0) == _abi.EINVAL
     assert lib.abrb_osc_destroy(hc) == 0 and lib.abrb_model_destroy(h) == 0
     jaco = _abi.chain_desc_from_dict(_abi.load_arm_json("jaco2"))
     assert lib.abrb_model_create(C.byref(jaco), C.byref(h)) == 0

@@ -161,6 +161,43 @@ def test_null_controllers_vs_reference_golden(name):
     _close(u, ref, 1e-8, 1e-9 * max(1.0, np.abs(ref).max()), name)
 
 
+@pytest.mark.parametrize("name", list(cases.SLIDING_CASES))
+def test_sliding_vs_reference_golden(name):
+    import torch
+
+    from abr_control_b200.controllers import Sliding
+
+    cs = cases.SLIDING_CASES[name]
+    o = np.load(f"{GOLD}/{cs['arm']}_osc.npz")
+    q, dq = o["q"], o["dq"]
+    tgt, tv, ta = cases.sliding_inputs(cs)
+    ref, ref_s = o[f"{name}__sliding64"], o[f"{name}__s64"]
+    kw = {}
+    if cs.get("ref_frame"):
+        kw["ref_frame"] = cs["ref_frame"]
+    if cs.get("offset") is not None:
+        kw["offset"] = cs["offset"]
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    sscale = np.abs(ref_s).max(axis=1, keepdims=True)
+    for dtype, tol in ((np.float64, 1e-9), (np.float32, 5e-3)):
+        ctrl = Sliding(_cfg(cs["arm"], dtype=dtype), **cs["ctrl"])
+        cast = lambda a: None if a is None else a.astype(dtype)  # noqa: E731
+        u = ctrl.generate(cast(q), cast(dq), cast(tgt), target_velocity=0 if tv is None else cast(tv),
+                          target_acc=0 if ta is None else cast(ta), **kw)
+        assert u.dtype == dtype and u.shape == ref.shape
+        assert (np.abs(u - ref) / scale).max() < tol, (name, dtype)
+        assert (np.abs(ctrl.s - ref_s) / sscale).max() < tol
+    # one state: float64 out like the reference; CUDA tensors in -> CUDA tensors out
+    ctrl = Sliding(_cfg(cs["arm"]), **cs["ctrl"])
+    one = ctrl.generate(q[0], dq[0], tgt[0], target_velocity=0 if tv is None else tv[0],
+                        target_acc=0 if ta is None else ta[0], **kw)
+    assert one.shape == ref[0].shape and np.abs(one - ref[0]).max() < 1e-9 * max(1.0, np.abs(ref[0]).max())
+    assert np.abs(ctrl.s - ref_s[0]).max() < 1e-9 * max(1.0, np.abs(ref_s[0]).max())
+    ud = ctrl.generate(torch.as_tensor(q, device="cuda"), torch.as_tensor(dq, device="cuda"),
+                       torch.as_tensor(tgt, device="cuda"), **kw)
+    assert ud.is_cuda and ud.shape == ref.shape and ctrl.s.is_cuda
+
+
 @pytest.mark.parametrize("name", list(cases.CTRL_CASES))
 def test_joint_and_floating_vs_reference_golden(name):
     import torch
@@ -307,10 +344,11 @@ def test_large_batch_deferred_pinv_states():
 
 
 def test_two_launch_mode_matches_single_launch():
-    """From 16384 states up the 6-row OSC path runs as two launches (everything but the truncating-pinv states, then
-    those states from an index queue; abr_control_b200/csrc/kernels.cu).  It must agree with the single-launch mode
-    (the same rows in chunks below the threshold) for every row, repeatedly (the queue re-arms itself), for batch
-    sizes that grow, shrink and are not multiples of the warp size, with and without the training-signal output."""
+    """Optional two-launch mode of the 6-row OSC path (everything but the truncating-pinv states, then those states
+    from an index queue; abr_control_b200/csrc/kernels.cu, abrb_osc_set_option "two_launch_min").  It must agree with
+    the single-launch mode (the same rows in chunks below the threshold) for every row, repeatedly (the queue re-arms
+    itself), for batch sizes that grow, shrink and are not multiples of the warp size, with and without the
+    training-signal output."""
     import torch
 
     rng = np.random.default_rng(23)
@@ -318,6 +356,7 @@ def test_two_launch_mode_matches_single_launch():
     for dtype, tol in ((np.float64, 1e-9), (np.float32, 2e-3)):
         rc = _cfg("ur5", dtype=dtype)
         ctrlr = _build_ctrl(rc, case)
+        ctrlr.set_option("two_launch_min", 16384)
         for B in (20000, 40003, 16384):
             q = rng.uniform(0, 2 * np.pi, (B, 6)).astype(dtype)
             dq = rng.uniform(0, 5, (B, 6)).astype(dtype)

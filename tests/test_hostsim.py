@@ -143,6 +143,28 @@ def test_joint_floating_math_vs_oracle(hostsim, name):
     assert _err(u, ref) < 1e-9 * max(1, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("name", list(cases.SLIDING_CASES))
+def test_sliding_math_vs_oracle(hostsim, name):
+    cs = cases.SLIDING_CASES[name]
+    q, dq, _, _ = cases.states(cs["arm"], 32)
+    tgt, tv, ta = cases.sliding_inputs(cs, 32)
+    cd = _abi.chain_desc_from_dict(_abi.load_arm_json(cs["arm"]))
+    n = cd.n_joints
+    kw = cs["ctrl"]
+    xo = None if cs.get("offset") is None else np.array(cs["offset"], dtype=np.float64)
+    fid = hostsim.hs_frame_id(n, cs.get("ref_frame", "EE").encode())
+    ref, ref_s = oo.run_sliding_case(cs, q, dq, tgt, tv, ta)
+    for f32, tol in ((0, 1e-9), (1, 2e-3)):
+        u, s = np.zeros((len(q), n)), np.zeros((len(q), n))
+        rc = hostsim.hs_sliding(C.byref(cd), f32, 0, C.c_double(kw.get("kd", 160.0)), C.c_double(kw.get("lamb", 30.0)),
+                                int(kw.get("cartesian", True)), fid, P(xo), P(np.ascontiguousarray(q)),
+                                P(np.ascontiguousarray(dq)), P(tgt), P(tv), P(ta), C.c_int64(len(q)), P(u), P(s))
+        assert rc == 0
+        scale = np.abs(ref).max(axis=1, keepdims=True)
+        assert np.max(np.abs(u - ref) / scale) < tol, (name, f32)
+        assert np.max(np.abs(s - ref_s) / np.abs(ref_s).max(axis=1, keepdims=True)) < tol
+
+
 def test_singular_states_pinv_branch(hostsim):
     """rank-deficient J M^-1 J^T -> the reference's pinv(rcond=1e-4) branch (osc.py:143-145), incl. truncation."""
     for arm, qs in (("twojoint", [[0.3, 0.0], [1.0, np.pi], [2.0, 1e-9]]),
@@ -161,6 +183,35 @@ def test_singular_states_pinv_branch(hostsim):
     ref, _ = oo.run_case(cs, q, dq, target)
     u, _, _ = hs_osc(hostsim, cs, q, dq, target, None)
     assert np.max(np.abs(u - ref) / np.abs(ref).max(axis=1, keepdims=True)) < 1e-9
+
+
+def test_two_launch_halves_reproduce_the_single_pass(hostsim):
+    """osc_eval MODE 1 (stop at a truncating-pinv state and write the record) followed by MODE 2 (finish from the
+    record on a fresh scratch) must give the single-pass result for every state; the kernels of the two-launch mode
+    are exactly these two halves."""
+    rng = np.random.default_rng(5)
+    B = 1500
+    q, dq, target = rng.uniform(0, 2 * np.pi, (B, 6)), rng.uniform(0, 5, (B, 6)), rng.uniform(-1, 1, (B, 6))
+    tv = rng.uniform(-0.5, 0.5, (B, 6))
+    for cs in (dict(arm="ur5", osc=dict(kp=50, ctrlr_dof=[True] * 6, use_C=True), null=[("Damping", dict(kv=10))]),
+               dict(arm="ur5", osc=dict(kp=20, ko=30, ctrlr_dof=[True, True, True, False, True, True], use_g=False), tv=True),
+               dict(arm="jaco2", osc=dict(kp=30, ctrlr_dof=[True] * 6),
+                    null=[("AvoidObstacles", dict(obstacles=[[0.1, -0.2, 0.5, 0.08]], threshold=0.5))])):
+        cd = _abi.chain_desc_from_dict(_abi.load_arm_json(cs["arm"]))
+        nulls = [_abi.null_params(k, 6, **kw) for k, kw in cs.get("null", [])]
+        p = _abi.osc_params(6, null=nulls, **cs["osc"])
+        tvv = np.ascontiguousarray(tv) if cs.get("tv") else None
+        for f32, tol in ((0, 1e-12), (1, 1e-5)):
+            a, ta, _ = hs_osc(hostsim, cs, q, dq, target, tv, f32=f32)
+            b, tb, n_def = np.zeros((B, 6)), np.zeros((B, 6)), C.c_int64(0)
+            rc = hostsim.hs_osc_split(C.byref(cd), C.byref(p), f32, 0, hostsim.hs_frame_id(6, b"EE"), None, P(q), P(dq),
+                                      P(target), 6, P(tvv), 6, C.c_int64(B), P(b), P(tb), C.byref(n_def))
+            assert rc == 0
+            if cs["arm"] == "ur5" and all(cs["osc"]["ctrlr_dof"]):
+                assert 25 < n_def.value < 100  # ~3.8 % of uniformly random UR5 states
+            scale = np.abs(a).max(axis=1, keepdims=True)
+            assert np.max(np.abs(a - b) / scale) < tol, (cs["arm"], f32)
+            assert np.max(np.abs(ta - tb) / scale) < tol
 
 
 def test_plant_acceleration(hostsim):
