@@ -73,9 +73,10 @@ class ShardedController:
         B = len(q)
         lo, hi = shard_range(B, rank, world)
         tgt = target[lo:hi] if np.ndim(target) == 2 else target
-        tv = kw.get("target_velocity")
-        if tv is not None and np.ndim(tv) == 2:
-            kw = dict(kw, target_velocity=tv[lo:hi])
+        for name in ("target_velocity", "target_acc"):  # per-state rows follow the shard, broadcast rows do not
+            v = kw.get(name)
+            if v is not None and np.ndim(v) == 2:
+                kw = dict(kw, **{name: v[lo:hi]})
         u = self.controller.generate(q[lo:hi], dq[lo:hi], tgt, **kw)
         if not gather or world == 1:
             return u

@@ -214,6 +214,22 @@ def test_two_launch_halves_reproduce_the_single_pass(hostsim):
             assert np.max(np.abs(ta - tb) / scale) < tol
 
 
+def test_non_finite_states_terminate_and_stay_local(hostsim):
+    """NaN / Inf in one state must not hang the iterative routes (bounded loops everywhere) nor touch other states."""
+    cs = cases.OSC_CASES["ur5_6dof_C_damp"]
+    rng = np.random.default_rng(0)
+    q, tg = rng.uniform(0, 6, (8, 6)), rng.uniform(-1, 1, (8, 6))
+    dq = 0.1 * q
+    clean, _, _ = hs_osc(hostsim, cs, q, dq, tg, None)
+    q2, dq2, tg2 = q.copy(), dq.copy(), tg.copy()
+    q2[1, 2], q2[2, 0], dq2[3, 1], tg2[4, 4] = np.nan, np.inf, np.nan, np.nan
+    u, _, _ = hs_osc(hostsim, cs, q2, dq2, tg2, None)
+    bad = [1, 2, 3, 4]
+    good = [0, 5, 6, 7]
+    assert not np.isfinite(u[bad]).all(axis=1).any()
+    assert np.array_equal(u[good], clean[good])
+
+
 def test_plant_acceleration(hostsim):
     """ddq returned by the rollout variant solves M ddq = u + g - C dq."""
     cs = cases.OSC_CASES["ur5_xyz"]
