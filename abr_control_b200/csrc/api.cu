@@ -372,18 +372,22 @@ static int osc_generate_host(const abrb_osc *c, int frame_id, const double *x_of
   // Chunked 3-stage pipeline over three streams: the H2D copy of chunk c+1 overlaps the kernel of chunk c and the
   // D2H copy of chunk c-1 (the copy engines are full duplex), so a large batch costs ~max(H2D, kernel, D2H).
   const size_t row = n * es;
-  // chunks stay large: a launch is latency bound below ~64k states, so splitting smaller batches only adds latency
   static const int64_t chunk_env = [] {  // tuning knob: states per pipeline chunk
     const char *v = std::getenv("ABRB_HOST_CHUNK");
     return v ? (int64_t)std::atoll(v) : (int64_t)0;
   }();
-  int64_t chunk = B <= 131072 ? B : ((B + 3) / 4 + 127) / 128 * 128;
+  // measured on B200 (tools/dbg/e2e_probe.py, UR5 6-DOF fp64, B = 65536): 1 chunk 347 us, 2 chunks 306 us, 3: 310,
+  // 4: 330, 8: 373 — every chunk costs ~20 us of copy/launch overheads, so two chunks up to ~200 k states, four above
+  int64_t chunk = B < 49152 ? B : ((B + (B <= 196608 ? 1 : 3)) / (B <= 196608 ? 2 : 4) + 127) / 128 * 128;
   if (chunk_env > 0) chunk = (chunk_env < B ? chunk_env : B + 127) / 128 * 128;
   if (chunk <= 0) chunk = B;
+  cudaError_t ce = cudaSuccess;
   if (!target_stride) cudaMemcpyAsync(d_t, target, sz_t, cudaMemcpyHostToDevice, g_ws.stream);
   if (tv && !tv_stride) cudaMemcpyAsync(d_tv, tv, sz_tv, cudaMemcpyHostToDevice, g_ws.stream);
-  cudaError_t ce = cudaStreamSynchronize(g_ws.stream);
-  if (ce) return cuda_fail(ce, "abrb_osc_generate_host");
+  if (!target_stride || (tv && !tv_stride)) {  // broadcast rows must be resident before any lane starts
+    ce = cudaStreamSynchronize(g_ws.stream);
+    if (ce) return cuda_fail(ce, "abrb_osc_generate_host");
+  }
   int lane = 0;
   for (int64_t b0 = 0; b0 < B; b0 += chunk, lane = (lane + 1) % 3) {
     const int64_t nb = B - b0 < chunk ? B - b0 : chunk;
@@ -402,8 +406,9 @@ static int osc_generate_host(const abrb_osc *c, int frame_id, const double *x_of
     cudaMemcpyAsync(atw(u, off_s), at(d_u, off_s), (size_t)nb * row, cudaMemcpyDeviceToHost, s);
     if (train) cudaMemcpyAsync(atw(train, off_s), at(d_tr, off_s), (size_t)nb * row, cudaMemcpyDeviceToHost, s);
   }
-  for (auto &l : g_ws.lanes) {
-    ce = cudaStreamSynchronize(l);
+  const int used = (int)((B + chunk - 1) / chunk) < 3 ? (int)((B + chunk - 1) / chunk) : 3;
+  for (int l = 0; l < used; ++l) {
+    ce = cudaStreamSynchronize(g_ws.lanes[l]);
     if (ce) return cuda_fail(ce, "abrb_osc_generate_host");
   }
   return ABRB_OK;

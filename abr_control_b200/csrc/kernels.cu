@@ -33,7 +33,10 @@ struct MinBlocks {
 #ifndef ABRB_MINBLOCKS_F32
 #define ABRB_MINBLOCKS_F32 4
 #endif
-  static constexpr int value = sizeof(T) == 8 ? 2 : ABRB_MINBLOCKS_F32;
+#ifndef ABRB_MINBLOCKS_F64
+#define ABRB_MINBLOCKS_F64 2
+#endif
+  static constexpr int value = sizeof(T) == 8 ? ABRB_MINBLOCKS_F64 : ABRB_MINBLOCKS_F32;
 };
 constexpr int kWarps = kBlock / 32;
 

@@ -50,18 +50,64 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region."""
+    """SM clock and throttle reasons DURING the timed region.
+
+    Primary source: NVML in this process (the library nvidia-smi itself reads), polled every 2 ms by a thread — it has
+    no start-up latency, so even a 50 ms timed region gets samples.  `nvidia-smi --query-gpu=... -lms 10` runs beside
+    it as a second source (it needs ~100 ms to print its first line); the two are merged."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
+        import threading
+
+        self.sm, self.mx, self.reasons, self.src = [], [], set(), []
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self._stop = threading.Event()
+        self._thread = None
         period = os.environ.get("ABRB_BENCH_CLOCK_MS", "10")  # tuning knob: "off" disables the sampler (A/B only)
         if period == "off":
             return
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                for cand in (f"GPU-{uuid}", str(uuid)):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons",
+                                 getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)))
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        if reasons_fn is not None:
+                            mask = int(reasons_fn(h))
+                            for bit, name in self.BITS.items():
+                                if mask & bit:
+                                    self.reasons.add(name)
+                    except Exception:
+                        pass
+                    self._stop.wait(0.002)
+
+            self._thread = threading.Thread(target=poll, daemon=True)
+            self._thread.start()
+            self.src.append("nvml")
+        except Exception:
+            self._thread = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
                                        period, "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
@@ -69,31 +115,37 @@ class ClockSampler:
             pass
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": []}
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1)
+        if self.p is not None:
+            self.p.terminate()
             try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+            self.f.flush()
+            self.f.seek(0)
+            n_smi = 0
+            for line in self.f.read().splitlines():
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    self.sm.append(float(c[1]))
+                    self.mx.append(float(c[2]))
+                    n_smi += 1
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+            if n_smi:
+                self.src.append("nvidia-smi")
+        if self.sm:
+            out.update(sm_mhz=float(np.median(self.sm)), sm_max_mhz=float(max(self.mx)) if self.mx else None,
+                       reasons=sorted(self.reasons), samples=len(self.sm), source=self.src)
         try:
             os.unlink(self.f.name)
         except OSError:
@@ -273,7 +325,7 @@ def run_ours(args):
     for i in range(max(args.warmup, 3)):
         step(i)
     fence()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) if rank == 0 else None
     n0 = L.abrb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -296,8 +348,8 @@ def run_ours(args):
     for _ in range(3):
         ctrlr.generate(nq, ndq, ntg)
     fence()
-    # several short blocks, median block: host-side copies share the box with whatever else runs on its cores
-    e2e_blocks = 5
+    # nine short blocks, median block: host-side copies share the box with whatever else runs on its cores
+    e2e_blocks = 9
     per_block = max(2, min(args.steps, 200) // e2e_blocks)
     e2e_steps = e2e_blocks * per_block
     block_t = []
@@ -422,7 +474,7 @@ def run_ours(args):
                 "steps": e2e_steps, "blocks": e2e_blocks, "block_range": e2e_spread,
                 "how": "OSC.generate(q, dq, target) on pinned host NumPy buffers -> abrb_osc_generate_host_f64 (H2D of q, dq, "
                        "target / kernel / D2H of u into a page-locked result, stream sync inside every call); wall clock, "
-                       "median of the blocks"},
+                       "median of the nine blocks"},
         "roofline": {"bound": "hbm", "achieved": (B * bytes_per_state / kernel_s / 1e9) if kernel_s else None,
                      "peak": hbm_peak, "unit": "GB/s",
                      "frac": (B * bytes_per_state / kernel_s / 1e9 / hbm_peak) if kernel_s else None, "traffic": traffic,
