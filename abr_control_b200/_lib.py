@@ -55,6 +55,8 @@ SIGNATURES = {
     "abrb_floating_generate_f32": (_I, [_VP, _I, _I, _VP, _VP, _VP, _I64, _VP]),
     "abrb_sliding_generate_f64": (_I, [_VP, _D, _D, _I, _I, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _VP, _VP, _I64, _VP]),
     "abrb_sliding_generate_f32": (_I, [_VP, _D, _D, _I, _I, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _VP, _VP, _I64, _VP]),
+    "abrb_ik_path_f64": (_I, [_VP, _D, _D, _D, _I, _D, _I, _VP, _VP, _I, _VP, _VP, _I64, _VP]),
+    "abrb_ik_path_f32": (_I, [_VP, _D, _D, _D, _I, _D, _I, _VP, _VP, _I, _VP, _VP, _I64, _VP]),
     "abrb_osc_rollout_f64": (_I, _roll),
     "abrb_osc_rollout_f32": (_I, _roll),
     "abrb_launch_count": (_I64, []),

@@ -82,6 +82,17 @@ struct SlidingCall {
   cudaStream_t stream;
 };
 
+struct IkCall {
+  double max_dx, max_dr, max_dq, dt;
+  int method, steps;
+  const void *position, *target;
+  int target_stride;
+  void *pos_path, *vel_path;
+  int64_t B;
+  bool f32;
+  cudaStream_t stream;
+};
+
 // Each returns a cudaError_t (0 = success).  Defined once per joint count in kernels.cu (-DABRB_N=<n>).
 template <int N> int launch_rbd(const ChainHost &h, const RbdCall &c);
 template <int N> int launch_osc(const ChainHost &h, const abrb_osc_params &p, const OscCall &c);
@@ -89,6 +100,7 @@ template <int N> int launch_rollout(const ChainHost &h, const abrb_osc_params &p
 template <int N> int launch_null(const ChainHost &h, const abrb_null_params &z, const NullCall &c);
 template <int N> int launch_ctrl(const ChainHost &h, const CtrlCall &c);
 template <int N> int launch_sliding(const ChainHost &h, const SlidingCall &c);
+template <int N> int launch_ik(const ChainHost &h, const IkCall &c);
 
 void count_launch();
 

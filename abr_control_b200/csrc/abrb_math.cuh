@@ -864,6 +864,93 @@ ABRB_HD void quat_from_euler_rxyz(T al, T be, T ga, T *qo) {
   qo[1] = cj * cs - sj * sc;     // k = 1
 }
 
+// quaternion_from_euler(ai, aj, ak, axes="sxyz")  (utils/transformations.py:1096-1147 with the axes tuple (0,0,0,0):
+// i, j, k = 1, 2, 3, no parity flip, no frame swap)
+template <typename T>
+ABRB_HD void quat_from_euler_sxyz(T ai, T aj, T ak, T *qo) {
+  T si, ci, sj, cj, sk, ck;
+  sincos_t(ai * T(0.5), &si, &ci);
+  sincos_t(aj * T(0.5), &sj, &cj);
+  sincos_t(ak * T(0.5), &sk, &ck);
+  const T cc = ci * ck, cs = ci * sk, sc = si * ck, ss = si * sk;
+  qo[0] = cj * cc + sj * ss;
+  qo[1] = cj * sc - sj * cs;
+  qo[2] = cj * ss + sj * cc;
+  qo[3] = cj * cs - sj * sc;
+}
+
+// out = pinv(A) y for an R x N matrix A (row-major, R <= N expected), numpy.linalg.pinv's rcond = 1e-15: one-sided
+// Jacobi on the rows as in RowPinv3 (abrb_osc.cuh) but for any R, with every loop rolled over local-memory arrays —
+// the 15 row pairs of R = 6 unrolled would be ~3 k instructions, and this is a latency-bound sequential caller anyway.
+template <typename T, int R, int N>
+ABRB_HD_NOINLINE void pinv_rows_apply(const T *A, const T *y, T *out) {
+  T Bm[R][N], V[R][R];
+  ABRB_NOUNROLL
+  for (int i = 0; i < R; ++i) {
+    ABRB_NOUNROLL
+    for (int k = 0; k < N; ++k) Bm[i][k] = A[i * N + k];
+    ABRB_NOUNROLL
+    for (int k = 0; k < R; ++k) V[i][k] = i == k ? T(1) : T(0);
+  }
+  const T tol = sizeof(T) == 8 ? T(1e-32) : T(1e-14);
+  ABRB_NOUNROLL
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    bool rotated = false;
+    ABRB_NOUNROLL
+    for (int i = 0; i < R - 1; ++i) {
+      ABRB_NOUNROLL
+      for (int j = i + 1; j < R; ++j) {
+        T al = T(0), be = T(0), ga = T(0);
+        ABRB_NOUNROLL
+        for (int k = 0; k < N; ++k) {
+          al += Bm[i][k] * Bm[i][k];
+          be += Bm[j][k] * Bm[j][k];
+          ga += Bm[i][k] * Bm[j][k];
+        }
+        if (!(ga * ga > tol * al * be) || ga == T(0)) continue;
+        rotated = true;
+        const T zeta = (be - al) / (T(2) * ga);
+        const T t = (zeta >= T(0) ? T(1) : T(-1)) / (abs_t(zeta) + sqrt_t(T(1) + zeta * zeta));
+        const T c = T(1) / sqrt_t(T(1) + t * t), sn = c * t;
+        ABRB_NOUNROLL
+        for (int k = 0; k < N; ++k) {
+          const T x = Bm[i][k], w = Bm[j][k];
+          Bm[i][k] = c * x - sn * w;
+          Bm[j][k] = sn * x + c * w;
+        }
+        ABRB_NOUNROLL
+        for (int k = 0; k < R; ++k) {
+          const T x = V[i][k], w = V[j][k];
+          V[i][k] = c * x - sn * w;
+          V[j][k] = sn * x + c * w;
+        }
+      }
+    }
+    if (!rotated) break;
+  }
+  T s2[R], smax = T(0);
+  ABRB_NOUNROLL
+  for (int i = 0; i < R; ++i) {
+    T acc = T(0);
+    ABRB_NOUNROLL
+    for (int k = 0; k < N; ++k) acc += Bm[i][k] * Bm[i][k];
+    s2[i] = acc;
+    smax = acc > smax ? acc : smax;
+  }
+  ABRB_NOUNROLL
+  for (int k = 0; k < N; ++k) out[k] = T(0);
+  ABRB_NOUNROLL
+  for (int i = 0; i < R; ++i) {
+    if (!(s2[i] > T(1e-30) * smax)) continue;
+    T c = T(0);
+    ABRB_NOUNROLL
+    for (int k = 0; k < R; ++k) c += V[i][k] * y[k];
+    c /= s2[i];
+    ABRB_NOUNROLL
+    for (int k = 0; k < N; ++k) out[k] += Bm[i][k] * c;
+  }
+}
+
 // euler_matrix(a, b, g, axes="rxyz")[:3,:3]  (utils/transformations.py:973-1035), row-major R[9]
 template <typename T>
 ABRB_HD void R_from_euler_rxyz(T al, T be, T ga, T *R) {

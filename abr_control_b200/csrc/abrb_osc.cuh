@@ -790,54 +790,55 @@ ABRB_HD void floating_state(const ChainK<T, N> &P, bool task_space, bool dynamic
   (void)ORTHO;
 }
 
-// Sliding.generate (controllers/sliding.py:34-99).  pinv(J) for the 3 x N position Jacobian is applied through a
-// one-sided (Hestenes) Jacobi SVD of its rows: rotations of row pairs until they are mutually orthogonal give
-// J = V diag(sigma) U^T with sigma_i u_i = rotated row i, so pinv(J) y = sum_i row_i (v_i . y) / sigma_i^2 over the
-// sigma_i > 1e-15 sigma_max that numpy.linalg.pinv keeps.  (Going through J J^T would square the condition number.)
-template <typename T, int N, class K_>
-ABRB_HD void sliding_state(const ChainK<T, N> &P, T kd, T lamb, bool cartesian, int frame, const T *xoff, const T *q,
-                           const T *dq, const T *target, const T *tv, const T *ta, T *u, T *s_out, K_ &K) {
-  walk<T, N>(P, q, cartesian ? frame : 0, K);
-  T dq_ref[N], ddq_ref[N];
-  if (cartesian) {
-    const int dep = frame_dep<N>(frame);
-    T pF[3];
-    frame_point(K.F, xoff, pF);
-    T J[6][N], dJ[6][N];
-    jacobian<T, N>(K, pF, dep, J);
-    T b0[N], b1[N], b2[N], v0[3] = {T(1), T(0), T(0)}, v1[3] = {T(0), T(1), T(0)}, v2[3] = {T(0), T(0), T(1)};
+// pinv of a 3 x N matrix (the position or the orientation rows of a Jacobian) as numpy.linalg.pinv computes it
+// (rcond = 1e-15), applied to right-hand sides: a one-sided (Hestenes) Jacobi SVD of the rows — rotations of row pairs
+// until they are mutually orthogonal give J = V^T diag(sigma) U^T with sigma_i u_i = rotated row i, so
+// pinv(J) y = sum_i row_i (v_i . y) / sigma_i^2 over the sigma_i > 1e-15 sigma_max.  (Going through J J^T would square
+// the condition number.)  The sweep loop is rolled around three rotations with static indices.
+template <typename T, int N>
+struct RowPinv3 {
+  T b0[N], b1[N], b2[N], v0[3], v1[3], v2[3], i0, i1, i2;
+
+  ABRB_HD static void rotate(T *bi, T *bj, T *vi, T *vj) {
+    T al = T(0), be = T(0), ga = T(0);
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) {
-      b0[k] = J[0][k];
-      b1[k] = J[1][k];
-      b2[k] = J[2][k];
+      al += bi[k] * bi[k];
+      be += bj[k] * bj[k];
+      ga += bi[k] * bj[k];
     }
-    auto rotate = [](T *bi, T *bj, T *vi, T *vj) {
-      T al = T(0), be = T(0), ga = T(0);
+    if (ga * ga > (sizeof(T) == 8 ? T(1e-32) : T(1e-14)) * al * be && ga != T(0)) {
+      const T zeta = (be - al) / (T(2) * ga);
+      const T t = (zeta >= T(0) ? T(1) : T(-1)) / (abs_t(zeta) + sqrt_t(T(1) + zeta * zeta));
+      const T c = T(1) / sqrt_t(T(1) + t * t), sn = c * t;
       ABRB_UNROLL
       for (int k = 0; k < N; ++k) {
-        al += bi[k] * bi[k];
-        be += bj[k] * bj[k];
-        ga += bi[k] * bj[k];
+        const T x = bi[k], y = bj[k];
+        bi[k] = c * x - sn * y;
+        bj[k] = sn * x + c * y;
       }
-      if (ga * ga > (sizeof(T) == 8 ? T(1e-32) : T(1e-14)) * al * be && ga != T(0)) {
-        const T zeta = (be - al) / (T(2) * ga);
-        const T t = (zeta >= T(0) ? T(1) : T(-1)) / (abs_t(zeta) + sqrt_t(T(1) + zeta * zeta));
-        const T c = T(1) / sqrt_t(T(1) + t * t), sn = c * t;
-        ABRB_UNROLL
-        for (int k = 0; k < N; ++k) {
-          const T x = bi[k], y = bj[k];
-          bi[k] = c * x - sn * y;
-          bj[k] = sn * x + c * y;
-        }
-        ABRB_UNROLL
-        for (int k = 0; k < 3; ++k) {
-          const T x = vi[k], y = vj[k];
-          vi[k] = c * x - sn * y;
-          vj[k] = sn * x + c * y;
-        }
+      ABRB_UNROLL
+      for (int k = 0; k < 3; ++k) {
+        const T x = vi[k], y = vj[k];
+        vi[k] = c * x - sn * y;
+        vj[k] = sn * x + c * y;
       }
-    };
+    }
+  }
+
+  ABRB_HD void build(const T *r0, const T *r1, const T *r2) {
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) {
+      b0[k] = r0[k];
+      b1[k] = r1[k];
+      b2[k] = r2[k];
+    }
+    ABRB_UNROLL
+    for (int k = 0; k < 3; ++k) {
+      v0[k] = k == 0 ? T(1) : T(0);
+      v1[k] = k == 1 ? T(1) : T(0);
+      v2[k] = k == 2 ? T(1) : T(0);
+    }
     ABRB_NOUNROLL
     for (int sweep = 0; sweep < 8; ++sweep) {
       rotate(b0, b1, v0, v1);
@@ -853,14 +854,35 @@ ABRB_HD void sliding_state(const ChainK<T, N> &P, T kd, T lamb, bool cartesian, 
     }
     const T smax = s0 > s1 ? (s0 > s2 ? s0 : s2) : (s1 > s2 ? s1 : s2);
     const T cut = T(1e-30) * smax;  // (rcond = 1e-15)^2 on the squared singular values
-    const T i0 = s0 > cut ? T(1) / s0 : T(0), i1 = s1 > cut ? T(1) / s1 : T(0), i2 = s2 > cut ? T(1) / s2 : T(0);
-    auto pinv_J = [&](const T *y, T *out) {
-      const T c0 = (v0[0] * y[0] + v0[1] * y[1] + v0[2] * y[2]) * i0;
-      const T c1 = (v1[0] * y[0] + v1[1] * y[1] + v1[2] * y[2]) * i1;
-      const T c2 = (v2[0] * y[0] + v2[1] * y[1] + v2[2] * y[2]) * i2;
-      ABRB_UNROLL
-      for (int k = 0; k < N; ++k) out[k] = b0[k] * c0 + b1[k] * c1 + b2[k] * c2;
-    };
+    i0 = s0 > cut ? T(1) / s0 : T(0);
+    i1 = s1 > cut ? T(1) / s1 : T(0);
+    i2 = s2 > cut ? T(1) / s2 : T(0);
+  }
+
+  ABRB_HD void apply(const T *y, T *out) const {  // out = pinv(J) y
+    const T c0 = (v0[0] * y[0] + v0[1] * y[1] + v0[2] * y[2]) * i0;
+    const T c1 = (v1[0] * y[0] + v1[1] * y[1] + v1[2] * y[2]) * i1;
+    const T c2 = (v2[0] * y[0] + v2[1] * y[1] + v2[2] * y[2]) * i2;
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) out[k] = b0[k] * c0 + b1[k] * c1 + b2[k] * c2;
+  }
+};
+
+// Sliding.generate (controllers/sliding.py:34-99); pinv(J[:3]) through RowPinv3.
+template <typename T, int N, class K_>
+ABRB_HD void sliding_state(const ChainK<T, N> &P, T kd, T lamb, bool cartesian, int frame, const T *xoff, const T *q,
+                           const T *dq, const T *target, const T *tv, const T *ta, T *u, T *s_out, K_ &K) {
+  walk<T, N>(P, q, cartesian ? frame : 0, K);
+  T dq_ref[N], ddq_ref[N];
+  if (cartesian) {
+    const int dep = frame_dep<N>(frame);
+    T pF[3];
+    frame_point(K.F, xoff, pF);
+    T J[6][N], dJ[6][N];
+    jacobian<T, N>(K, pF, dep, J);
+    RowPinv3<T, N> Jp;
+    Jp.build(J[0], J[1], J[2]);
+    auto pinv_J = [&](const T *y, T *out) { Jp.apply(y, out); };
     T r1[3], r2[3];
     ABRB_UNROLL
     for (int c = 0; c < 3; ++c) r1[c] = (tv != nullptr ? tv[c] : T(0)) + lamb * (target[c] - pF[c]);
@@ -896,6 +918,103 @@ ABRB_HD void sliding_state(const ChainK<T, N> &P, T kd, T lamb, bool cartesian, 
     const T sa = dq[a] - dq_ref[a];
     if (s_out != nullptr) s_out[a] = sa;
     u[a] = acc + g[a] - kd * sa;
+  }
+}
+
+// One iteration of InverseKinematics.generate_path (controllers/path_planners/inverse_kinematics.py:83-137): the joint
+// step dq towards the task-space target from the current q.  `Qd`: unit target quaternion (the reference builds it
+// with axes="sxyz" whatever `axes` it was given, :72-81).  max_dx / max_dr / max_dq are already multiplied by dt.
+//   method 1: dq = pinv(J) [dx, dr];   2: dq = J^T (J J^T + 0.001 I)^-1 [dx, 0.3 dr];
+//   method 3: dq = pinv(Jx) dx + (I - pinv(Jx) Jx) pinv(Jr) dr      (Jx = J[:3], Jr = J[3:])
+template <typename T, int N, class K_>
+ABRB_HD void ik_step(const ChainK<T, N> &P, T max_dx, T max_dr, T max_dq, int method, const T *q, const T *target,
+                     const T *Qd, T *dq, K_ &K) {
+  walk<T, N>(P, q, 2 * N + 1, K);
+  T pF[3] = {K.F[3], K.F[7], K.F[11]};
+  T J[6][N];
+  jacobian<T, N>(K, pF, N, J);
+  T R[9], Qe[4];
+  ABRB_UNROLL
+  for (int r = 0; r < 3; ++r)
+    ABRB_UNROLL
+  for (int c = 0; c < 3; ++c) R[r * 3 + c] = K.F[r * 4 + c];
+  quat_from_R(R, Qe);
+  T dx[3], dr[3];
+  ABRB_UNROLL
+  for (int c = 0; c < 3; ++c) dx[c] = target[c] - pF[c];
+  // dr = Qe[0] Qd[1:] - Qd[0] Qe[1:] - Qd[1:] x Qe[1:]   (:93)
+  T cr[3];
+  cross3(Qd + 1, Qe + 1, cr);
+  ABRB_UNROLL
+  for (int c = 0; c < 3; ++c) dr[c] = Qe[0] * Qd[1 + c] - Qd[0] * Qe[1 + c] - cr[c];
+  const T ndx = sqrt_t(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
+  const T ndr = sqrt_t(dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
+  if (ndx > max_dx) {
+    ABRB_UNROLL
+    for (int c = 0; c < 3; ++c) dx[c] = dx[c] / ndx * max_dx;
+  }
+  if (ndr > max_dr) {
+    ABRB_UNROLL
+    for (int c = 0; c < 3; ++c) dr[c] = dr[c] / ndr * max_dr;
+  }
+  if (method == 1) {
+    T Af[6 * N], yf[6], of[N];  // private copies: the out-of-line routine takes addresses
+    ABRB_UNROLL
+    for (int r = 0; r < 6; ++r) {
+      yf[r] = r < 3 ? dx[r < 3 ? r : 0] : dr[r < 3 ? 0 : r - 3];
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) Af[r * N + k] = J[r][k];
+    }
+    pinv_rows_apply<T, 6, N>(Af, yf, of);
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) dq[k] = of[k];
+  } else if (method == 2) {
+    T S[6][6], Si[6], y[6];
+    ABRB_UNROLL
+    for (int a = 0; a < 6; ++a) {
+      y[a] = a < 3 ? dx[a < 3 ? a : 0] : T(0.3) * dr[a < 3 ? 0 : a - 3];
+      ABRB_UNROLL
+      for (int b = 0; b < 6; ++b) {
+        T acc = a == b ? T(0.001) : T(0);
+        ABRB_UNROLL
+        for (int k = 0; k < N; ++k) acc += J[a][k] * J[b][k];
+        S[a][b] = acc;
+      }
+    }
+    chol<T, 6>(S, Si);  // J J^T + 0.001 I is positive definite
+    fwd_solve<T, 6>(S, Si, y);
+    bwd_solve<T, 6>(S, Si, y);
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) {
+      T acc = T(0);
+      ABRB_UNROLL
+      for (int a = 0; a < 6; ++a) acc += J[a][k] * y[a];
+      dq[k] = acc;
+    }
+  } else {
+    RowPinv3<T, N> Px, Pr;
+    Px.build(J[0], J[1], J[2]);
+    Pr.build(J[3], J[4], J[5]);
+    T a[N], w[N], jw[3], pw[N];
+    Px.apply(dx, a);
+    Pr.apply(dr, w);
+    ABRB_UNROLL
+    for (int c = 0; c < 3; ++c) {
+      T acc = T(0);
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) acc += J[c][k] * w[k];
+      jw[c] = acc;
+    }
+    Px.apply(jw, pw);
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) dq[k] = a[k] + w[k] - pw[k];
+  }
+  T big = T(0);
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) big = abs_t(dq[k]) > big ? abs_t(dq[k]) : big;
+  if (big > max_dq) {
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) dq[k] = dq[k] / big * max_dq;
   }
 }
 

@@ -503,6 +503,44 @@ int abrb_sliding_generate_f32(const abrb_model *m, double kd, double lamb, int c
                           tv_stride, target_acc, ta_stride, u, s, B, stream, true);
 }
 
+// ------------------------------------------------------------------------------------------------ inverse kinematics
+static int ik_path(const abrb_model *m, double max_dx, double max_dr, double max_dq, int method, double dt, int steps,
+                   const void *position, const void *target, int target_stride, void *pos_path, void *vel_path,
+                   int64_t B, void *stream, bool f32) {
+  if (!m) return fail(ABRB_EINVAL, "abrb_ik_path: NULL model");
+  if (B < 0 || steps < 0) return fail(ABRB_EINVAL, "abrb_ik_path: negative size");
+  if (method < 1 || method > 3) return fail(ABRB_EUNSUP, "abrb_ik_path: method must be 1, 2 or 3");
+  if (target_stride != 0 && target_stride != 6) return fail(ABRB_EINVAL, "abrb_ik_path: stride must be 0 or 6");
+  if (B == 0 || steps == 0) return ABRB_OK;
+  if (!position || !target || !pos_path || !vel_path) return fail(ABRB_EINVAL, "abrb_ik_path: NULL argument");
+  if (!aligned16(position) || !aligned16(pos_path) || !aligned16(vel_path))
+    return fail(ABRB_EINVAL, "abrb_ik_path: pointers must be 16-byte aligned");
+  int rc = ensure_device();
+  if (rc) return rc;
+  IkCall k{max_dx, max_dr, max_dq, dt, method, steps, position, target, target_stride, pos_path, vel_path, B, f32,
+           (cudaStream_t)stream};
+  int e = cudaErrorInvalidValue;
+  switch (m->host.n) {
+#define X(j) case j: e = launch_ik<j>(m->host, k); break;
+    ABRB_N_LIST(X)
+#undef X
+  }
+  return e ? cuda_fail(e, "abrb_ik_path") : ABRB_OK;
+}
+
+int abrb_ik_path_f64(const abrb_model *m, double max_dx, double max_dr, double max_dq, int method, double dt,
+                     int n_timesteps, const double *position, const double *target, int target_stride,
+                     double *position_path, double *velocity_path, int64_t B, void *stream) {
+  return ik_path(m, max_dx, max_dr, max_dq, method, dt, n_timesteps, position, target, target_stride, position_path,
+                 velocity_path, B, stream, false);
+}
+int abrb_ik_path_f32(const abrb_model *m, double max_dx, double max_dr, double max_dq, int method, double dt,
+                     int n_timesteps, const float *position, const float *target, int target_stride,
+                     float *position_path, float *velocity_path, int64_t B, void *stream) {
+  return ik_path(m, max_dx, max_dr, max_dq, method, dt, n_timesteps, position, target, target_stride, position_path,
+                 velocity_path, B, stream, true);
+}
+
 // ------------------------------------------------------------------------------------------------ joint / floating
 static int ctrl_generate(const abrb_model *m, int kind, double kp, double kv, int fa, int fb, const void *q,
                          const void *dq, const void *target, int target_stride, const void *tv, int tv_stride, void *u,

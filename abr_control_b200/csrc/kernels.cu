@@ -468,6 +468,51 @@ sliding_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ S
   }
 }
 
+template <typename T>
+struct IkArgs {
+  const T *position, *target;
+  T *pos_path, *vel_path;  // (steps, B, n)
+  int64_t B;
+  int target_stride, steps, method;
+  T max_dx, max_dr, max_dq;  // already multiplied by dt
+};
+
+// InverseKinematics.generate_path: one trajectory per thread, the joint state stays in registers over the steps
+// (sequential by construction, like the rollout kernel)
+template <typename T, int N, bool ORTHO>
+__global__ void __launch_bounds__(kBlock)
+ik_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ IkArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T *stage = reinterpret_cast<T *>(smem_raw) + warp * kPitch * N;
+  for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
+    const int64_t warp_b0 = base + warp * 32;
+    if (warp_b0 >= a.B) break;
+    const int64_t rem = a.B - warp_b0;
+    const int nvalid = rem < 32 ? (int)rem : 32;
+    const int64_t b = warp_b0 + (lane < nvalid ? lane : nvalid - 1);
+    T q[N], dq[N], tg[3], Qd[4];
+#pragma unroll
+    for (int k = 0; k < N; ++k) q[k] = a.position[b * N + k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tg[c] = a.target[b * a.target_stride + c];
+    quat_from_euler_sxyz(a.target[b * a.target_stride + 3], a.target[b * a.target_stride + 4],
+                         a.target[b * a.target_stride + 5], Qd);
+    const T nq = T(1) / sqrt_t(Qd[0] * Qd[0] + Qd[1] * Qd[1] + Qd[2] * Qd[2] + Qd[3] * Qd[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Qd[i] *= nq;
+    for (int t = 0; t < a.steps; ++t) {
+      Kin<T, N, ORTHO> K;
+      ik_step<T, N>(P, a.max_dx, a.max_dr, a.max_dq, a.method, q, tg, Qd, dq, K);
+      const int64_t row0 = (int64_t)t * a.B + warp_b0;
+      store_records<T, N>(a.pos_path, row0, nvalid, q, stage, lane);
+      store_records<T, N>(a.vel_path, row0, nvalid, dq, stage, lane);
+#pragma unroll
+      for (int k = 0; k < N; ++k) q[k] += dq[k];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ launch
 inline int num_sms() {
   static int sm_count = 0;
@@ -728,6 +773,34 @@ int sliding_go(const ChainHost &h, const SlidingCall &c) {
   sliding_kernel<T, N, ORTHO><<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, a);
   count_launch();
   return (int)cudaGetLastError();
+}
+
+template <typename T, int N, bool ORTHO>
+int ik_go(const ChainHost &h, const IkCall &c) {
+  ChainK<T, N> P;
+  fill_chain<T, N>(h, P);
+  IkArgs<T> a;
+  a.position = static_cast<const T *>(c.position);
+  a.target = static_cast<const T *>(c.target);
+  a.pos_path = static_cast<T *>(c.pos_path);
+  a.vel_path = static_cast<T *>(c.vel_path);
+  a.B = c.B;
+  a.target_stride = c.target_stride;
+  a.steps = c.steps;
+  a.method = c.method;
+  a.max_dx = T(c.max_dx * c.dt);
+  a.max_dr = T(c.max_dr * c.dt);
+  a.max_dq = T(c.max_dq * c.dt);
+  const size_t smem = (size_t)kWarps * kPitch * N * sizeof(T);
+  ik_kernel<T, N, ORTHO><<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, a);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+template <>
+int launch_ik<ABRB_N>(const ChainHost &h, const IkCall &c) {
+  if (c.f32) return h.ortho ? ik_go<float, ABRB_N, true>(h, c) : ik_go<float, ABRB_N, false>(h, c);
+  return h.ortho ? ik_go<double, ABRB_N, true>(h, c) : ik_go<double, ABRB_N, false>(h, c);
 }
 
 template <>

@@ -245,6 +245,20 @@ int abrb_sliding_generate_f32(const abrb_model *m, double kd, double lamb, int c
                               int target_stride, const float *target_velocity, int tv_stride,
                               const float *target_acc, int ta_stride, float *u, float *s, int64_t B, void *stream);
 
+/* Iterative inverse-kinematics path  InverseKinematics(robot_config, max_dx, max_dr, max_dq).generate_path(position,
+ * target_position, n_timesteps, dt, method)  (controllers/path_planners/inverse_kinematics.py:28-166), one path per
+ * state: n_timesteps resolved-motion steps towards target (x, y, z, Euler a, b, g) at frame "EE", the task-space
+ * step clipped to max_dx dt / max_dr dt and the joint step to max_dq dt.  method 1: pinv(J); 2: damped least
+ * squares; 3: position first, orientation in its null space (the reference's default).
+ *   position (B,n);  target (B,6) if target_stride == 6, one (6,) row if 0
+ *   position_path, velocity_path: (n_timesteps, B, n) out — row t holds q_t and the step dq_t taken from it */
+int abrb_ik_path_f64(const abrb_model *m, double max_dx, double max_dr, double max_dq, int method, double dt,
+                     int n_timesteps, const double *position, const double *target, int target_stride,
+                     double *position_path, double *velocity_path, int64_t B, void *stream);
+int abrb_ik_path_f32(const abrb_model *m, double max_dx, double max_dr, double max_dq, int method, double dt,
+                     int n_timesteps, const float *position, const float *target, int target_stride,
+                     float *position_path, float *velocity_path, int64_t B, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

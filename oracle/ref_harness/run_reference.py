@@ -171,12 +171,40 @@ def main(arm, phase):
         osc_out[f"{name}__s64"] = np.array(ss)
         print(f"[{arm}] sliding case {name} done {time.time()-t0:.0f}s", flush=True)
 
+    # inverse-kinematics path planner (its module imports matplotlib for an optional plot; the image has none, so the
+    # harness registers an empty stand-in — the plotting branch is never taken)
+    ik_out = {}
+    if any(c["arm"] == arm for c in cases.IK_CASES.values()):
+        import types
+
+        for mod in ("matplotlib", "matplotlib.pyplot", "mpl_toolkits", "mpl_toolkits.mplot3d"):
+            sys.modules.setdefault(mod, types.ModuleType(mod))
+        sys.modules["mpl_toolkits.mplot3d"].axes3d = None  # `from mpl_toolkits.mplot3d import axes3d` (path_planner.py)
+        from abr_control.controllers.path_planners.inverse_kinematics import InverseKinematics
+
+        n_ik = cases.N_IK if phase == "eval" else 1
+        ik_targets = cases.ik_targets(arm)
+        ik_out["position"], ik_out["target"] = q[: cases.N_IK], ik_targets
+        for name, c in cases.IK_CASES.items():
+            if c["arm"] != arm:
+                continue
+            planner = InverseKinematics(rc, **c.get("init", {}))
+            pos, vel = [], []
+            for i in range(n_ik):
+                p_path, v_path = planner.generate_path(np.copy(q[i]), ik_targets[i], plot=False, **c["path"])
+                pos.append(np.array(p_path, dtype=np.float64))
+                vel.append(np.array(v_path, dtype=np.float64))
+            ik_out[f"{name}__pos64"], ik_out[f"{name}__vel64"] = np.array(pos), np.array(vel)
+            print(f"[{arm}] ik case {name} done {time.time()-t0:.0f}s", flush=True)
+
     # the reference's own pinned quantities for OSC helpers (controllers/tests/test_osc.py:19-59)
     if phase == "eval":
         gdir = os.path.join(REPO, "tests", "golden")
         os.makedirs(gdir, exist_ok=True)
         np.savez_compressed(os.path.join(gdir, f"{arm}_rbd.npz"), **out)
         np.savez_compressed(os.path.join(gdir, f"{arm}_osc.npz"), **osc_out)
+        if ik_out:
+            np.savez_compressed(os.path.join(gdir, f"{arm}_ik.npz"), **ik_out)
         loaded = [k for k in ("_M", "_g", "_C") if getattr(rc, k, None) is not None]
         kinds = {k: type(getattr(rc, k)).__name__ for k in loaded}
         print(f"[{arm}] wrote golden; function kinds: {kinds}")

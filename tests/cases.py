@@ -190,6 +190,25 @@ def sliding_inputs(case, count=N_GOLDEN):
             np.ascontiguousarray(ta) if case.get("ta") else None)
 
 
+# InverseKinematics(robot_config, **init).generate_path(position, target_position, **path)  (SURVEY.md S8f#3);
+# positions = states()[0], targets = ik_targets(); short horizons keep the fixtures small
+IK_CASES = {
+    "ur5_ik_m3": dict(arm="ur5", path=dict(n_timesteps=24, dt=0.05, method=3)),
+    "ur5_ik_m2": dict(arm="ur5", path=dict(n_timesteps=24, dt=0.05, method=2)),
+    "ur5_ik_m1": dict(arm="ur5", path=dict(n_timesteps=24, dt=0.02, method=1)),
+    "ur5_ik_default_dt": dict(arm="ur5", init=dict(max_dx=0.5, max_dr=1.0, max_dq=2.0), path=dict(n_timesteps=16, method=3)),
+    "jaco2_ik_m3": dict(arm="jaco2", path=dict(n_timesteps=24, dt=0.05, method=3)),
+}
+N_IK = 12  # trajectories per IK case
+
+
+def ik_targets(arm, count=N_IK):
+    """task-space targets inside the arm's reach: xyz in a box, Euler angles in (-pi, pi)"""
+    rng = np.random.default_rng(hash_name(arm) + 29)
+    xyz = rng.uniform(-0.45, 0.45, (count, 3)) + np.array([0.0, 0.0, 0.45])
+    return np.hstack([xyz, rng.uniform(-np.pi, np.pi, (count, 3))])
+
+
 def joint_targets(arm, count=N_GOLDEN):
     n = ARMS[arm]["n"]
     rng = np.random.default_rng(hash_name(arm) + 17)

@@ -169,6 +169,30 @@ void sliding_loop(const ChainHost &h, double kd, double lamb, int cartesian, int
 }
 
 template <typename T, int N, bool ORTHO>
+void ik_loop(const ChainHost &h, double max_dx, double max_dr, double max_dq, int method, double dt, int steps,
+             const double *position, const double *target, int64_t B, double *pos_path, double *vel_path) {
+  ChainK<T, N> P;
+  fill_chain<T, N>(h, P);
+  for (int64_t b = 0; b < B; ++b) {
+    T q[N], dq[N], tg[3], Qd[4];
+    for (int k = 0; k < N; ++k) q[k] = T(position[b * N + k]);
+    for (int c = 0; c < 3; ++c) tg[c] = T(target[b * 6 + c]);
+    quat_from_euler_sxyz(T(target[b * 6 + 3]), T(target[b * 6 + 4]), T(target[b * 6 + 5]), Qd);
+    const T nq = T(1) / sqrt_t(Qd[0] * Qd[0] + Qd[1] * Qd[1] + Qd[2] * Qd[2] + Qd[3] * Qd[3]);
+    for (int i = 0; i < 4; ++i) Qd[i] *= nq;
+    for (int t = 0; t < steps; ++t) {
+      Kin<T, N, ORTHO> K;
+      ik_step<T, N>(P, T(max_dx * dt), T(max_dr * dt), T(max_dq * dt), method, q, tg, Qd, dq, K);
+      for (int k = 0; k < N; ++k) {
+        pos_path[((int64_t)t * B + b) * N + k] = double(q[k]);  // (steps, B, n) like the kernel
+        vel_path[((int64_t)t * B + b) * N + k] = double(dq[k]);
+        q[k] += dq[k];
+      }
+    }
+  }
+}
+
+template <typename T, int N, bool ORTHO>
 void ctrl_loop(const ChainHost &h, int kind, double kp, double kv, int fa, int fb, const double *q, const double *dq,
                const double *target, const double *tv, int64_t B, double *u) {
   ChainK<T, N> P;
@@ -277,6 +301,16 @@ int hs_sliding(const abrb_chain_desc *d, int f32, int force_general, double kd, 
   if (!chain_from_desc(*d, h).empty()) return ABRB_EINVAL;
   const bool ortho = h.ortho && !force_general;
   DISPATCH_N(sliding_loop, h, kd, lamb, cartesian, frame, xoff, q, dq, target, tv, ta, B, u, s);
+  return 0;
+}
+
+int hs_ik(const abrb_chain_desc *d, int f32, int force_general, double max_dx, double max_dr, double max_dq, int method,
+          double dt, int steps, const double *position, const double *target, int64_t B, double *pos_path,
+          double *vel_path) {
+  ChainHost h;
+  if (!chain_from_desc(*d, h).empty()) return ABRB_EINVAL;
+  const bool ortho = h.ortho && !force_general;
+  DISPATCH_N(ik_loop, h, max_dx, max_dr, max_dq, method, dt, steps, position, target, B, pos_path, vel_path);
   return 0;
 }
 

@@ -198,6 +198,35 @@ def test_sliding_vs_reference_golden(name):
     assert ud.is_cuda and ud.shape == ref.shape and ctrl.s.is_cuda
 
 
+@pytest.mark.parametrize("name", list(cases.IK_CASES))
+def test_inverse_kinematics_paths_vs_reference_golden(name):
+    import torch
+
+    from abr_control_b200.controllers.path_planners import InverseKinematics
+
+    cs = cases.IK_CASES[name]
+    o = np.load(f"{GOLD}/{cs['arm']}_ik.npz")
+    position, target = o["position"], o["target"]
+    ref_p, ref_v = o[f"{name}__pos64"], o[f"{name}__vel64"]
+    vs = np.abs(ref_v).max()
+    # fp64: the iteration is contracting, errors do not grow over the horizon; fp32 drifts by rounding per step
+    for dtype, tol in ((np.float64, 1e-8), (np.float32, 2e-2)):
+        ik = InverseKinematics(_cfg(cs["arm"], dtype=dtype), **cs.get("init", {}))
+        pos, vel = ik.generate_path(position.astype(dtype), target.astype(dtype), **cs["path"])
+        assert pos.shape == ref_p.shape and pos.dtype == dtype
+        assert np.abs(vel - ref_v).max() < tol * vs, (name, dtype)
+        assert np.abs(pos - ref_p).max() < tol * max(1.0, vs * ref_p.shape[1])
+    ik = InverseKinematics(_cfg(cs["arm"]), **cs.get("init", {}))
+    one_p, one_v = ik.generate_path(position[0], target[0], **cs["path"])  # the reference's single-path contract
+    assert one_p.shape == ref_p[0].shape and np.abs(one_p - ref_p[0]).max() < 1e-8
+    assert np.abs(one_v - ref_v[0]).max() < 1e-8 * vs
+    p0, _ = ik.next()
+    assert np.array_equal(p0, one_p[0]) and ik.n == 1
+    dp, dv = ik.generate_path(torch.as_tensor(position, device="cuda"), torch.as_tensor(target[0], device="cuda"),
+                              **cs["path"])  # CUDA tensors, one broadcast target
+    assert dp.is_cuda and tuple(dp.shape) == ref_p.shape and bool(torch.isfinite(dv).all())
+
+
 @pytest.mark.parametrize("name", list(cases.CTRL_CASES))
 def test_joint_and_floating_vs_reference_golden(name):
     import torch

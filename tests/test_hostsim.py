@@ -165,6 +165,29 @@ def test_sliding_math_vs_oracle(hostsim, name):
         assert np.max(np.abs(s - ref_s) / np.abs(ref_s).max(axis=1, keepdims=True)) < tol
 
 
+@pytest.mark.parametrize("name", list(cases.IK_CASES))
+def test_ik_math_vs_oracle(hostsim, name):
+    from oracle import ik_oracle
+
+    cs = cases.IK_CASES[name]
+    q = np.ascontiguousarray(cases.states(cs["arm"], cases.N_IK)[0])
+    tg = np.ascontiguousarray(cases.ik_targets(cs["arm"]))
+    ref_p, ref_v = ik_oracle.run_ik_case(cs, q, tg)
+    cd = _abi.chain_desc_from_dict(_abi.load_arm_json(cs["arm"]))
+    n, B = cd.n_joints, len(q)
+    init, path = cs.get("init", {}), cs["path"]
+    steps = path["n_timesteps"]
+    pp, vv = np.zeros((steps, B, n)), np.zeros((steps, B, n))
+    rc = hostsim.hs_ik(C.byref(cd), 0, 0, C.c_double(init.get("max_dx", 0.2)), C.c_double(init.get("max_dr", 2 * np.pi)),
+                       C.c_double(init.get("max_dq", np.pi)), path.get("method", 3), C.c_double(path.get("dt", 0.001)),
+                       steps, P(q), P(tg), C.c_int64(B), P(pp), P(vv))
+    assert rc == 0
+    pp, vv = pp.transpose(1, 0, 2), vv.transpose(1, 0, 2)
+    vs = np.abs(ref_v).max()
+    assert np.abs(vv - ref_v).max() < 1e-8 * vs, name
+    assert np.abs(pp - ref_p).max() < 1e-8
+
+
 def test_singular_states_pinv_branch(hostsim):
     """rank-deficient J M^-1 J^T -> the reference's pinv(rcond=1e-4) branch (osc.py:143-145), incl. truncation."""
     for arm, qs in (("twojoint", [[0.3, 0.0], [1.0, np.pi], [2.0, 1e-9]]),
