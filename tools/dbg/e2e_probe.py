@@ -16,15 +16,8 @@ dev = torch.device("cuda", 0)
 rc = ur5.Config()
 c = OSC(rc, **bench.OSC_KW)
 c.record_training_signal = False
-from abr_control_b200._numa import gpu_local_cpus
-import contextlib
-ctx = gpu_local_cpus(0, getattr(torch.cuda.get_device_properties(0), "uuid", None)) if os.environ.get("PROBE_LOCAL") else contextlib.nullcontext()
-print("affinity before", len(os.sched_getaffinity(0)))
-with ctx:
-    print("affinity inside", len(os.sched_getaffinity(0)), sorted(os.sched_getaffinity(0))[:4])
-    hq, hdq, htg = (torch.as_tensor(a).pin_memory() for a in bench.synth(B, n, 77))
-    hu = torch.empty((B, n), dtype=torch.float64).pin_memory()
-    hu.zero_()
+hq, hdq, htg = (torch.as_tensor(a).pin_memory() for a in bench.synth(B, n, 77))
+hu = torch.empty((B, n), dtype=torch.float64).pin_memory()
 nq, ndq, ntg = hq.numpy(), hdq.numpy(), htg.numpy()
 dq_, ddq_, dtg_ = (torch.empty_like(t, device=dev) for t in (hq, hdq, htg))
 du = torch.empty((B, n), dtype=torch.float64, device=dev)
