@@ -77,9 +77,28 @@ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 struct Workspace {
   void *ptr = nullptr;
   size_t cap = 0;
+  int dev = -1;
   cudaStream_t stream = nullptr;
   cudaStream_t lanes[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of the *_host OSC call
   int ensure(size_t bytes) {
+    int cur = 0;
+    cudaError_t ed = cudaGetDevice(&cur);
+    if (ed != cudaSuccess) return (int)ed;
+    if (dev != cur) {  // the calling thread switched devices: streams and memory belong to the device they were made on
+      if (dev >= 0) {
+        cudaSetDevice(dev);
+        cudaFree(ptr);
+        if (stream) cudaStreamDestroy(stream);
+        for (auto &l : lanes)
+          if (l) cudaStreamDestroy(l);
+        cudaSetDevice(cur);
+      }
+      ptr = nullptr;
+      cap = 0;
+      stream = nullptr;
+      for (auto &l : lanes) l = nullptr;
+      dev = cur;
+    }
     if (stream == nullptr) {
       cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
       if (e != cudaSuccess) return (int)e;
@@ -101,6 +120,13 @@ struct Workspace {
 thread_local Workspace g_ws;
 
 size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+// a cudaMemcpyAsync that is rejected (bad pointer, wrong direction) fails at the call, NOT at the later synchronise
+#define ABRB_CU(call, where)                                \
+  do {                                                      \
+    cudaError_t e_ = (call);                                \
+    if (e_ != cudaSuccess) return cuda_fail((int)e_, where); \
+  } while (0)
 
 }  // namespace
 
@@ -210,15 +236,17 @@ static int rbd_eval_host(const abrb_model *m, int frame_id, const double *x_off,
   auto take = [&](size_t bytes) { char *p = base + off; off += align_up(bytes); return (void *)p; };
   void *dq_q = take((size_t)B * n * es), *dq_dq = take((size_t)B * n * es);
   cudaStream_t s = g_ws.stream;
-  cudaMemcpyAsync(dq_q, q, (size_t)B * n * es, cudaMemcpyHostToDevice, s);
-  if (dq) cudaMemcpyAsync(dq_dq, dq, (size_t)B * n * es, cudaMemcpyHostToDevice, s);
+  ABRB_CU(cudaMemcpyAsync(dq_q, q, (size_t)B * n * es, cudaMemcpyHostToDevice, s), "abrb_rbd_eval_host(q)");
+  if (dq) ABRB_CU(cudaMemcpyAsync(dq_dq, dq, (size_t)B * n * es, cudaMemcpyHostToDevice, s), "abrb_rbd_eval_host(dq)");
   void *dev_out[10];
   for (int i = 0; i < 10; ++i) dev_out[i] = host_out[i] ? take((size_t)B * len[i] * es) : nullptr;
   abrb_rbd_out d{dev_out[0], dev_out[1], dev_out[2], dev_out[3], dev_out[4], dev_out[5], dev_out[6], dev_out[7], dev_out[8], dev_out[9]};
   rc = rbd_eval(m, frame_id, x_off, dq_q, dq ? dq_dq : nullptr, B, &d, s, f32);
   if (rc) return rc;
   for (int i = 0; i < 10; ++i)
-    if (host_out[i]) cudaMemcpyAsync(host_out[i], dev_out[i], (size_t)B * len[i] * es, cudaMemcpyDeviceToHost, s);
+    if (host_out[i])
+      ABRB_CU(cudaMemcpyAsync(host_out[i], dev_out[i], (size_t)B * len[i] * es, cudaMemcpyDeviceToHost, s),
+              "abrb_rbd_eval_host(result)");
   cudaError_t ce = cudaStreamSynchronize(s);
   return ce ? cuda_fail(ce, "abrb_rbd_eval_host") : ABRB_OK;
 }
@@ -382,8 +410,10 @@ static int osc_generate_host(const abrb_osc *c, int frame_id, const double *x_of
   if (chunk_env > 0) chunk = (chunk_env < B ? chunk_env : B + 127) / 128 * 128;
   if (chunk <= 0) chunk = B;
   cudaError_t ce = cudaSuccess;
-  if (!target_stride) cudaMemcpyAsync(d_t, target, sz_t, cudaMemcpyHostToDevice, g_ws.stream);
-  if (tv && !tv_stride) cudaMemcpyAsync(d_tv, tv, sz_tv, cudaMemcpyHostToDevice, g_ws.stream);
+  if (!target_stride)
+    ABRB_CU(cudaMemcpyAsync(d_t, target, sz_t, cudaMemcpyHostToDevice, g_ws.stream), "abrb_osc_generate_host(target)");
+  if (tv && !tv_stride)
+    ABRB_CU(cudaMemcpyAsync(d_tv, tv, sz_tv, cudaMemcpyHostToDevice, g_ws.stream), "abrb_osc_generate_host(target_velocity)");
   if (!target_stride || (tv && !tv_stride)) {  // broadcast rows must be resident before any lane starts
     ce = cudaStreamSynchronize(g_ws.stream);
     if (ce) return cuda_fail(ce, "abrb_osc_generate_host");
@@ -395,16 +425,22 @@ static int osc_generate_host(const abrb_osc *c, int frame_id, const double *x_of
     const size_t off_s = (size_t)b0 * row, off_t = (size_t)b0 * 6 * es;
     auto at = [](const void *p, size_t o) { return (const void *)((const char *)p + o); };
     auto atw = [](void *p, size_t o) { return (void *)((char *)p + o); };
-    cudaMemcpyAsync(atw(d_q, off_s), at(q, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, s);
-    cudaMemcpyAsync(atw(d_dq, off_s), at(dq, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, s);
-    if (target_stride) cudaMemcpyAsync(atw(d_t, off_t), at(target, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s);
-    if (tv && tv_stride) cudaMemcpyAsync(atw(d_tv, off_t), at(tv, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s);
+    const char *where = "abrb_osc_generate_host(copy in)";
+    ABRB_CU(cudaMemcpyAsync(atw(d_q, off_s), at(q, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, s), where);
+    ABRB_CU(cudaMemcpyAsync(atw(d_dq, off_s), at(dq, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, s), where);
+    if (target_stride)
+      ABRB_CU(cudaMemcpyAsync(atw(d_t, off_t), at(target, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s), where);
+    if (tv && tv_stride)
+      ABRB_CU(cudaMemcpyAsync(atw(d_tv, off_t), at(tv, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s), where);
     rc = osc_generate(c, frame_id, x_off, at(d_q, off_s), at(d_dq, off_s), target_stride ? at(d_t, off_t) : d_t,
                       target_stride, tv ? (tv_stride ? at(d_tv, off_t) : d_tv) : nullptr, tv_stride, atw(d_u, off_s),
                       train ? atw(d_tr, off_s) : nullptr, nb, s, f32);
     if (rc) return rc;
-    cudaMemcpyAsync(atw(u, off_s), at(d_u, off_s), (size_t)nb * row, cudaMemcpyDeviceToHost, s);
-    if (train) cudaMemcpyAsync(atw(train, off_s), at(d_tr, off_s), (size_t)nb * row, cudaMemcpyDeviceToHost, s);
+    ABRB_CU(cudaMemcpyAsync(atw(u, off_s), at(d_u, off_s), (size_t)nb * row, cudaMemcpyDeviceToHost, s),
+            "abrb_osc_generate_host(result)");
+    if (train)
+      ABRB_CU(cudaMemcpyAsync(atw(train, off_s), at(d_tr, off_s), (size_t)nb * row, cudaMemcpyDeviceToHost, s),
+              "abrb_osc_generate_host(training signal)");
   }
   const int used = (int)((B + chunk - 1) / chunk) < 3 ? (int)((B + chunk - 1) / chunk) : 3;
   for (int l = 0; l < used; ++l) {
