@@ -47,3 +47,11 @@ for name, dt in (("f64", np.float64), ("f32", np.float32)):
     u3 = torch.empty((262144, 6), dtype=tdt, device=dev)
     res[f"jaco2_cfg3_B262144_{name}"] = bench.time_kernel(lambda s: c3.generate_into(s[0], s[1], s[2], u3), 50, torch, S3) * 1e6
 print(os.environ.get("ABRB_LIBRARY", "default"), json.dumps({k: round(v, 1) for k, v in res.items()}))
+if os.environ.get("KB_CLOCKS"):
+    # SM clock / throttle reasons over a sustained run of the heaviest kernel (is a long FP64 burst power capped?)
+    S = sets(np.float64)
+    c = OSC(ur5.Config(), kp=10.0, ctrlr_dof=[True] * 6, use_C=True)
+    u = torch.empty((B, n), dtype=torch.float64, device=dev)
+    sampler = bench.ClockSampler(0, getattr(torch.cuda.get_device_properties(0), "uuid", None))
+    dt = bench.time_kernel(lambda s: c.generate_into(s[0], s[1], s[2], u), int(os.environ.get("KB_CLOCKS")), torch, S)
+    print("clocks", json.dumps(dict(us_per_launch=round(dt * 1e6, 1), **sampler.stop())))
