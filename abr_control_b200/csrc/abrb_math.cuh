@@ -44,6 +44,43 @@ ABRB_HD void sincos_t(double x, double *s, double *c) { ::sincos(x, s, c); }
 ABRB_HD void sincos_t(float x, float *s, float *c) { ::sincosf(x, s, c); }
 ABRB_HD double sqrt_t(double x) { return ::sqrt(x); }
 ABRB_HD float sqrt_t(float x) { return ::sqrtf(x); }
+// Reciprocal and reciprocal square root.  Default: the IEEE division / square root (a ~30-instruction sequence each in
+// double on the GPU).  ABRB_FAST_DIV=1 (experimental, not the shipped default): hardware seed (rcp/rsqrt.approx.ftz.f64,
+// ~20 bits) refined by two Newton steps to ~1 ulp; operands here are pivots and norms far from the subnormal range.
+#ifndef ABRB_FAST_DIV
+#define ABRB_FAST_DIV 0
+#endif
+ABRB_HD float inv_t(float x) { return 1.0f / x; }
+ABRB_HD float inv_sqrt_t(float x) { return 1.0f / ::sqrtf(x); }
+#if ABRB_FAST_DIV
+ABRB_HD double inv_t(double x) {
+  double r;
+#ifdef __CUDA_ARCH__
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#else
+  const double ax = ::fabs(x);
+  if (!(ax > 1e-30 && ax < 1e30)) return 1.0 / x;
+  r = (double)(1.0f / (float)x);  // host stand-in for the hardware seed (tests/hostsim)
+#endif
+  r = ::fma(r, ::fma(-x, r, 1.0), r);
+  return ::fma(r, ::fma(-x, r, 1.0), r);
+}
+ABRB_HD double inv_sqrt_t(double x) {
+  double y;
+#ifdef __CUDA_ARCH__
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+  if (!(x > 1e-30 && x < 1e30)) return 1.0 / ::sqrt(x);
+  y = (double)(1.0f / ::sqrtf((float)x));
+#endif
+  const double hx = 0.5 * x;
+  y = ::fma(y, ::fma(-hx * y, y, 0.5), y);
+  return ::fma(y, ::fma(-hx * y, y, 0.5), y);
+}
+#else
+ABRB_HD double inv_t(double x) { return 1.0 / x; }
+ABRB_HD double inv_sqrt_t(double x) { return 1.0 / ::sqrt(x); }
+#endif
 ABRB_HD double abs_t(double x) { return ::fabs(x); }
 ABRB_HD float abs_t(float x) { return ::fabsf(x); }
 ABRB_HD double fmod_t(double x, double y) { return ::fmod(x, y); }
@@ -839,7 +876,11 @@ ABRB_HD void quat_from_R(const T *m, T *qo) {
     T w[4];
     ABRB_UNROLL
     for (int r = 0; r < 4; ++r) w[r] = Kp[r][0] * v[0] + Kp[r][1] * v[1] + Kp[r][2] * v[2] + Kp[r][3] * v[3];
+#if ABRB_FAST_DIV
+    const T inv = inv_sqrt_t(w[0] * w[0] + w[1] * w[1] + w[2] * w[2] + w[3] * w[3]);
+#else
     const T inv = T(1) / sqrt_t(w[0] * w[0] + w[1] * w[1] + w[2] * w[2] + w[3] * w[3]);
+#endif
     ABRB_UNROLL
     for (int r = 0; r < 4; ++r) v[r] = w[r] * inv;
   }
@@ -993,9 +1034,16 @@ ABRB_HD bool chol(T (*A)[S_], T *invd) {  // invd[j] = 1 / L[j][j] (the solves m
     for (int k = 0; k < S_; ++k)
       if (k < j) d -= A[j][k] * A[j][k];
     ok = ok && (d > T(0));
+#if ABRB_FAST_DIV
+    const T dpos = d > T(0) ? d : T(1);
+    const T inv = inv_sqrt_t(dpos);
+    const T ljj = dpos * inv;
+    A[j][j] = ljj;
+#else
     const T ljj = sqrt_t(d > T(0) ? d : T(1));
     A[j][j] = ljj;
     const T inv = T(1) / ljj;
+#endif
     invd[j] = inv;
     ABRB_UNROLL
     for (int i = 0; i < S_; ++i) {
@@ -1147,7 +1195,11 @@ ABRB_HD int inertia_below(const T (*Sm)[S_], T sigma) {  // #eigenvalues of Sm b
     const T d = D[j][j];
     bad = bad || !(abs_t(d) > T(0));
     neg += d < T(0) ? 1 : 0;
+#if ABRB_FAST_DIV
+    const T inv = inv_t(d);
+#else
     const T inv = T(1) / d;
+#endif
     ABRB_UNROLL
     for (int i = 0; i < S_; ++i) {
       if (i > j) {
@@ -1220,7 +1272,11 @@ ABRB_HD bool pinv_solve_fast2(const T (*Sm)[S_], const T (*L)[S_], const T *invd
       nn += acc * acc;
     }
     if (!(nn > T(0))) return false;
+#if ABRB_FAST_DIV
+    const T sc = inv_sqrt_t(nn);
+#else
     const T sc = T(1) / sqrt_t(nn);
+#endif
     ABRB_UNROLL
     for (int i = 0; i < S_; ++i) v[i] = w[i] * sc;
   }
@@ -1307,7 +1363,11 @@ ABRB_HD bool pinv_solve_fast2(const T (*Sm)[S_], const T (*L)[S_], const T *invd
             T nn = T(0);
             ABRB_UNROLL
             for (int i = 0; i < S_; ++i) nn += V[j][i] * V[j][i];
+#if ABRB_FAST_DIV
+            const T sc = inv_sqrt_t(nn);
+#else
             const T sc = T(1) / sqrt_t(nn);
+#endif
             ABRB_UNROLL
             for (int i = 0; i < S_; ++i) V[j][i] *= sc;
           }
