@@ -382,7 +382,25 @@ ABRB_HD bool osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
   ABRB_UNROLL
   for (int a = 0; a < KD; ++a) det *= Sc[a][a] * Sc[a][a];
   fast = pd && (det >= O.thr);
+#ifndef ABRB_CERT_PRECHECK
+#define ABRB_CERT_PRECHECK 0  // experimental (not the shipped default): 1 = skip the certificate when it cannot pass,
+#endif                        // 2 = also never try it on the 6-row path (it passed for 0 of 2 361 UR5 / Jaco2 pinv states;
+                              // the truncating route returns S^-1 y itself when nothing is truncated)
+#if ABRB_CERT_PRECHECK
+  bool try_cert = pd && !fast && !(ABRB_CERT_PRECHECK >= 2 && KD == 6);
+  if (try_cert) {
+    // (S^-1)_aa >= 1 / L_aa^2, so ||S^-1||_F >= max_a 1/L_aa^2: if already that bound breaks the inequality below,
+    // the six solves are pointless (always the case for the UR5 states that get here)
+    T big = T(0);
+    ABRB_UNROLL
+    for (int a = 0; a < KD; ++a)
+      if (((O.dof_mask >> a) & 1u) && Si[a] * Si[a] > big) big = Si[a] * Si[a];
+    try_cert = rcond * trS * big < T(1);
+  }
+  if (try_cert) {
+#else
   if (pd && !fast) {
+#endif
     // pinv == inv whenever no eigenvalue is truncated; certify that cheaply:
     // lambda_max <= trace(S_active), 1/lambda_min <= ||S^-1||_F  =>  no truncation if 1/||S^-1||_F > rcond*trace
     const T tr = trS;
