@@ -218,9 +218,13 @@ void ctrl_loop(const ChainHost &h, int kind, double kp, double kv, int fa, int f
 
 #define DISPATCH_N(FN, ...)                                       \
   switch (h.n) {                                                  \
+    case 1: DISPATCH_T(FN, 1, __VA_ARGS__); break;                \
     case 2: DISPATCH_T(FN, 2, __VA_ARGS__); break;                \
     case 3: DISPATCH_T(FN, 3, __VA_ARGS__); break;                \
+    case 4: DISPATCH_T(FN, 4, __VA_ARGS__); break;                \
+    case 5: DISPATCH_T(FN, 5, __VA_ARGS__); break;                \
     case 6: DISPATCH_T(FN, 6, __VA_ARGS__); break;                \
+    case 7: DISPATCH_T(FN, 7, __VA_ARGS__); break;                \
     default: return ABRB_ESHAPE;                                  \
   }
 #define DISPATCH_T(FN, N, ...)                                    \
