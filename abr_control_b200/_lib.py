@@ -25,8 +25,8 @@ class AbrbError(RuntimeError):
 
 # every symbol include/abrb.h declares: name -> (restype, argtypes)
 _VP, _I, _I64, _D, _CP = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_char_p
-_gen = [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _VP, _I64]
-_roll = [_VP, _I, _VP, _VP, _VP, _VP, _I, _I, _D, _VP, _VP, _VP, _I64, _VP]
+_gen = [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _VP, _VP, _I64]  # ... u, training_signal, integrated_error, B
+_roll = [_VP, _I, _VP, _VP, _VP, _VP, _I, _I, _D, _VP, _VP, _VP, _VP, _I64, _VP]
 SIGNATURES = {
     "abrb_version": (_I, []),
     "abrb_last_error": (_CP, []),
@@ -47,6 +47,18 @@ SIGNATURES = {
     "abrb_osc_generate_f32": (_I, _gen + [_VP]),
     "abrb_osc_generate_host_f64": (_I, _gen),
     "abrb_osc_generate_host_f32": (_I, _gen),
+    "abrb_osc_generate_host_async_f64": (_I, _gen + [_I]),
+    "abrb_osc_generate_host_async_f32": (_I, _gen + [_I]),
+    "abrb_osc_host_wait": (_I, [_VP, _I]),
+    "abrb_gather_create": (_I, [_I, _I, _I64, _I, C.POINTER(_VP)]),
+    "abrb_gather_destroy": (_I, [_VP]),
+    "abrb_gather_export": (_I, [_VP, C.c_char_p]),
+    "abrb_gather_import": (_I, [_VP, _I, C.c_char_p]),
+    "abrb_gather_buffer": (_VP, [_VP, _I]),
+    "abrb_gather_wait": (_I, [_VP, _VP]),
+    "abrb_gather_status": (_I, [_VP]),
+    "abrb_osc_generate_gather_f64": (_I, _gen + [_VP, _I, _I64, _VP]),
+    "abrb_osc_generate_gather_f32": (_I, _gen + [_VP, _I, _I64, _VP]),
     "abrb_null_generate_f64": (_I, [_VP, C.POINTER(_abi.NullParams), _VP, _VP, _VP, _I64, _VP]),
     "abrb_null_generate_f32": (_I, [_VP, C.POINTER(_abi.NullParams), _VP, _VP, _VP, _I64, _VP]),
     "abrb_joint_generate_f64": (_I, [_VP, _D, _D, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I64, _VP]),

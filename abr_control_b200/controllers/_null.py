@@ -1,5 +1,6 @@
 """Common part of the secondary ("null space") controllers: standalone batched ``generate(q, dq)``."""
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -11,14 +12,21 @@ from .controller import Controller
 class NullController(Controller):
     def __init__(self, robot_config):
         super().__init__(robot_config)
-        self._owners = []  # OSC instances that embedded our parameters
+        self._owners = weakref.WeakSet()  # OSC instances that embedded our parameters (weak: they may die first)
 
     def _params(self):
         raise NotImplementedError
 
     def _dirty(self):
-        for o in self._owners:
+        for o in list(self._owners):
             o._invalidate()
+
+    def __setattr__(self, name, value):
+        # the reference reads a secondary controller's attributes on every call; an OSC that embedded them in its
+        # native handle has to rebuild it when one changes (damping.kv = ..., avoid.obstacles = ...)
+        object.__setattr__(self, name, value)
+        if not name.startswith("_") and name != "robot_config" and "_owners" in self.__dict__:
+            self._dirty()
 
     def generate(self, q, dq):
         """(n,) -> (n,) float64;  (B,n) -> (B,n) (NumPy in/out or CUDA tensor in/out)."""

@@ -153,7 +153,6 @@ inline void fill_null(const abrb_null_params &z, NullK<T, N> &Z) {
 }
 
 inline std::string check_osc(int n, const abrb_osc_params &p) {
-  if (p.ki != 0.0) return "ki != 0 (integrated error state) is not supported";
   if (p.orientation_algorithm != 0 && p.orientation_algorithm != 1)
     return "Invalid algorithm number for calculating orientation error";
   if (p.n_null < 0 || p.n_null > ABRB_MAX_NULL) return "n_null out of range";
@@ -170,6 +169,7 @@ inline void fill_osc(const abrb_osc_params &p, int frame, const double *x_off, O
   O.kp = T(p.kp);
   O.ko = T(p.ko);
   O.kv = T(p.kv);
+  O.ki = T(p.ki);
   // sat_gain / scale (identical expressions in the reference, osc.py:112-115), evaluated in double
   O.lim_xyz = p.use_vmax ? T(p.vmax[0] / p.kp * p.kv) : T(0);
   O.lim_abg = p.use_vmax ? T(p.vmax[1] / p.ko * p.kv) : T(0);

@@ -16,6 +16,19 @@ struct RbdCall {
   cudaStream_t stream;
 };
 
+// Fused all-gather of the control outputs over NVLink peer memory (BASELINE config 5): the OSC kernel's epilogue stores
+// every rank's rows straight into the gathered (B_total, n) array of EVERY rank (buffers mapped with CUDA IPC), so the
+// exchange overlaps the arithmetic tile by tile instead of following it as a separate collective.
+constexpr int kMaxPeers = 8;
+struct GatherArgs {
+  void *peer_u[kMaxPeers];                  // base of the gathered array on each rank (own rank included)
+  unsigned long long *peer_flag[kMaxPeers]; // &flags[my_rank] on each rank: receives `epoch` when all my rows are there
+  int n_peer = 0;
+  int64_t row0 = 0;                         // first row of this rank's block in the gathered array
+  unsigned long long epoch = 0;
+  unsigned *cta_counter = nullptr;          // local: CTAs of this launch that have finished
+};
+
 struct OscCall {
   int frame;
   const double *xoff;
@@ -25,15 +38,9 @@ struct OscCall {
   int64_t B;
   bool f32;
   cudaStream_t stream;
-  // two-launch mode (6-row path only): queue = 4 + B ints with [0..3] zero; records = osc_record_len(n) * rec_stride
-  // values of the compute type, rec_stride >= B
-  int *queue = nullptr;
-  void *records = nullptr;
-  int64_t rec_stride = 0;
+  void *ierr = nullptr;  // (B, 6) integrated task-space error, in/out (device), only with ki != 0
+  const GatherArgs *gather = nullptr;
 };
-
-// values per deferred state (OscRecord<N, 6>::kLen in abrb_osc.cuh)
-inline int osc_record_len(int n) { return 12 + 4 * n + n * (n + 1) / 2 + n + 6 * n; }
 
 struct RolloutCall {
   int frame;
@@ -47,6 +54,7 @@ struct RolloutCall {
   int64_t B;
   bool f32;
   cudaStream_t stream;
+  void *ierr = nullptr;  // (B, 6) integrated task-space error, in/out (device), only with ki != 0
 };
 
 struct NullCall {

@@ -119,6 +119,7 @@ ABRB_HD int frame_dep(int frame) {  // number of joints the frame moves with == 
 // what the fp64 kernels use to stay under the register limit without spilling to local memory.
 template <typename T, int COUNT>
 struct RegStore {
+  static constexpr bool kShared = false;
   T v[COUNT];
   ABRB_HD T ld(int i) const { return v[i]; }
   ABRB_HD void st(int i, T x) { v[i] = x; }
@@ -126,6 +127,7 @@ struct RegStore {
 };
 template <typename T, int COUNT>
 struct StridedStore {
+  static constexpr bool kShared = true;
   T *base;
   int stride;
   ABRB_HD T ld(int i) const { return base[i * stride]; }
@@ -152,6 +154,7 @@ struct Kin {
   static constexpr int kN = N;
   static constexpr bool kOrtho = ORTHO_;
   typedef KinSlots<N, ORTHO_> S;
+  static constexpr bool kSharedScratch = Store<T, S::kCount>::kShared;
   Store<T, S::kCount> s;
   T F[12];  // the requested frame
   ABRB_HD void ld3(int slot, T *o) const {
@@ -165,6 +168,8 @@ struct Kin {
     s.st(slot + 2, v[2]);
   }
   ABRB_HD void sync() const { s.sync(); }
+  // slot of element (r, k) of the task-space matrices that osc_eval writes over t_k / z_k (J, then A = (L^-1 J^T)^T)
+  static ABRB_HD int aslot(int r, int k) { return r < 3 ? S::kT + 3 * k + r : S::kZ + 3 * k + (r - 3); }
   ABRB_HD void t(int k, T *o) const { ld3(S::kT + 3 * k, o); }
   ABRB_HD void z(int k, T *o) const { ld3(S::kZ + 3 * k, o); }
   ABRB_HD void pl(int l, T *o) const { ld3(S::kPl + 3 * l, o); }
@@ -1163,294 +1168,110 @@ ABRB_HD_NOINLINE void pinv_apply_sym(const T *Sin, unsigned active, T rcond, con
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fast route to x = pinv(S, rcond) y for a symmetric positive definite (possibly very ill-conditioned) S whose
-// Cholesky factor L (with reciprocal diagonal invd) is already known.  numpy.linalg.pinv drops the eigenvalues
-// <= rcond * lambda_max; instead of a full eigen-decomposition this
-//   1. brackets lambda_max: Rayleigh quotient rho after power iteration with (S/tr)^8 (a lower bound) and an
-//      inertia count (LDL^T of S - sigma I, Sylvester's law) proving that no eigenvalue exceeds rho (1 + delta);
-//   2. counts the eigenvalues below the cutoff with the same inertia count at both ends of the bracket;
-//   3. finds the (at most 2) truncated eigenvectors by inverse subspace iteration with L and projects them out:
-//      x = P S^-1 P y,  P = I - V V^T.
-// Returns false whenever a step is inconclusive (more than 2 truncated eigenvalues, slow convergence, a vanishing
-// pivot, the bracket straddling an eigenvalue): the caller then falls back to the Jacobi routine above.
-// Rows not in `active` must be decoupled from the rest (zero off-diagonals) with a diagonal >= lambda_max, and
-// y must vanish on them.  Everything is unrolled on registers (about 1.5 k flops): this is what keeps the
-// "second pass" over the deferred states of a tile short.
-// (This cold path is executed by a few warps only, so its instructions are never resident in the instruction
-// caches and fetching them costs as much as executing them: repeated steps are therefore written as ROLLED loops
-// around bodies with static register indices — one copy of the squaring, of the inertia count and of the solve —
-// which keeps the footprint small without sending the matrices to local memory, as a real call would (measured).)
-template <typename T, int S_>
-ABRB_HD int inertia_below(const T (*Sm)[S_], T sigma) {  // #eigenvalues of Sm below sigma, -1 if inconclusive
-  T D[S_][S_];
-  ABRB_UNROLL
-  for (int i = 0; i < S_; ++i)
-    ABRB_UNROLL
-  for (int j = 0; j < S_; ++j)
-    if (j >= i) D[i][j] = Sm[i][j] - (i == j ? sigma : T(0));
-  int neg = 0;
-  bool bad = false;
-  ABRB_UNROLL
-  for (int j = 0; j < S_; ++j) {
-    const T d = D[j][j];
-    bad = bad || !(abs_t(d) > T(0));
-    neg += d < T(0) ? 1 : 0;
-#if ABRB_FAST_DIV
-    const T inv = inv_t(d);
-#else
-    const T inv = T(1) / d;
-#endif
-    ABRB_UNROLL
-    for (int i = 0; i < S_; ++i) {
-      if (i > j) {
-        const T f = D[j][i] * inv;  // symmetric: use the upper triangle only
-        ABRB_UNROLL
-        for (int k = 0; k < S_; ++k)
-          if (k >= i) D[i][k] -= f * D[j][k];
-      }
-    }
-  }
-  return bad ? -1 : neg;
+// x = pinv(A A^T, rcond) y for a KD x N matrix A (the rows of L^-1 J^T, so that A A^T = J M^-1 J^T), the route taken
+// by OSC._Mx when |det| is below its threshold (/root/reference/abr_control/controllers/osc.py:138-145).
+// numpy.linalg.pinv drops the singular values <= rcond * largest; for the symmetric positive semi-definite A A^T
+// they are its eigenvalues, i.e. the SQUARED singular values of A.  A one-sided (Hestenes) Jacobi SVD of the rows
+// of A finds them without ever forming A A^T (whose eigenvalue ratios reach 1e-16 here): pairs of rows are rotated
+// until all rows are mutually orthogonal, B = V A, B B^T = diag(s2), and then
+//   pinv(A A^T) y = sum_{i: s2_i > rcond * max s2} V_i^T (V_i . y) / s2_i .
+// The pairs of one round (round-robin tournament schedule) are disjoint, so a round is ONE parallel step: on the GPU
+// each row lives in its own lane of an 8-lane group of the warp and the partners exchange rows with shuffles
+// (abrb_coop.cuh); the host instantiation (tests/hostsim) walks the same schedule sequentially.  Both use the
+// per-row step below, so the arithmetic is the same.
+template <int N, int KD>
+struct JacobiRow {
+  double b[N];   // the (rotated) row of A
+  double v[KD];  // its row of the accumulated rotations V
+};
+
+// Partner of player i in round r of a round-robin tournament of n (even) players, r = 0 .. n-2: player n-1 stays,
+// the others move around a circle (i + j = 2 r mod n-1).
+ABRB_HD int rr_partner(int n, int i, int r) {
+  if (i == n - 1) return r;
+  int j = 2 * r - i;
+  j = j < 0 ? j + (n - 1) : j;
+  j = j >= n - 1 ? j - (n - 1) : j;
+  return j == i ? n - 1 : j;
 }
 
-template <typename T, int S_>
-ABRB_HD void sym_square(const T (*A)[S_], T (*B)[S_]) {  // B = A A for symmetric A
+// One row's share of the rotation of a pair of rows.  `lo`: this row has the smaller index of the two.  Returns
+// 0 (already orthogonal to rounding: untouched), 1 (rotated, the cosine of the angle was below 1e-8: the quadratically
+// convergent iteration is finished by this very rotation) or 2 (rotated, not yet converged).
+template <int N, int KD>
+ABRB_HD int jacobi_pair(bool lo, JacobiRow<N, KD> &me, const JacobiRow<N, KD> &other) {
+  double mine = 0.0, theirs = 0.0, ga = 0.0;
   ABRB_UNROLL
-  for (int i = 0; i < S_; ++i)
-    ABRB_UNROLL
-  for (int j = 0; j < S_; ++j) {
-    if (j >= i) {
-      T acc = T(0);
-      ABRB_UNROLL
-      for (int k = 0; k < S_; ++k) acc += A[i][k] * A[k][j];
-      B[i][j] = acc;
-      B[j][i] = acc;
+  for (int k = 0; k < N; ++k) {
+    mine += me.b[k] * me.b[k];
+    theirs += other.b[k] * other.b[k];
+    ga += me.b[k] * other.b[k];
+  }
+  const double prod = mine * theirs, g2 = ga * ga;
+  if (!(g2 > 1e-30 * prod)) return 0;
+  // rows (lo, hi) with squared norms (al, be):  lo' = c lo - s hi,  hi' = s lo + c hi  with the rotation angle
+  //   tan 2 theta = 2 ga / d,  d = be - al  (|theta| <= pi/4).  With h = sqrt(d^2 + 4 ga^2):
+  //   cos 2 theta = |d| / h,   c^2 = (1 + |d| / h) / 2  (in [1/2, 1]),   s = sgn(d) ga / (h c)
+  // — two reciprocal square roots, no division, and no cancellation anywhere.
+  const double d = lo ? theirs - mine : mine - theirs;
+  const double r1 = inv_sqrt_t(d * d + 4.0 * g2);  // 1 / h
+  const double c2 = 0.5 + 0.5 * abs_t(d) * r1;
+  const double r2 = inv_sqrt_t(c2);                // 1 / c
+  const double c = c2 * r2;
+  const double sn = (d >= 0.0 ? ga : -ga) * r1 * r2;
+  const double sp = lo ? -sn : sn;
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) me.b[k] = c * me.b[k] + sp * other.b[k];
+  ABRB_UNROLL
+  for (int k = 0; k < KD; ++k) me.v[k] = c * me.v[k] + sp * other.v[k];
+  return g2 > 1e-16 * prod ? 2 : 1;
+}
+
+constexpr int kJacobiMaxSweeps = 24;
+
+// Sequential walk over the same schedule (host instantiation and single-state fall-backs).  A: KD x N row-major.
+template <int N, int KD>
+ABRB_HD void pinv_rows_jacobi_seq(const double *A, double rcond, const double *y, const double *z, bool two, double *xy,
+                                  double *xz) {
+  constexpr int NRR = KD + (KD & 1);
+  JacobiRow<N, KD> row[NRR], old[NRR];
+  for (int i = 0; i < NRR; ++i) {
+    for (int k = 0; k < N; ++k) row[i].b[k] = i < KD ? A[i * N + k] : 0.0;
+    for (int k = 0; k < KD; ++k) row[i].v[k] = i == k ? 1.0 : 0.0;
+  }
+  for (int sweep = 0; sweep < kJacobiMaxSweeps; ++sweep) {
+    bool big = false;
+    for (int r = 0; r < NRR - 1; ++r) {
+      for (int i = 0; i < NRR; ++i) old[i] = row[i];
+      for (int i = 0; i < NRR; ++i) {
+        const int p = rr_partner(NRR, i, r);
+        big = (jacobi_pair<N, KD>(i < p, row[i], old[p]) == 2) || big;
+      }
+    }
+    if (!big) break;
+  }
+  double s2[KD], smax = 0.0;
+  for (int i = 0; i < KD; ++i) {
+    double acc = 0.0;
+    for (int k = 0; k < N; ++k) acc += row[i].b[k] * row[i].b[k];
+    s2[i] = acc;
+    smax = acc > smax ? acc : smax;
+  }
+  for (int k = 0; k < KD; ++k) xy[k] = xz[k] = 0.0;
+  for (int i = 0; i < KD; ++i) {
+    if (!(s2[i] > rcond * smax)) continue;
+    double cy = 0.0, cz = 0.0;
+    for (int k = 0; k < KD; ++k) {
+      cy += row[i].v[k] * y[k];
+      if (two) cz += row[i].v[k] * z[k];
+    }
+    cy /= s2[i];
+    cz /= s2[i];
+    for (int k = 0; k < KD; ++k) {
+      xy[k] += row[i].v[k] * cy;
+      if (two) xz[k] += row[i].v[k] * cz;
     }
   }
 }
-
-#ifndef ABRB_PINV_BLOCKS
-#define ABRB_PINV_BLOCKS 40
-#endif
-template <typename T, int S_>
-ABRB_HD bool pinv_solve_fast2(const T (*Sm)[S_], const T (*L)[S_], const T *invd, unsigned active, T rcond,
-                              const T *y, T *x, const T *y2, T *x2, bool two) {
-  // ---- 1. lambda_max of the active block
-  T tr = T(0);
-  ABRB_UNROLL
-  for (int i = 0; i < S_; ++i) tr += ((active >> i) & 1u) ? Sm[i][i] : T(0);
-  if (!(tr > T(0))) return false;
-  const T itr = T(1) / tr;
-  T P1[S_][S_], P2[S_][S_];
-  ABRB_UNROLL
-  for (int i = 0; i < S_; ++i)
-    ABRB_UNROLL
-  for (int j = 0; j < S_; ++j) {
-    const bool on = ((active >> i) & 1u) && ((active >> j) & 1u);
-    P1[i][j] = on ? Sm[i][j] * itr : T(0);  // active block scaled to trace 1 (all powers stay <= 1)
-  }
-  ABRB_NOUNROLL
-  for (int r = 0; r < 3; ++r) {  // P2 = P1^2, P1 <- P2: after three rounds P2 = (S/tr)^8
-    sym_square<T, S_>(P1, P2);
-    ABRB_UNROLL
-    for (int i = 0; i < S_; ++i)
-      ABRB_UNROLL
-    for (int j = 0; j < S_; ++j) P1[i][j] = P2[i][j];
-  }
-  T v[S_];
-  ABRB_UNROLL
-  for (int i = 0; i < S_; ++i) v[i] = ((active >> i) & 1u) ? T(1) + T(0.37) * T(i) : T(0);
-  ABRB_NOUNROLL
-  for (int it = 0; it < 4; ++it) {
-    T w[S_], nn = T(0);
-    ABRB_UNROLL
-    for (int i = 0; i < S_; ++i) {
-      T acc = T(0);
-      ABRB_UNROLL
-      for (int j = 0; j < S_; ++j) acc += P2[i][j] * v[j];
-      w[i] = acc;
-      nn += acc * acc;
-    }
-    if (!(nn > T(0))) return false;
-#if ABRB_FAST_DIV
-    const T sc = inv_sqrt_t(nn);
-#else
-    const T sc = T(1) / sqrt_t(nn);
-#endif
-    ABRB_UNROLL
-    for (int i = 0; i < S_; ++i) v[i] = w[i] * sc;
-  }
-  T rho = T(0);
-  ABRB_UNROLL
-  for (int i = 0; i < S_; ++i) {
-    T acc = T(0);
-    ABRB_UNROLL
-    for (int j = 0; j < S_; ++j) acc += Sm[i][j] * v[j];
-    rho += v[i] * acc;  // v is unit and vanishes on inactive rows
-  }
-  // bracket [rho, rho (1 + delta)]: all eigenvalues of the active block must lie below the upper end
-  int n_act = 0;
-  ABRB_UNROLL
-  for (int i = 0; i < S_; ++i) n_act += ((active >> i) & 1u) ? 1 : 0;
-  // One rolled loop over the (at most five) thresholds: steps 0-2 look for the tightest bracket
-  // [rho, rho (1 + delta)] that provably contains lambda_max (inertia count == all eigenvalues of the active block),
-  // steps 3-4 count the eigenvalues below the cutoff at both ends of that bracket.
-  T delta = T(-1);
-  int m_lo = -1, m_hi = -2;
-  ABRB_NOUNROLL
-  for (int step = 0; step < 5; ++step) {
-    const T dl = step == 0 ? (sizeof(T) == 8 ? T(1e-7) : T(2e-4)) : (step == 1 ? T(2e-3) : T(5e-2));
-    if (step < 3 && delta >= T(0)) continue;  // bracket already established
-    if (step >= 3 && delta < T(0)) continue;  // no bracket: give up below
-    if (step == 4 && delta <= T(1e-6)) {      // bracket tighter than the reference's own float32 noise on the cutoff:
-      m_hi = m_lo;                            // an eigenvalue inside it has probability ~1e-7, skip the second count
-      continue;
-    }
-    const T sigma = step < 3 ? rho * (T(1) + dl) : (step == 3 ? rcond * rho : rcond * rho * (T(1) + delta));
-    const int c = inertia_below<T, S_>(Sm, sigma);
-    if (step < 3) {
-      int inact_below = 0;
-      ABRB_UNROLL
-      for (int i = 0; i < S_; ++i) inact_below += (!((active >> i) & 1u) && Sm[i][i] < sigma) ? 1 : 0;
-      if (c >= 0 && c - inact_below == n_act) delta = dl;
-    } else if (step == 3) {
-      m_lo = c;
-    } else {
-      m_hi = c;
-    }
-  }
-  constexpr int MV = S_ >= 6 ? 3 : 2;  // truncated eigenvectors the register-resident route can carry
-  if (delta < T(0) || m_lo < 0 || m_lo != m_hi || m_lo > MV) return false;
-  const int m = m_lo;
-  // ---- 3. truncated eigenvectors by inverse subspace iteration.  MV vectors are carried; vector j only takes part
-  //         when j < m (runtime guards around static indices: the vectors stay in registers).  Three truncated
-  //         eigenvalues are ~7e-4 of the UR5 6-DOF pinv states, i.e. more than one state per 65 536-state launch,
-  //         and each state that leaves this routine for the Jacobi route costs the whole launch ~80 us of tail.
-  T V[MV][S_];
-  ABRB_UNROLL
-  for (int i = 0; i < S_; ++i) {
-    const bool on = (active >> i) & 1u;
-    V[0][i] = on ? T(1) / T(1 + i) + T(0.1) : T(0);
-    V[1][i] = on ? ((i & 1) ? T(-0.7) : T(0.45)) + T(0.05) * T(i) : T(0);
-    if (MV > 2) V[MV - 1][i] = on ? ((i % 3) == 0 ? T(0.8) : ((i % 3) == 1 ? T(-0.35) : T(0.2))) - T(0.03) * T(i) : T(0);
-  }
-  if (m >= 1) {
-    // Blocks of inverse iterations until the span is invariant (|| S v - span component || tiny relative to the
-    // cutoff).  The loops over `blk`/`it` stay rolled (their bodies use static indices only): convergence normally
-    // takes one block because the truncated eigenvalues sit orders of magnitude below the kept ones; the block limit is
-    // generous because a truncated eigenvalue within a factor ~2 of the next kept one converges at that ratio per
-    // iteration, and every state that runs out of blocks drops to the Jacobi route (with 6 blocks that was ~1 in 10^3
-    // of the pinv states: one or more per 65 536-state launch).
-    const T tol = (sizeof(T) == 8 ? T(1e-10) : T(1e-4)) * rcond * rho;
-    bool converged = false;
-    ABRB_NOUNROLL
-    for (int blk = 0; blk < ABRB_PINV_BLOCKS && !converged; ++blk) {
-      ABRB_NOUNROLL
-      for (int it = 0; it < 3; ++it) {
-        ABRB_UNROLL
-        for (int j = 0; j < MV; ++j) {
-          if (j < m) {
-            fwd_solve<T, S_>(L, invd, V[j]);
-            bwd_solve<T, S_>(L, invd, V[j]);
-            ABRB_UNROLL
-            for (int k = 0; k < j; ++k) {  // Gram-Schmidt against the vectors already done in this sweep
-              T d = T(0);
-              ABRB_UNROLL
-              for (int i = 0; i < S_; ++i) d += V[k][i] * V[j][i];
-              ABRB_UNROLL
-              for (int i = 0; i < S_; ++i) V[j][i] -= d * V[k][i];
-            }
-            T nn = T(0);
-            ABRB_UNROLL
-            for (int i = 0; i < S_; ++i) nn += V[j][i] * V[j][i];
-#if ABRB_FAST_DIV
-            const T sc = inv_sqrt_t(nn);
-#else
-            const T sc = T(1) / sqrt_t(nn);
-#endif
-            ABRB_UNROLL
-            for (int i = 0; i < S_; ++i) V[j][i] *= sc;
-          }
-        }
-      }
-      // residual of every carried vector against the span: e_j = S v_j - sum_k (v_k^T S v_j) v_k
-      T rmax = T(0);
-      ABRB_UNROLL
-      for (int j = 0; j < MV; ++j) {
-        if (j < m) {
-          T w[S_];
-          ABRB_UNROLL
-          for (int i = 0; i < S_; ++i) {
-            T acc = T(0);
-            ABRB_UNROLL
-            for (int l = 0; l < S_; ++l) acc += Sm[i][l] * V[j][l];
-            w[i] = acc;
-          }
-          ABRB_UNROLL
-          for (int k = 0; k < MV; ++k) {
-            if (k < m) {
-              T a = T(0);
-              ABRB_UNROLL
-              for (int i = 0; i < S_; ++i) a += V[k][i] * w[i];
-              // (w is updated in place: the v_k are orthonormal, so later coefficients are unaffected to rounding)
-              ABRB_UNROLL
-              for (int i = 0; i < S_; ++i) w[i] -= a * V[k][i];
-            }
-          }
-          T r = T(0);
-          ABRB_UNROLL
-          for (int i = 0; i < S_; ++i) r += w[i] * w[i];
-          rmax = (r <= rmax) ? rmax : r;  // a NaN residual propagates and fails the test below
-        }
-      }
-      // The result P S^-1 P y is off by O(theta) (theta = angle between the iterate and the true span, ~ r / gap to
-      // the kept eigenvalues), so the residual is held to 1e-10 of the cutoff.  NaNs compare false.
-      converged = rmax <= tol * tol;
-    }
-    if (!converged) return false;
-  }
-  // ---- 4. x = P S^-1 P y   (for one or two right-hand sides: the eigenvectors are the expensive part)
-  ABRB_NOUNROLL
-  for (int rhs = 0; rhs < (two ? 2 : 1); ++rhs) {
-    T b[S_];
-    ABRB_UNROLL
-    for (int i = 0; i < S_; ++i) b[i] = rhs == 0 ? y[i] : y2[i];
-    ABRB_NOUNROLL
-    for (int pass = 0; pass < 2; ++pass) {
-      ABRB_UNROLL
-      for (int j = 0; j < MV; ++j) {
-        if (j < m) {
-          T d = T(0);
-          ABRB_UNROLL
-          for (int i = 0; i < S_; ++i) d += V[j][i] * b[i];
-          ABRB_UNROLL
-          for (int i = 0; i < S_; ++i) b[i] -= d * V[j][i];
-        }
-      }
-      if (pass == 0) {
-        fwd_solve<T, S_>(L, invd, b);
-        bwd_solve<T, S_>(L, invd, b);
-      }
-    }
-    ABRB_UNROLL
-    for (int i = 0; i < S_; ++i) {
-      if (rhs == 0)
-        x[i] = b[i];
-      else
-        x2[i] = b[i];
-    }
-  }
-  return true;
-}
-
-template <typename T, int S_>
-ABRB_HD bool pinv_solve_fast(const T (*Sm)[S_], const T (*L)[S_], const T *invd, unsigned active, T rcond,
-                             const T *y, T *x) {
-  return pinv_solve_fast2<T, S_>(Sm, L, invd, active, rcond, y, x, y, x, false);
-}
-
-// (Measured and dropped on B200, 6-DOF fp64 OSC kernel at 99 us: an out-of-line entry with private register copies of the
-// arguments (120 us); forming S^-1 explicitly so that the inverse iteration becomes matrix-vector products (faster in
-// isolation, 13.7 k vs 16.7 k cycles, but 161 us in the kernel: the 36 extra live values spill).)
 
 }  // namespace abrb

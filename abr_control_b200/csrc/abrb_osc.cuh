@@ -58,7 +58,7 @@ ABRB_HD void joint_limits_generate(const NullK<T, N> &Z, const T *q, T *u) {
 
 template <typename T, int N>
 struct OscK {
-  T kp, ko, kv;
+  T kp, ko, kv, ki;
   T lim_xyz, lim_abg;  // vmax[0]/kp*kv, vmax[1]/ko*kv   (osc.py:109-115)
   T thr;               // |det| threshold of _Mx (osc.py:120,138)
   T xoff[3];
@@ -156,43 +156,44 @@ ABRB_HD T wrap_pm_pi(T d) {
   return r - pi;
 }
 
+// Sequential stand-in for the warp-cooperative truncating pseudo-inverse (abrb_coop.cuh): used by the host
+// instantiation (tests/hostsim), where a "warp" is one state.
+struct SeqCoop {
+  template <typename T, int N, int KD, class K_>
+  ABRB_HD void pinv(bool slow, K_ &K, T *y, T *z, bool two, double rcond) const {
+    if (!slow) return;
+    double A[KD * N], yd[KD], zd[KD], xy[KD], xz[KD];
+    for (int r = 0; r < KD; ++r) {
+      yd[r] = double(y[r]);
+      zd[r] = double(z[r]);
+      for (int k = 0; k < N; ++k) A[r * N + k] = double(K.s.ld(K_::aslot(r, k)));
+    }
+    pinv_rows_jacobi_seq<N, KD>(A, rcond, yd, zd, two, xy, xz);
+    for (int r = 0; r < KD; ++r) {
+      y[r] = T(xy[r]);
+      if (two) z[r] = T(xz[r]);
+    }
+  }
+};
+
 // One OSC evaluation.  KD = 3: only (a subset of) x,y,z controlled; KD = 6: any mask.
 // PLANT: also return ddq = M^-1 (u + g - C dq) for the rollout kernel.
-// Returns true only in MODE 1 (below) for a state left to the second launch; false when u has been produced.
 // `K`: caller-provided kinematic scratch (registers or shared memory).  Once the dynamics are done its t_k / z_k
 // slots are overwritten IN PLACE by the task Jacobian (column k of J only needs t_k, z_k), which later becomes
 // A = (L^-1 J^T)^T; so J, A never occupy registers of their own.
-//
-// MODE 0: everything in line.  MODE 1 / MODE 2 are the two halves of the two-launch mode: MODE 1 stops at a state that
-// needs the truncating route, writes what the rest of the evaluation needs (y, z, the partial u, C dq, g, u_null,
-// chol(M), A: OscRecord<N,KD>::kLen values) through `rec` and returns true; MODE 2 starts from such a record (q, dq,
-// target are not read), runs the truncating route and finishes u.  `Rec`: begin() reserves a record,
-// put(i, v) / get(i) access value i of it.
-struct NoRecord {
-  ABRB_HD void begin() {}
-  template <typename V> ABRB_HD void put(int, V) {}
-  ABRB_HD double get(int) const { return 0.0; }
-};
-
-template <int N, int KD>
-struct OscRecord {
-  static constexpr int kY = 0, kZ = KD, kU = 2 * KD, kCdq = kU + N, kG = kCdq + N, kUn = kG + N, kL = kUn + N,
-                       kMi = kL + N * (N + 1) / 2, kA = kMi + N, kLen = kA + KD * N;
-};
-
-template <typename T, int N, int KD, bool PLANT, int MODE, class K_, class Rec>
-ABRB_HD bool osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, const T *dq, const T *target,
-                      const T *tv, T *u, T *train, T *ddq, K_ &K, Rec &rec) {
+// `ierr`: the state's integrated task-space error (osc.py:81-82, :262-264), 6 values updated in place, or nullptr
+// when ki == 0.
+// `coop`: how the states whose task-space inertia needs the TRUNCATING pseudo-inverse (osc.py:138-145, a few percent
+// of random UR5 states) are finished.  On the GPU every lane of the warp reaches coop.pinv() together and the lanes
+// work on those states jointly (abrb_coop.cuh) instead of one lane walking a long serial path while 31 wait.
+template <typename T, int N, int KD, bool PLANT, class K_, class Coop>
+ABRB_HD void osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, const T *dq, const T *target,
+                      const T *tv, T *ierr, T *u, T *train, T *ddq, K_ &K, Coop &coop) {
   constexpr bool ORTHO = K_::kOrtho;
-  typedef typename K_::S SL;
-  typedef OscRecord<N, KD> RC;
-  // A(r,k): r<3 -> slot kT+3k+r,  r>=3 -> slot kZ+3k+r-3
-  auto Aslot = [](int r, int k) { return r < 3 ? SL::kT + 3 * k + r : SL::kZ + 3 * k + (r - 3); };
+  auto Aslot = [](int r, int k) { return K_::aslot(r, k); };
   T M[N][N], Mi[N], g[N], cdq[N], un[N], y[KD], z[KD];
   const bool any_null = O.n_null > 0;
   const T rcond = O.thr * T(0.1);
-  bool fast = true;
-  if constexpr (MODE != 2) {
   K.sync();
   walk<T, N>(P, q, O.frame, K);
   K.sync();
@@ -215,7 +216,7 @@ ABRB_HD bool osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
     if (O.alg == 0) {
       T qd[4], qe[4], qr[4];
       quat_from_euler_rxyz(target[3], target[4], target[5], qd);
-      const T nd = T(1) / sqrt_t(qd[0] * qd[0] + qd[1] * qd[1] + qd[2] * qd[2] + qd[3] * qd[3]);
+      const T nd = inv_sqrt_t(qd[0] * qd[0] + qd[1] * qd[1] + qd[2] * qd[2] + qd[3] * qd[3]);
       ABRB_UNROLL
       for (int i = 0; i < 4; ++i) qd[i] *= nd;
       quat_from_R(R, qe);
@@ -236,6 +237,13 @@ ABRB_HD bool osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
       quat_from_R(Red, qed);
       ABRB_UNROLL
       for (int r = 0; r < 3; ++r) err[3 + r] = -(R[r * 3 + 0] * qed[1] + R[r * 3 + 1] * qed[2] + R[r * 3 + 2] * qed[3]);
+    }
+  }
+  if (ierr != nullptr) {  // osc.py:262-264: integrated_error += u_task; u_task += ki * integrated_error
+    ABRB_UNROLL
+    for (int c = 0; c < 6; ++c) {
+      ierr[c] += err[c];
+      err[c] += O.ki * ierr[c];
     }
   }
   if (O.use_vmax) {  // osc.py:198-215
@@ -355,9 +363,8 @@ ABRB_HD bool osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) K.s.st(Aslot(r, k), row[k]);
   }
-  // S is built straight into the array that is then factorised in place; only its trace is kept.  The rare
-  // truncating branch re-forms S from A (shared memory) instead of keeping 36 more values live on the hot path.
-  T Sc[KD][KD], Si[KD], trS = T(0);
+  // S is built straight into the array that is then factorised in place
+  T Sc[KD][KD], Si[KD];
   ABRB_UNROLL
   for (int a = 0; a < KD; ++a) {
     T ra[N];
@@ -372,7 +379,6 @@ ABRB_HD bool osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
         const bool on = ((O.dof_mask >> a) & 1u) && ((O.dof_mask >> b) & 1u);
         Sc[a][b] = on ? s : (a == b ? T(1) : T(0));
         Sc[b][a] = Sc[a][b];
-        if (a == b && on) trS += s;
       }
     }
   }
@@ -381,47 +387,44 @@ ABRB_HD bool osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
   T det = T(1);
   ABRB_UNROLL
   for (int a = 0; a < KD; ++a) det *= Sc[a][a] * Sc[a][a];
-  fast = pd && (det >= O.thr);
-#ifndef ABRB_CERT_PRECHECK
-#define ABRB_CERT_PRECHECK 0  // experimental (not the shipped default): 1 = skip the certificate when it cannot pass,
-#endif                        // 2 = also never try it on the 6-row path (it passed for 0 of 2 361 UR5 / Jaco2 pinv states;
-                              // the truncating route returns S^-1 y itself when nothing is truncated)
-#if ABRB_CERT_PRECHECK
-  bool try_cert = pd && !fast && !(ABRB_CERT_PRECHECK >= 2 && KD == 6);
-  if (try_cert) {
-    // (S^-1)_aa >= 1 / L_aa^2, so ||S^-1||_F >= max_a 1/L_aa^2: if already that bound breaks the inequality below,
-    // the six solves are pointless (always the case for the UR5 states that get here)
-    T big = T(0);
-    ABRB_UNROLL
-    for (int a = 0; a < KD; ++a)
-      if (((O.dof_mask >> a) & 1u) && Si[a] * Si[a] > big) big = Si[a] * Si[a];
-    try_cert = rcond * trS * big < T(1);
-  }
-  if (try_cert) {
-#else
+  bool fast = pd && (det >= O.thr);
   if (pd && !fast) {
-#endif
-    // pinv == inv whenever no eigenvalue is truncated; certify that cheaply:
-    // lambda_max <= trace(S_active), 1/lambda_min <= ||S^-1||_F  =>  no truncation if 1/||S^-1||_F > rcond*trace
-    const T tr = trS;
-    T fro = T(0);
+    // pinv == inv whenever no eigenvalue is truncated; certify that cheaply before sending the state down the
+    // truncating route:  lambda_max <= trace(S_active) and 1/lambda_min <= ||S^-1||_F, so nothing is truncated if
+    // rcond * trace * ||S^-1||_F < 1.  (S^-1)_aa >= 1/L_aa^2 bounds ||S^-1||_F from below with values already at hand:
+    // when that bound alone breaks the inequality (every UR5 6-DOF state that gets here) the solves are skipped.
+    T tr = T(0), big = T(0);
     ABRB_UNROLL
     for (int a = 0; a < KD; ++a) {
       if ((O.dof_mask >> a) & 1u) {
-        T e[KD];
+        T saa = T(0);  // S_aa = sum_k L_ak^2
         ABRB_UNROLL
-        for (int b = 0; b < KD; ++b) e[b] = b == a ? T(1) : T(0);
-        fwd_solve<T, KD>(Sc, Si, e);
-        bwd_solve<T, KD>(Sc, Si, e);
-        ABRB_UNROLL
-        for (int b = 0; b < KD; ++b) fro += e[b] * e[b];
+        for (int b = 0; b < KD; ++b)
+          if (b <= a) saa += Sc[a][b] * Sc[a][b];
+        tr += saa;
+        big = Si[a] * Si[a] > big ? Si[a] * Si[a] : big;
       }
     }
-    fast = rcond * tr * sqrt_t(fro) < T(1);
+    if (rcond * tr * big < T(1)) {
+      T fro = T(0);
+      ABRB_UNROLL
+      for (int a = 0; a < KD; ++a) {
+        if ((O.dof_mask >> a) & 1u) {
+          T e[KD];
+          ABRB_UNROLL
+          for (int b = 0; b < KD; ++b) e[b] = b == a ? T(1) : T(0);
+          fwd_solve<T, KD>(Sc, Si, e);
+          bwd_solve<T, KD>(Sc, Si, e);
+          ABRB_UNROLL
+          for (int b = 0; b < KD; ++b) fro += e[b] * e[b];
+        }
+      }
+      fast = rcond * tr * sqrt_t(fro) < T(1);
+    }
   }
   // ---- secondary controllers that go through the null-space filter  I - J^T Mx J M^-1  (osc.py:310-318): their
   //      task-space image z = J M^-1 u_null is formed here so that Mx is applied to y and z in ONE place (the
-  //      truncating branch computes its eigenvectors once for both right-hand sides)
+  //      truncating route decomposes once for both right-hand sides)
   ABRB_UNROLL
   for (int r = 0; r < KD; ++r) z[r] = T(0);
   if (any_null) {
@@ -454,7 +457,7 @@ ABRB_HD bool osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
       z[r] = ((O.dof_mask >> r) & 1u) ? s : T(0);
     }
   }
-  // y <- Mx y,  z <- Mx z   (regular case; the truncating case follows below, possibly in another launch)
+  // y <- Mx y,  z <- Mx z: two triangular solves in the regular case ...
   if (fast) {
     fwd_solve<T, KD>(Sc, Si, y);
     bwd_solve<T, KD>(Sc, Si, y);
@@ -463,120 +466,10 @@ ABRB_HD bool osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
       bwd_solve<T, KD>(Sc, Si, z);
     }
   }
-  }  // MODE != 2
-  if constexpr (MODE == 1) {
-    if (!fast) {
-      rec.begin();
-      ABRB_UNROLL
-      for (int r = 0; r < KD; ++r) {
-        rec.put(RC::kY + r, y[r]);
-        rec.put(RC::kZ + r, z[r]);
-        ABRB_UNROLL
-        for (int k = 0; k < N; ++k) rec.put(RC::kA + r * N + k, K.s.ld(Aslot(r, k)));
-      }
-      int li = 0;
-      ABRB_UNROLL
-      for (int a = 0; a < N; ++a) {
-        rec.put(RC::kU + a, u[a]);
-        rec.put(RC::kCdq + a, (PLANT || O.use_C) ? cdq[a] : T(0));
-        rec.put(RC::kG + a, g[a]);
-        rec.put(RC::kUn + a, un[a]);
-        rec.put(RC::kMi + a, Mi[a]);
-        ABRB_UNROLL
-        for (int b = 0; b < N; ++b)
-          if (b <= a) rec.put(RC::kL + li++, M[a][b]);
-      }
-      return true;
-    }
-  }
-  if constexpr (MODE == 2) {
-    fast = false;
-    ABRB_UNROLL
-    for (int r = 0; r < KD; ++r) {
-      y[r] = T(rec.get(RC::kY + r));
-      z[r] = T(rec.get(RC::kZ + r));
-      ABRB_UNROLL
-      for (int k = 0; k < N; ++k) K.s.st(Aslot(r, k), T(rec.get(RC::kA + r * N + k)));
-    }
-    int li = 0;
-    ABRB_UNROLL
-    for (int a = 0; a < N; ++a) {
-      u[a] = T(rec.get(RC::kU + a));
-      cdq[a] = T(rec.get(RC::kCdq + a));
-      g[a] = T(rec.get(RC::kG + a));
-      un[a] = T(rec.get(RC::kUn + a));
-      Mi[a] = T(rec.get(RC::kMi + a));
-      ABRB_UNROLL
-      for (int b = 0; b < N; ++b) M[a][b] = b <= a ? T(rec.get(RC::kL + li++)) : T(0);
-    }
-  }
-  if (!fast) {
-    // cheap register-resident route first (inertia counts + inverse iteration, abrb_math.cuh); the rolled,
-    // local-memory Jacobi eigen-decomposition only when that is inconclusive.  Static indices everywhere: a
-    // rolled loop over S or v here would force them into local memory for the whole function.
-    const unsigned mask = O.dof_mask & ((1u << KD) - 1u);
-    // This branch always runs in double precision, also for the fp32 kernels: the matrices that end up here have
-    // eigenvalue ratios down to 1e-8, where a float Cholesky breaks down (and the FP64 pipe is idle there anyway).
-    double Sd[KD][KD], Ld[KD][KD], Sid[KD], yd[KD], xd[KD], zd[KD], xz[KD];
-    ABRB_UNROLL
-    for (int a = 0; a < KD; ++a) {
-      yd[a] = double(y[a]);
-      zd[a] = double(z[a]);
-      double ra[N];
-      ABRB_UNROLL
-      for (int k = 0; k < N; ++k) ra[k] = double(K.s.ld(Aslot(a, k)));
-      ABRB_UNROLL
-      for (int b = 0; b < KD; ++b) {
-        if (b <= a) {
-          double acc = 0.0;
-          ABRB_UNROLL
-          for (int k = 0; k < N; ++k) acc += ra[k] * double(K.s.ld(Aslot(b, k)));
-          const bool on = ((mask >> a) & 1u) && ((mask >> b) & 1u);
-          const double val = on ? acc : 0.0;
-          Sd[a][b] = val;
-          Sd[b][a] = val;
-        }
-      }
-    }
-    // inactive rows: decoupled, diagonal = trace >= lambda_max so that they are never counted as truncated
-    double trd = 0.0;
-    ABRB_UNROLL
-    for (int a = 0; a < KD; ++a) trd += Sd[a][a];
-    ABRB_UNROLL
-    for (int a = 0; a < KD; ++a)
-      if (!((mask >> a) & 1u)) Sd[a][a] = trd;
-    ABRB_UNROLL
-    for (int a = 0; a < KD; ++a)
-      ABRB_UNROLL
-    for (int b = 0; b < KD; ++b) Ld[a][b] = Sd[a][b];
-    const bool pdd = chol<double, KD>(Ld, Sid);
-    bool done = pdd && pinv_solve_fast2<double, KD>(Sd, Ld, Sid, mask, double(rcond), yd, xd, zd, xz, any_null);
-    if (!done) {
-      double Sf[KD * KD], yf[KD], xf[KD];
-      ABRB_UNROLL
-      for (int a = 0; a < KD; ++a)
-        ABRB_UNROLL
-      for (int b = 0; b < KD; ++b) Sf[a * KD + b] = (a == b && !((mask >> a) & 1u)) ? 1.0 : Sd[a][b];
-      ABRB_NOUNROLL
-      for (int rhs = 0; rhs < (any_null ? 2 : 1); ++rhs) {
-        ABRB_UNROLL
-        for (int a = 0; a < KD; ++a) yf[a] = rhs == 0 ? yd[a] : zd[a];
-        pinv_apply_sym<double, KD>(Sf, mask, double(rcond), yf, xf);
-        ABRB_UNROLL
-        for (int a = 0; a < KD; ++a) {
-          if (rhs == 0)
-            xd[a] = xf[a];
-          else
-            xz[a] = xf[a];
-        }
-      }
-    }
-    ABRB_UNROLL
-    for (int a = 0; a < KD; ++a) {
-      y[a] = T(xd[a]);
-      if (any_null) z[a] = T(xz[a]);
-    }
-  }
+  // ... and the truncating pseudo-inverse otherwise (always in double: the matrices that end up here have eigenvalue
+  // ratios down to 1e-16).  When nothing is below the cut-off it returns S^-1 y itself, as numpy's pinv does.
+  coop.template pinv<T, N, KD>(!fast, K, y, z, any_null, double(rcond));
+
   // J^T x = L (A^T x)   (osc.py:285-288)
   auto JT_apply = [&](const T *x, T *out) {
     T w[N];
@@ -630,14 +523,13 @@ ABRB_HD bool osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) ddq[k] = rhs[k];
   }
-  return false;
 }
 
 template <typename T, int N, int KD, bool PLANT, class K_>
-ABRB_HD bool osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, const T *dq, const T *target,
-                       const T *tv, T *u, T *train, T *ddq, K_ &K) {
-  NoRecord none;
-  return osc_eval<T, N, KD, PLANT, 0>(P, O, q, dq, target, tv, u, train, ddq, K, none);
+ABRB_HD void osc_state(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, const T *dq, const T *target,
+                       const T *tv, T *ierr, T *u, T *train, T *ddq, K_ &K) {
+  SeqCoop seq;
+  osc_eval<T, N, KD, PLANT>(P, O, q, dq, target, tv, ierr, u, train, ddq, K, seq);
 }
 
 // Standalone secondary controller (`Damping/RestingConfig/AvoidObstacles.generate`)

@@ -21,19 +21,22 @@ struct abrb_model {
   ChainHost host;
 };
 
-// Index queue of the two-launch OSC mode (kernels.cu): one per (device, stream) the controller has been used on.
-struct SlowQueue {
-  int *buf = nullptr;       // 4 + cap ints
-  void *records = nullptr;  // osc_record_len(n) * cap doubles (also used by the float kernels)
-  int64_t cap = 0;
-};
-
 struct abrb_osc {
   const abrb_model *model;
   abrb_osc_params params;
-  int64_t two_launch_min = 0;  // 0: single launch always
-  mutable std::mutex mu;
-  mutable std::map<std::pair<int, cudaStream_t>, SlowQueue> queues;
+  int64_t host_chunk = 0;  // option "host_chunk_states": states per pipeline chunk of the *_host entry points, 0 = auto
+};
+
+// Symmetric gather buffers of one rank (include/abrb.h): one cudaMalloc'd region [ n_buffers x bytes | flags | counter ]
+// exported with CUDA IPC; `peer[r]` is rank r's region mapped into this process (own region for r == rank).
+struct abrb_gather {
+  int rank = 0, world = 1, n_buffers = 1, dev = 0;
+  size_t bytes = 0;       // per buffer
+  size_t flag_off = 0;    // byte offset of flags[kMaxPeers] (unsigned long long) in a region
+  size_t counter_off = 0; // byte offset of the CTA counter + status word
+  void *peer[kMaxPeers] = {nullptr};
+  bool imported[kMaxPeers] = {false};
+  unsigned long long epoch = 0;  // launches issued so far (ranks call in lockstep, so epochs agree)
 };
 
 namespace {
@@ -71,50 +74,98 @@ int ensure_device() {
   return ABRB_OK;
 }
 
-bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// The kernels read and write with scalar (element-sized) accesses only, so element alignment is all they need: a
+// row slice of a contiguous (B, n) array (q[1:], a rank's shard at an odd row) is a valid argument.
+bool aligned_elem(const void *p, bool f32) { return (reinterpret_cast<uintptr_t>(p) & (f32 ? 3u : 7u)) == 0; }
 
-// grow-only device workspace for the *_host entry points (one per host thread)
+// grow-only device workspace for the *_host entry points (one per host thread).  The OSC host path has kSlots
+// independent pipeline slots (own device region, own streams) so that consecutive asynchronous calls overlap:
+// slot 1's H2D runs under slot 0's kernel and D2H (PCIe is full duplex, and the copy engines run beside the SMs).
+constexpr int kSlots = 2, kLanes = 2;
 struct Workspace {
   void *ptr = nullptr;
   size_t cap = 0;
   int dev = -1;
   cudaStream_t stream = nullptr;
-  cudaStream_t lanes[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of the *_host OSC call
-  int ensure(size_t bytes) {
+  struct Slot {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    cudaStream_t lanes[kLanes] = {nullptr, nullptr};  // chunk pipeline inside one call
+    int used = 0;                                      // lanes with work in flight
+  } slots[kSlots];
+  void release() {
+    if (dev < 0) return;
     int cur = 0;
-    cudaError_t ed = cudaGetDevice(&cur);
-    if (ed != cudaSuccess) return (int)ed;
-    if (dev != cur) {  // the calling thread switched devices: streams and memory belong to the device they were made on
-      if (dev >= 0) {
-        cudaSetDevice(dev);
-        cudaFree(ptr);
-        if (stream) cudaStreamDestroy(stream);
-        for (auto &l : lanes)
-          if (l) cudaStreamDestroy(l);
-        cudaSetDevice(cur);
-      }
-      ptr = nullptr;
-      cap = 0;
-      stream = nullptr;
-      for (auto &l : lanes) l = nullptr;
+    if (cudaGetDevice(&cur) != cudaSuccess) return;  // process is shutting down
+    cudaSetDevice(dev);
+    cudaFree(ptr);
+    if (stream) cudaStreamDestroy(stream);
+    for (auto &sl : slots) {
+      cudaFree(sl.ptr);
+      for (auto &l : sl.lanes)
+        if (l) cudaStreamDestroy(l);
+      sl = Slot();
+    }
+    cudaSetDevice(cur);
+    ptr = nullptr;
+    cap = 0;
+    stream = nullptr;
+    dev = -1;
+  }
+  ~Workspace() { release(); }
+  int bind() {  // make the workspace belong to the calling thread's current device
+    int cur = 0;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e != cudaSuccess) return (int)e;
+    if (dev != cur) {  // the thread switched devices: streams and memory belong to the device they were made on
+      release();
       dev = cur;
     }
     if (stream == nullptr) {
-      cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+      e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
       if (e != cudaSuccess) return (int)e;
-      for (auto &l : lanes) {
-        e = cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking);
-        if (e != cudaSuccess) return (int)e;
-      }
+      for (auto &sl : slots)
+        for (auto &l : sl.lanes) {
+          e = cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking);
+          if (e != cudaSuccess) return (int)e;
+        }
     }
+    return 0;
+  }
+  int ensure(size_t bytes) {
+    int e = bind();
+    if (e) return e;
     if (bytes <= cap) return 0;
     if (ptr) cudaFree(ptr);
     ptr = nullptr;
     cap = 0;
-    cudaError_t e = cudaMalloc(&ptr, bytes);
-    if (e != cudaSuccess) return (int)e;
+    cudaError_t ce = cudaMalloc(&ptr, bytes);
+    if (ce != cudaSuccess) return (int)ce;
     cap = bytes;
     return 0;
+  }
+  int ensure_slot(int i, size_t bytes) {
+    int e = bind();
+    if (e) return e;
+    Slot &sl = slots[i];
+    if (bytes <= sl.cap) return 0;
+    if (sl.ptr) cudaFree(sl.ptr);  // synchronises with anything still using it
+    sl.ptr = nullptr;
+    sl.cap = 0;
+    cudaError_t ce = cudaMalloc(&sl.ptr, bytes);
+    if (ce != cudaSuccess) return (int)ce;
+    sl.cap = bytes;
+    return 0;
+  }
+  int wait_slot(int i) {  // returns the first CUDA error of the slot's lanes
+    Slot &sl = slots[i];
+    cudaError_t first = cudaSuccess;
+    for (int l = 0; l < sl.used; ++l) {
+      cudaError_t e = cudaStreamSynchronize(sl.lanes[l]);
+      if (e != cudaSuccess && first == cudaSuccess) first = e;
+    }
+    sl.used = 0;
+    return (int)first;
   }
 };
 thread_local Workspace g_ws;
@@ -127,6 +178,25 @@ size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
     cudaError_t e_ = (call);                                \
     if (e_ != cudaSuccess) return cuda_fail((int)e_, where); \
   } while (0)
+
+// Consumer side of the fused all-gather: one thread per rank spins (system-scope acquire loads) until that rank has
+// published `epoch` in our flag array, i.e. all its rows of this launch have landed in our buffer.
+__global__ void gather_wait_kernel(const unsigned long long *flags, int world, unsigned long long epoch, int *status) {
+  const int r = threadIdx.x;
+  if (r < world) {
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
+      if (v >= epoch) break;
+      if (clock64() - t0 > (6LL << 30)) {  // ~3 s: a peer never arrived; report instead of hanging the GPU
+        *status = 1;
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+}
 
 }  // namespace
 
@@ -193,7 +263,7 @@ static int rbd_eval(const abrb_model *m, int frame_id, const double *x_off, cons
   if (!q) return fail(ABRB_EINVAL, "abrb_rbd_eval: NULL q");
   const void *ptrs[] = {q, dq, out->Tx, out->T, out->R, out->T_inv, out->quat, out->J, out->dJ, out->M, out->g, out->C};
   for (const void *p : ptrs)
-    if (p && !aligned16(p)) return fail(ABRB_EINVAL, "abrb_rbd_eval: pointers must be 16-byte aligned");
+    if (p && !aligned_elem(p, f32)) return fail(ABRB_EINVAL, "abrb_rbd_eval: misaligned pointer");
   int rc = ensure_device();
   if (rc) return rc;
   RbdCall c{frame_id, x_off, q, dq, B, *out, f32, (cudaStream_t)stream};
@@ -270,92 +340,46 @@ int abrb_osc_create(const abrb_model *m, const abrb_osc_params *p, abrb_osc **ou
   if (!c) return fail(ABRB_ENOMEM, "abrb_osc_create: out of memory");
   c->model = m;
   c->params = *p;
-  if (const char *v = std::getenv("ABRB_OSC_DEFER_MIN")) c->two_launch_min = (int64_t)std::atoll(v);
+  if (const char *v = std::getenv("ABRB_HOST_CHUNK")) c->host_chunk = (int64_t)std::atoll(v);
   *out = c;
   return ABRB_OK;
 }
 
 int abrb_osc_set_option(abrb_osc *c, const char *name, double value) {
   if (!c || !name) return fail(ABRB_EINVAL, "abrb_osc_set_option: NULL argument");
-  if (std::strcmp(name, "two_launch_min") == 0) {
-    c->two_launch_min = value > 0 ? (int64_t)value : 0;
+  if (std::strcmp(name, "host_chunk_states") == 0) {
+    c->host_chunk = value > 0 ? (int64_t)value : 0;
     return ABRB_OK;
   }
   return fail(ABRB_EINVAL, std::string("abrb_osc_set_option: unknown option ") + name);
 }
 
 int abrb_osc_destroy(abrb_osc *c) {
-  if (c) {
-    int cur = 0;
-    cudaGetDevice(&cur);
-    for (auto &kv : c->queues) {
-      cudaSetDevice(kv.first.first);
-      cudaFree(kv.second.buf);
-      cudaFree(kv.second.records);
-    }
-    cudaSetDevice(cur);
-  }
   delete c;
   return ABRB_OK;
 }
 
-// Two-launch mode (kernels.cu, osc_kernel<DEFER> + osc_slow_kernel) for the 6-row task space, from
-// `two_launch_min` states up.  Returns the queue for this (device, stream), growing it on demand, or nullptr for the
-// single-launch mode.
-static SlowQueue slow_queue_for(const abrb_osc *c, int64_t B, cudaStream_t stream, int *err) {
-  const int64_t min_b = c->two_launch_min > 0 ? c->two_launch_min : -1;
-  *err = 0;
-  const abrb_osc_params &p = c->params;
-  if (min_b < 0 || B < min_b || B > (int64_t)0x7fffffff - 8) return SlowQueue();
-  if (!(p.ctrlr_dof[3] || p.ctrlr_dof[4] || p.ctrlr_dof[5])) return SlowQueue();
-  int dev = 0;
-  cudaGetDevice(&dev);
-  std::lock_guard<std::mutex> lock(c->mu);
-  SlowQueue &sq = c->queues[std::make_pair(dev, stream)];
-  if (sq.cap < B) {
-    cudaError_t e = cudaSuccess;
-    if (sq.buf) e = cudaFree(sq.buf);  // synchronises with any launch still using it
-    if (sq.records) cudaFree(sq.records);
-    sq = SlowQueue();
-    if (e == cudaSuccess) e = cudaMalloc(&sq.buf, (size_t)(B + 4) * sizeof(int));
-    if (e == cudaSuccess)
-      e = cudaMalloc(&sq.records, (size_t)osc_record_len(c->model->host.n) * (size_t)B * sizeof(double));
-    if (e == cudaSuccess) e = cudaMemsetAsync(sq.buf, 0, 4 * sizeof(int), stream);
-    if (e != cudaSuccess) {
-      cudaFree(sq.buf);
-      cudaFree(sq.records);
-      sq = SlowQueue();
-      *err = (int)e;
-      return SlowQueue();
-    }
-    sq.cap = B;
-  }
-  return sq;
-}
-
 static int osc_generate(const abrb_osc *c, int frame_id, const double *x_off, const void *q, const void *dq,
                         const void *target, int target_stride, const void *tv, int tv_stride, void *u, void *train,
-                        int64_t B, void *stream, bool f32) {
+                        void *ierr, int64_t B, void *stream, bool f32, const GatherArgs *gather = nullptr) {
   if (!c) return fail(ABRB_EINVAL, "abrb_osc_generate: NULL controller");
   if (B < 0) return fail(ABRB_EINVAL, "abrb_osc_generate: B < 0");
   const int n = c->model->host.n;
   if (frame_id < 0 || frame_id > 2 * n + 1) return fail(ABRB_EFRAME, "abrb_osc_generate: invalid frame id");
   if ((target_stride != 0 && target_stride != 6) || (tv && tv_stride != 0 && tv_stride != 6))
     return fail(ABRB_EINVAL, "abrb_osc_generate: stride must be 0 (broadcast) or 6");
+  if ((c->params.ki != 0.0) != (ierr != nullptr))
+    return fail(ABRB_EINVAL, "abrb_osc_generate: integrated_error must be given if and only if ki != 0");
   if (B == 0) return ABRB_OK;
-  if (!q || !dq || !target || !u) return fail(ABRB_EINVAL, "abrb_osc_generate: NULL q/dq/target/u");
-  const void *ptrs[] = {q, dq, u, train};
+  if (!q || !dq || !target || (!u && !gather)) return fail(ABRB_EINVAL, "abrb_osc_generate: NULL q/dq/target/u");
+  const void *ptrs[] = {q, dq, target, tv, u, train, ierr};
   for (const void *p : ptrs)
-    if (p && !aligned16(p)) return fail(ABRB_EINVAL, "abrb_osc_generate: pointers must be 16-byte aligned");
+    if (p && !aligned_elem(p, f32)) return fail(ABRB_EINVAL, "abrb_osc_generate: misaligned pointer");
   int rc = ensure_device();
   if (rc) return rc;
   OscCall k{frame_id, x_off, q, dq, target, tv, target_stride, tv_stride, u, train, B, f32, (cudaStream_t)stream};
-  int qe = 0;
-  const SlowQueue sq = slow_queue_for(c, B, (cudaStream_t)stream, &qe);
-  if (qe) return cuda_fail(qe, "abrb_osc_generate (two-launch workspace)");
-  k.queue = sq.buf;
-  k.records = sq.records;
-  k.rec_stride = sq.cap;
+  k.ierr = ierr;
+  k.gather = gather;
   int e = cudaErrorInvalidValue;
   switch (n) {
 #define X(j) case j: e = launch_osc<j>(c->model->host, c->params, k); break;
@@ -367,100 +391,292 @@ static int osc_generate(const abrb_osc *c, int frame_id, const double *x_off, co
 
 int abrb_osc_generate_f64(const abrb_osc *c, int frame_id, const double *x_off, const double *q, const double *dq,
                           const double *target, int target_stride, const double *target_velocity, int tv_stride,
-                          double *u, double *training_signal, int64_t B, void *stream) {
+                          double *u, double *training_signal, double *integrated_error, int64_t B, void *stream) {
   return osc_generate(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride, u,
-                      training_signal, B, stream, false);
+                      training_signal, integrated_error, B, stream, false);
 }
 int abrb_osc_generate_f32(const abrb_osc *c, int frame_id, const double *x_off, const float *q, const float *dq,
                           const float *target, int target_stride, const float *target_velocity, int tv_stride,
-                          float *u, float *training_signal, int64_t B, void *stream) {
+                          float *u, float *training_signal, float *integrated_error, int64_t B, void *stream) {
   return osc_generate(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride, u,
-                      training_signal, B, stream, true);
+                      training_signal, integrated_error, B, stream, true);
 }
 
-static int osc_generate_host(const abrb_osc *c, int frame_id, const double *x_off, const void *q, const void *dq,
-                             const void *target, int target_stride, const void *tv, int tv_stride, void *u,
-                             void *train, int64_t B, bool f32) {
+// Host-pointer path.  One call = a chunked pipeline on the slot's two streams: every chunk carries its own H2D copies,
+// its kernel launch and its D2H copies on ONE stream, consecutive chunks alternate streams, so chunk k+1's H2D overlaps
+// chunk k's kernel and D2H.  The call returns as soon as everything is enqueued; abrb_osc_host_wait() (or the
+// synchronous wrappers below) waits for the slot.  Measured on B200 (tools/dbg/e2e_probe.py, UR5 6-DOF fp64,
+// B = 65536): 1 chunk 347 us, 2 chunks 306 us, 3: 310, 4: 330, 8: 373 — every chunk costs ~20 us of copy / launch
+// overheads, so two chunks up to ~200 k states and four above.
+static int osc_generate_host_async(const abrb_osc *c, int frame_id, const double *x_off, const void *q, const void *dq,
+                                   const void *target, int target_stride, const void *tv, int tv_stride, void *u,
+                                   void *train, void *ierr, int64_t B, int slot, bool f32) {
   if (!c) return fail(ABRB_EINVAL, "abrb_osc_generate_host: NULL controller");
   if (B < 0) return fail(ABRB_EINVAL, "abrb_osc_generate_host: B < 0");
+  if (slot < 0 || slot >= kSlots) return fail(ABRB_EINVAL, "abrb_osc_generate_host: slot must be 0 or 1");
+  if ((c->params.ki != 0.0) != (ierr != nullptr))
+    return fail(ABRB_EINVAL, "abrb_osc_generate_host: integrated_error must be given if and only if ki != 0");
   if (B == 0) return ABRB_OK;
   if (!q || !dq || !target || !u) return fail(ABRB_EINVAL, "abrb_osc_generate_host: NULL q/dq/target/u");
   int rc = ensure_device();
   if (rc) return rc;
-  const size_t es = f32 ? 4 : 8, n = (size_t)c->model->host.n;
-  const size_t sz_state = (size_t)B * n * es;
-  const size_t sz_t = (target_stride ? (size_t)B : 1) * 6 * es, sz_tv = tv ? (tv_stride ? (size_t)B : 1) * 6 * es : 0;
-  int e = g_ws.ensure(4 * align_up(sz_state) + align_up(sz_t) + align_up(sz_tv) + 256);
+  int e = g_ws.bind();
   if (e) return cuda_fail(e, "abrb_osc_generate_host(workspace)");
-  char *base = static_cast<char *>(g_ws.ptr);
+  e = g_ws.wait_slot(slot);  // a slot is reused only after its previous batch has left it
+  if (e) return cuda_fail(e, "abrb_osc_generate_host(previous batch of this slot)");
+  const size_t es = f32 ? 4 : 8, n = (size_t)c->model->host.n;
+  const size_t sz_state = (size_t)B * n * es, sz_six = (size_t)B * 6 * es;
+  const size_t sz_t = target_stride ? sz_six : 6 * es, sz_tv = tv ? (tv_stride ? sz_six : 6 * es) : 0;
+  e = g_ws.ensure_slot(slot, 4 * align_up(sz_state) + align_up(sz_t) + align_up(sz_tv) + (ierr ? align_up(sz_six) : 0) + 256);
+  if (e) return cuda_fail(e, "abrb_osc_generate_host(workspace)");
+  Workspace::Slot &sl = g_ws.slots[slot];
+  char *base = static_cast<char *>(sl.ptr);
   size_t off = 0;
   auto take = [&](size_t bytes) { char *p = base + off; off += align_up(bytes); return (void *)p; };
   void *d_q = take(sz_state), *d_dq = take(sz_state), *d_u = take(sz_state), *d_tr = take(sz_state);
-  void *d_t = take(sz_t), *d_tv = tv ? take(sz_tv) : nullptr;
-  // Chunked 3-stage pipeline over three streams: the H2D copy of chunk c+1 overlaps the kernel of chunk c and the
-  // D2H copy of chunk c-1 (the copy engines are full duplex), so a large batch costs ~max(H2D, kernel, D2H).
+  void *d_t = take(sz_t), *d_tv = tv ? take(sz_tv) : nullptr, *d_ie = ierr ? take(sz_six) : nullptr;
   const size_t row = n * es;
-  static const int64_t chunk_env = [] {  // tuning knob: states per pipeline chunk
-    const char *v = std::getenv("ABRB_HOST_CHUNK");
-    return v ? (int64_t)std::atoll(v) : (int64_t)0;
-  }();
-  // measured on B200 (tools/dbg/e2e_probe.py, UR5 6-DOF fp64, B = 65536): 1 chunk 347 us, 2 chunks 306 us, 3: 310,
-  // 4: 330, 8: 373 — every chunk costs ~20 us of copy/launch overheads, so two chunks up to ~200 k states, four above
   int64_t chunk = B < 49152 ? B : ((B + (B <= 196608 ? 1 : 3)) / (B <= 196608 ? 2 : 4) + 127) / 128 * 128;
-  if (chunk_env > 0) chunk = (chunk_env < B ? chunk_env : B + 127) / 128 * 128;
+  if (c->host_chunk > 0) chunk = (c->host_chunk < B ? c->host_chunk : B + 127) / 128 * 128;
   if (chunk <= 0) chunk = B;
-  cudaError_t ce = cudaSuccess;
-  if (!target_stride)
-    ABRB_CU(cudaMemcpyAsync(d_t, target, sz_t, cudaMemcpyHostToDevice, g_ws.stream), "abrb_osc_generate_host(target)");
-  if (tv && !tv_stride)
-    ABRB_CU(cudaMemcpyAsync(d_tv, tv, sz_tv, cudaMemcpyHostToDevice, g_ws.stream), "abrb_osc_generate_host(target_velocity)");
-  if (!target_stride || (tv && !tv_stride)) {  // broadcast rows must be resident before any lane starts
-    ce = cudaStreamSynchronize(g_ws.stream);
-    if (ce) return cuda_fail(ce, "abrb_osc_generate_host");
+  const int n_chunks = (int)((B + chunk - 1) / chunk);
+  sl.used = n_chunks < kLanes ? n_chunks : kLanes;
+  // any failure below leaves copies in flight into the caller's buffers: drain the slot before reporting it
+  auto bail = [&](int code) {
+    g_ws.wait_slot(slot);
+    return code;
+  };
+#define ABRB_CUH(call, where)                                    \
+  do {                                                            \
+    cudaError_t e_ = (call);                                      \
+    if (e_ != cudaSuccess) return bail(cuda_fail((int)e_, where)); \
+  } while (0)
+  const char *where = "abrb_osc_generate_host(copy in)";
+  if (!target_stride || (tv && !tv_stride)) {
+    // broadcast rows go first on lane 0; the other lane waits for just these two small copies (the event is recorded
+    // before chunk 0's own copies are enqueued, so the chunks still overlap)
+    if (!target_stride) ABRB_CUH(cudaMemcpyAsync(d_t, target, sz_t, cudaMemcpyHostToDevice, sl.lanes[0]), where);
+    if (tv && !tv_stride) ABRB_CUH(cudaMemcpyAsync(d_tv, tv, sz_tv, cudaMemcpyHostToDevice, sl.lanes[0]), where);
+    if (sl.used > 1) {
+      cudaEvent_t ev;
+      ABRB_CUH(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), where);
+      cudaError_t e1 = cudaEventRecord(ev, sl.lanes[0]);
+      for (int l = 1; l < sl.used && e1 == cudaSuccess; ++l) e1 = cudaStreamWaitEvent(sl.lanes[l], ev, 0);
+      cudaEventDestroy(ev);  // released once the recorded work has completed
+      if (e1 != cudaSuccess) return bail(cuda_fail((int)e1, where));
+    }
   }
   int lane = 0;
-  for (int64_t b0 = 0; b0 < B; b0 += chunk, lane = (lane + 1) % 3) {
+  for (int64_t b0 = 0; b0 < B; b0 += chunk, lane = (lane + 1) % kLanes) {
     const int64_t nb = B - b0 < chunk ? B - b0 : chunk;
-    cudaStream_t s = g_ws.lanes[lane];
+    cudaStream_t s = sl.lanes[lane];
     const size_t off_s = (size_t)b0 * row, off_t = (size_t)b0 * 6 * es;
     auto at = [](const void *p, size_t o) { return (const void *)((const char *)p + o); };
     auto atw = [](void *p, size_t o) { return (void *)((char *)p + o); };
-    const char *where = "abrb_osc_generate_host(copy in)";
-    ABRB_CU(cudaMemcpyAsync(atw(d_q, off_s), at(q, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, s), where);
-    ABRB_CU(cudaMemcpyAsync(atw(d_dq, off_s), at(dq, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, s), where);
+    ABRB_CUH(cudaMemcpyAsync(atw(d_q, off_s), at(q, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, s), where);
+    ABRB_CUH(cudaMemcpyAsync(atw(d_dq, off_s), at(dq, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, s), where);
     if (target_stride)
-      ABRB_CU(cudaMemcpyAsync(atw(d_t, off_t), at(target, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s), where);
+      ABRB_CUH(cudaMemcpyAsync(atw(d_t, off_t), at(target, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s), where);
     if (tv && tv_stride)
-      ABRB_CU(cudaMemcpyAsync(atw(d_tv, off_t), at(tv, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s), where);
+      ABRB_CUH(cudaMemcpyAsync(atw(d_tv, off_t), at(tv, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s), where);
+    if (ierr)
+      ABRB_CUH(cudaMemcpyAsync(atw(d_ie, off_t), at(ierr, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s), where);
     rc = osc_generate(c, frame_id, x_off, at(d_q, off_s), at(d_dq, off_s), target_stride ? at(d_t, off_t) : d_t,
                       target_stride, tv ? (tv_stride ? at(d_tv, off_t) : d_tv) : nullptr, tv_stride, atw(d_u, off_s),
-                      train ? atw(d_tr, off_s) : nullptr, nb, s, f32);
-    if (rc) return rc;
-    ABRB_CU(cudaMemcpyAsync(atw(u, off_s), at(d_u, off_s), (size_t)nb * row, cudaMemcpyDeviceToHost, s),
-            "abrb_osc_generate_host(result)");
+                      train ? atw(d_tr, off_s) : nullptr, ierr ? atw(d_ie, off_t) : nullptr, nb, s, f32);
+    if (rc) return bail(rc);
+    ABRB_CUH(cudaMemcpyAsync(atw(u, off_s), at(d_u, off_s), (size_t)nb * row, cudaMemcpyDeviceToHost, s),
+             "abrb_osc_generate_host(result)");
     if (train)
-      ABRB_CU(cudaMemcpyAsync(atw(train, off_s), at(d_tr, off_s), (size_t)nb * row, cudaMemcpyDeviceToHost, s),
-              "abrb_osc_generate_host(training signal)");
+      ABRB_CUH(cudaMemcpyAsync(atw(train, off_s), at(d_tr, off_s), (size_t)nb * row, cudaMemcpyDeviceToHost, s),
+               "abrb_osc_generate_host(training signal)");
+    if (ierr)
+      ABRB_CUH(cudaMemcpyAsync(atw(ierr, off_t), at(d_ie, off_t), (size_t)nb * 6 * es, cudaMemcpyDeviceToHost, s),
+               "abrb_osc_generate_host(integrated error)");
   }
-  const int used = (int)((B + chunk - 1) / chunk) < 3 ? (int)((B + chunk - 1) / chunk) : 3;
-  for (int l = 0; l < used; ++l) {
-    ce = cudaStreamSynchronize(g_ws.lanes[l]);
-    if (ce) return cuda_fail(ce, "abrb_osc_generate_host");
-  }
+#undef ABRB_CUH
   return ABRB_OK;
 }
 
+int abrb_osc_host_wait(const abrb_osc *c, int slot) {
+  if (!c) return fail(ABRB_EINVAL, "abrb_osc_host_wait: NULL controller");
+  if (slot < 0 || slot >= kSlots) return fail(ABRB_EINVAL, "abrb_osc_host_wait: slot must be 0 or 1");
+  if (g_ws.dev < 0) return ABRB_OK;  // nothing was ever enqueued from this thread
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != g_ws.dev) cudaSetDevice(g_ws.dev);
+  const int e = g_ws.wait_slot(slot);
+  if (cur != g_ws.dev) cudaSetDevice(cur);
+  return e ? cuda_fail(e, "abrb_osc_host_wait") : ABRB_OK;
+}
+
+int abrb_osc_generate_host_async_f64(const abrb_osc *c, int frame_id, const double *x_off, const double *q,
+                                     const double *dq, const double *target, int target_stride,
+                                     const double *target_velocity, int tv_stride, double *u, double *training_signal,
+                                     double *integrated_error, int64_t B, int slot) {
+  return osc_generate_host_async(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride, u,
+                                 training_signal, integrated_error, B, slot, false);
+}
+int abrb_osc_generate_host_async_f32(const abrb_osc *c, int frame_id, const double *x_off, const float *q,
+                                     const float *dq, const float *target, int target_stride,
+                                     const float *target_velocity, int tv_stride, float *u, float *training_signal,
+                                     float *integrated_error, int64_t B, int slot) {
+  return osc_generate_host_async(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride, u,
+                                 training_signal, integrated_error, B, slot, true);
+}
 int abrb_osc_generate_host_f64(const abrb_osc *c, int frame_id, const double *x_off, const double *q, const double *dq,
                                const double *target, int target_stride, const double *target_velocity,
-                               int tv_stride, double *u, double *training_signal, int64_t B) {
-  return osc_generate_host(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride, u,
-                           training_signal, B, false);
+                               int tv_stride, double *u, double *training_signal, double *integrated_error,
+                               int64_t B) {
+  const int rc = osc_generate_host_async(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride,
+                                         u, training_signal, integrated_error, B, 0, false);
+  return rc ? rc : abrb_osc_host_wait(c, 0);
 }
 int abrb_osc_generate_host_f32(const abrb_osc *c, int frame_id, const double *x_off, const float *q, const float *dq,
                                const float *target, int target_stride, const float *target_velocity, int tv_stride,
-                               float *u, float *training_signal, int64_t B) {
-  return osc_generate_host(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride, u,
-                           training_signal, B, true);
+                               float *u, float *training_signal, float *integrated_error, int64_t B) {
+  const int rc = osc_generate_host_async(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride,
+                                         u, training_signal, integrated_error, B, 0, true);
+  return rc ? rc : abrb_osc_host_wait(c, 0);
+}
+
+// ------------------------------------------------------------------------------------------------ peer gather
+int abrb_gather_create(int rank, int world, int64_t bytes_per_buffer, int n_buffers, abrb_gather **out) {
+  if (!out) return fail(ABRB_EINVAL, "abrb_gather_create: NULL argument");
+  *out = nullptr;
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || bytes_per_buffer <= 0 || n_buffers < 1 || n_buffers > 8)
+    return fail(ABRB_EINVAL, "abrb_gather_create: need 0 <= rank < world <= 8, bytes > 0, 1 <= n_buffers <= 8");
+  int rc = ensure_device();
+  if (rc) return rc;
+  abrb_gather *g = new (std::nothrow) abrb_gather;
+  if (!g) return fail(ABRB_ENOMEM, "abrb_gather_create: out of memory");
+  g->rank = rank;
+  g->world = world;
+  g->n_buffers = n_buffers;
+  g->bytes = align_up((size_t)bytes_per_buffer);
+  g->flag_off = g->bytes * (size_t)n_buffers;
+  g->counter_off = g->flag_off + align_up(kMaxPeers * sizeof(unsigned long long));
+  cudaGetDevice(&g->dev);
+  const size_t total = g->counter_off + 256;
+  cudaError_t e = cudaMalloc(&g->peer[rank], total);
+  if (e == cudaSuccess) e = cudaMemset(static_cast<char *>(g->peer[rank]) + g->flag_off, 0, total - g->flag_off);
+  if (e != cudaSuccess) {
+    cudaFree(g->peer[rank]);
+    delete g;
+    return cuda_fail((int)e, "abrb_gather_create");
+  }
+  *out = g;
+  return ABRB_OK;
+}
+
+int abrb_gather_export(const abrb_gather *g, unsigned char handle[64]) {
+  if (!g || !handle) return fail(ABRB_EINVAL, "abrb_gather_export: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, g->peer[g->rank]);
+  if (e != cudaSuccess) return cuda_fail((int)e, "abrb_gather_export");
+  std::memcpy(handle, &h, 64);
+  return ABRB_OK;
+}
+
+int abrb_gather_import(abrb_gather *g, int peer_rank, const unsigned char handle[64]) {
+  if (!g || !handle) return fail(ABRB_EINVAL, "abrb_gather_import: NULL argument");
+  if (peer_rank < 0 || peer_rank >= g->world || peer_rank == g->rank || g->peer[peer_rank])
+    return fail(ABRB_EINVAL, "abrb_gather_import: bad or repeated peer rank");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(&g->peer[peer_rank], h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    g->peer[peer_rank] = nullptr;
+    return cuda_fail((int)e, "abrb_gather_import (is peer access between the two GPUs possible?)");
+  }
+  g->imported[peer_rank] = true;
+  return ABRB_OK;
+}
+
+void *abrb_gather_buffer(const abrb_gather *g, int buffer_index) {
+  if (!g || buffer_index < 0 || buffer_index >= g->n_buffers) return nullptr;
+  return static_cast<char *>(g->peer[g->rank]) + (size_t)buffer_index * g->bytes;
+}
+
+int abrb_gather_destroy(abrb_gather *g) {
+  if (!g) return ABRB_OK;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  cudaSetDevice(g->dev);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < g->world; ++r)
+    if (g->imported[r]) cudaIpcCloseMemHandle(g->peer[r]);
+  cudaFree(g->peer[g->rank]);
+  cudaSetDevice(cur);
+  delete g;
+  return ABRB_OK;
+}
+
+int abrb_gather_wait(abrb_gather *g, void *stream) {
+  if (!g) return fail(ABRB_EINVAL, "abrb_gather_wait: NULL argument");
+  char *mine = static_cast<char *>(g->peer[g->rank]);
+  gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long *>(mine + g->flag_off),
+                                                          g->world, g->epoch,
+                                                          reinterpret_cast<int *>(mine + g->counter_off + 64));
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  return e ? cuda_fail((int)e, "abrb_gather_wait") : ABRB_OK;
+}
+
+int abrb_gather_status(const abrb_gather *g) {  // after a stream synchronise: 1 if a wait ever timed out
+  if (!g) return fail(ABRB_EINVAL, "abrb_gather_status: NULL argument");
+  int st = 0;
+  cudaError_t e = cudaMemcpy(&st, static_cast<char *>(g->peer[g->rank]) + g->counter_off + 64, sizeof st, cudaMemcpyDeviceToHost);
+  return e ? cuda_fail((int)e, "abrb_gather_status") : st;
+}
+
+static int osc_generate_gather(const abrb_osc *c, int frame_id, const double *x_off, const void *q, const void *dq,
+                               const void *target, int target_stride, const void *tv, int tv_stride, void *u,
+                               void *train, void *ierr, int64_t B, abrb_gather *g, int buffer_index, int64_t row0,
+                               void *stream, bool f32) {
+  if (!c || !g) return fail(ABRB_EINVAL, "abrb_osc_generate_gather: NULL argument");
+  if (buffer_index < 0 || buffer_index >= g->n_buffers || row0 < 0 || B < 0)
+    return fail(ABRB_EINVAL, "abrb_osc_generate_gather: bad buffer index / row offset");
+  const size_t es = f32 ? 4 : 8, n = (size_t)c->model->host.n;
+  if ((size_t)(row0 + B) * n * es > g->bytes)
+    return fail(ABRB_EINVAL, "abrb_osc_generate_gather: rows do not fit the gather buffer");
+  for (int r = 0; r < g->world; ++r)
+    if (!g->peer[r]) return fail(ABRB_EINVAL, "abrb_osc_generate_gather: not every peer has been imported");
+  GatherArgs ga;
+  ga.n_peer = g->world;
+  ga.row0 = row0;
+  ga.epoch = ++g->epoch;
+  for (int r = 0; r < g->world; ++r) {
+    char *base = static_cast<char *>(g->peer[r]);
+    ga.peer_u[r] = base + (size_t)buffer_index * g->bytes;
+    ga.peer_flag[r] = reinterpret_cast<unsigned long long *>(base + g->flag_off) + g->rank;
+  }
+  ga.cta_counter = reinterpret_cast<unsigned *>(static_cast<char *>(g->peer[g->rank]) + g->counter_off);
+  if (B == 0) {  // an empty shard still has to publish its epoch: the peers wait for it
+    for (int r = 0; r < g->world; ++r) {
+      cudaError_t e = cudaMemcpyAsync(ga.peer_flag[r], &g->epoch, sizeof(unsigned long long), cudaMemcpyHostToDevice,
+                                      (cudaStream_t)stream);
+      if (e != cudaSuccess) return cuda_fail((int)e, "abrb_osc_generate_gather(empty shard)");
+    }
+    return ABRB_OK;
+  }
+  return osc_generate(c, frame_id, x_off, q, dq, target, target_stride, tv, tv_stride, u, train, ierr, B, stream, f32, &ga);
+}
+
+int abrb_osc_generate_gather_f64(const abrb_osc *c, int frame_id, const double *x_off, const double *q, const double *dq,
+                                 const double *target, int target_stride, const double *target_velocity, int tv_stride,
+                                 double *u, double *training_signal, double *integrated_error, int64_t B,
+                                 abrb_gather *g, int buffer_index, int64_t row0, void *stream) {
+  return osc_generate_gather(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride, u,
+                             training_signal, integrated_error, B, g, buffer_index, row0, stream, false);
+}
+int abrb_osc_generate_gather_f32(const abrb_osc *c, int frame_id, const double *x_off, const float *q, const float *dq,
+                                 const float *target, int target_stride, const float *target_velocity, int tv_stride,
+                                 float *u, float *training_signal, float *integrated_error, int64_t B, abrb_gather *g,
+                                 int buffer_index, int64_t row0, void *stream) {
+  return osc_generate_gather(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride, u,
+                             training_signal, integrated_error, B, g, buffer_index, row0, stream, true);
 }
 
 // ------------------------------------------------------------------------------------------------ null
@@ -472,8 +688,8 @@ static int null_generate(const abrb_model *m, const abrb_null_params *p, const v
   if (!e.empty()) return fail(ABRB_EUNSUP, "abrb_null_generate: " + e);
   if (B == 0) return ABRB_OK;
   if (!q || !dq || !u) return fail(ABRB_EINVAL, "abrb_null_generate: NULL q/dq/u");
-  if (!aligned16(q) || !aligned16(dq) || !aligned16(u))
-    return fail(ABRB_EINVAL, "abrb_null_generate: pointers must be 16-byte aligned");
+  if (!aligned_elem(q, f32) || !aligned_elem(dq, f32) || !aligned_elem(u, f32))
+    return fail(ABRB_EINVAL, "abrb_null_generate: misaligned pointer");
   int rc = ensure_device();
   if (rc) return rc;
   NullCall k{q, dq, u, B, f32, (cudaStream_t)stream};
@@ -509,8 +725,8 @@ static int sliding_generate(const abrb_model *m, double kd, double lamb, int car
     return fail(ABRB_EINVAL, "abrb_sliding_generate: stride must be 0 (broadcast) or the row width (3 or n_joints)");
   if (B == 0) return ABRB_OK;
   if (!q || !dq || !target || !u) return fail(ABRB_EINVAL, "abrb_sliding_generate: NULL q/dq/target/u");
-  if (!aligned16(q) || !aligned16(dq) || !aligned16(u) || (s && !aligned16(s)))
-    return fail(ABRB_EINVAL, "abrb_sliding_generate: pointers must be 16-byte aligned");
+  if (!aligned_elem(q, f32) || !aligned_elem(dq, f32) || !aligned_elem(u, f32) || (s && !aligned_elem(s, f32)))
+    return fail(ABRB_EINVAL, "abrb_sliding_generate: misaligned pointer");
   int rc = ensure_device();
   if (rc) return rc;
   SlidingCall k{kd, lamb, cartesian, frame_id, x_off, q, dq, target, tv, ta, target_stride, tv_stride, ta_stride,
@@ -549,8 +765,8 @@ static int ik_path(const abrb_model *m, double max_dx, double max_dr, double max
   if (target_stride != 0 && target_stride != 6) return fail(ABRB_EINVAL, "abrb_ik_path: stride must be 0 or 6");
   if (B == 0 || steps == 0) return ABRB_OK;
   if (!position || !target || !pos_path || !vel_path) return fail(ABRB_EINVAL, "abrb_ik_path: NULL argument");
-  if (!aligned16(position) || !aligned16(pos_path) || !aligned16(vel_path))
-    return fail(ABRB_EINVAL, "abrb_ik_path: pointers must be 16-byte aligned");
+  if (!aligned_elem(position, f32) || !aligned_elem(pos_path, f32) || !aligned_elem(vel_path, f32))
+    return fail(ABRB_EINVAL, "abrb_ik_path: misaligned pointer");
   int rc = ensure_device();
   if (rc) return rc;
   IkCall k{max_dx, max_dr, max_dq, dt, method, steps, position, target, target_stride, pos_path, vel_path, B, f32,
@@ -589,8 +805,8 @@ static int ctrl_generate(const abrb_model *m, int kind, double kp, double kv, in
   if (B == 0) return ABRB_OK;
   if (!q || !u || (kind == 0 && (!dq || !target)) || (kind == 1 && fb && !dq))
     return fail(ABRB_EINVAL, std::string(who) + ": NULL q/dq/target/u");
-  if (!aligned16(q) || !aligned16(u) || (dq && !aligned16(dq)))
-    return fail(ABRB_EINVAL, std::string(who) + ": pointers must be 16-byte aligned");
+  if (!aligned_elem(q, f32) || !aligned_elem(u, f32) || (dq && !aligned_elem(dq, f32)))
+    return fail(ABRB_EINVAL, std::string(who) + ": misaligned pointer");
   int rc = ensure_device();
   if (rc) return rc;
   CtrlCall k{kind, kp, kv, fa, fb, q, dq, target, tv, target_stride, tv_stride, u, B, f32, (cudaStream_t)stream};
@@ -628,21 +844,24 @@ int abrb_floating_generate_f32(const abrb_model *m, int task_space, int dynamic,
 
 // ------------------------------------------------------------------------------------------------ rollout
 static int osc_rollout(const abrb_osc *c, int frame_id, const double *x_off, void *q, void *dq, const void *target,
-                       int target_stride, int steps, double dt, void *q_traj, void *dq_traj, void *u_traj, int64_t B,
-                       void *stream, bool f32) {
+                       int target_stride, int steps, double dt, void *q_traj, void *dq_traj, void *u_traj, void *ierr,
+                       int64_t B, void *stream, bool f32) {
   if (!c) return fail(ABRB_EINVAL, "abrb_osc_rollout: NULL controller");
   if (B < 0 || steps < 0) return fail(ABRB_EINVAL, "abrb_osc_rollout: B < 0 or steps < 0");
   const int n = c->model->host.n;
   if (frame_id < 0 || frame_id > 2 * n + 1) return fail(ABRB_EFRAME, "abrb_osc_rollout: invalid frame id");
   if (target_stride != 0 && target_stride != 6) return fail(ABRB_EINVAL, "abrb_osc_rollout: stride must be 0 or 6");
+  if ((c->params.ki != 0.0) != (ierr != nullptr))
+    return fail(ABRB_EINVAL, "abrb_osc_rollout: integrated_error must be given if and only if ki != 0");
   if (B == 0 || steps == 0) return ABRB_OK;
   if (!q || !dq || !target) return fail(ABRB_EINVAL, "abrb_osc_rollout: NULL q/dq/target");
-  const void *ptrs[] = {q, dq, q_traj, dq_traj, u_traj};
+  const void *ptrs[] = {q, dq, target, q_traj, dq_traj, u_traj, ierr};
   for (const void *p : ptrs)
-    if (p && !aligned16(p)) return fail(ABRB_EINVAL, "abrb_osc_rollout: pointers must be 16-byte aligned");
+    if (p && !aligned_elem(p, f32)) return fail(ABRB_EINVAL, "abrb_osc_rollout: misaligned pointer");
   int rc = ensure_device();
   if (rc) return rc;
   RolloutCall k{frame_id, x_off, q, dq, target, target_stride, steps, dt, q_traj, dq_traj, u_traj, B, f32, (cudaStream_t)stream};
+  k.ierr = ierr;
   int e = cudaErrorInvalidValue;
   switch (n) {
 #define X(j) case j: e = launch_rollout<j>(c->model->host, c->params, k); break;
@@ -654,13 +873,15 @@ static int osc_rollout(const abrb_osc *c, int frame_id, const double *x_off, voi
 
 int abrb_osc_rollout_f64(const abrb_osc *c, int frame_id, const double *x_off, double *q, double *dq,
                          const double *target, int target_stride, int steps, double dt, double *q_traj,
-                         double *dq_traj, double *u_traj, int64_t B, void *stream) {
-  return osc_rollout(c, frame_id, x_off, q, dq, target, target_stride, steps, dt, q_traj, dq_traj, u_traj, B, stream, false);
+                         double *dq_traj, double *u_traj, double *integrated_error, int64_t B, void *stream) {
+  return osc_rollout(c, frame_id, x_off, q, dq, target, target_stride, steps, dt, q_traj, dq_traj, u_traj,
+                     integrated_error, B, stream, false);
 }
 int abrb_osc_rollout_f32(const abrb_osc *c, int frame_id, const double *x_off, float *q, float *dq, const float *target,
                          int target_stride, int steps, double dt, float *q_traj, float *dq_traj, float *u_traj,
-                         int64_t B, void *stream) {
-  return osc_rollout(c, frame_id, x_off, q, dq, target, target_stride, steps, dt, q_traj, dq_traj, u_traj, B, stream, true);
+                         float *integrated_error, int64_t B, void *stream) {
+  return osc_rollout(c, frame_id, x_off, q, dq, target, target_stride, steps, dt, q_traj, dq_traj, u_traj,
+                     integrated_error, B, stream, true);
 }
 
 }  // extern "C"

@@ -9,6 +9,7 @@
 
 #include <atomic>
 
+#include "abrb_coop.cuh"
 #include "abrb_launch.hpp"
 #include "abrb_osc.cuh"
 #include "abrb_rbd.cuh"
@@ -131,12 +132,16 @@ struct RbdArgs {
 };
 
 // shared memory per warp: [ kinematic scratch (KSMEM only): kSlots x 32 ][ staging tile: kPitch x max record ]
-template <typename T, int N, bool ORTHO, bool KSMEM, int MAXREC>
+//                        [ exchange area of the cooperative pseudo-inverse (OSC kernels only): XCH x 32 ]
+template <typename T, int N, bool ORTHO, bool KSMEM, int MAXREC, int XCH = 0>
 struct WarpSmem {
   static constexpr int kKin = 32 * KinSel<T, N, ORTHO, KSMEM>::kSlots;
   static constexpr int kTile = kPitch * (MAXREC < kChunk ? MAXREC : kChunk);
-  static constexpr int kElems = kKin + kTile;
+  static constexpr int kXch = 32 * XCH;
+  static constexpr int kElems = kKin + kTile + kXch;
 };
+template <typename T, int N, bool ORTHO, int KD, bool KSMEM>
+struct OscSmem : WarpSmem<T, N, ORTHO, KSMEM, (N > 6 ? N : 6), CoopLayout<N, KD, !KSMEM>::kSlots> {};
 
 template <typename T, int N, bool ORTHO, bool DYN, bool CMAT, bool XTRA, bool KSMEM>
 __global__ void __launch_bounds__(kBlock, MinBlocks<T>::value)
@@ -184,55 +189,36 @@ template <typename T>
 struct OscArgs {
   const T *q, *dq, *target, *tv;
   T *u, *train;
+  T *ierr;  // (B, 6) integrated task-space error, updated in place (ki != 0), or nullptr
   int64_t B;
   int target_stride, tv_stride;
-  // two-launch mode: queue[0] = number of deferred states, queue[1] = CTA ticket, queue[4 + i] = state index of
-  // record i; records[f * rec_stride + i] = value f of record i (OscRecord<N,KD> layout, abrb_osc.cuh)
-  int *queue;
-  T *records;
-  int64_t rec_stride;
+  GatherArgs g;  // n_peer > 0: also store u into every rank's gathered array (peer memory over NVLink)
 };
 
-template <typename T>
-struct DevRecord {
-  int *queue;
-  T *store;
-  int64_t stride, state;
-  int pos;
-  __device__ void begin() {
-    pos = atomicAdd(queue, 1);
-    queue[4 + pos] = (int)state;
-  }
-  template <typename V>
-  __device__ void put(int i, V v) { store[(int64_t)i * stride + pos] = T(v); }
-  __device__ T get(int i) const { return store[(int64_t)i * stride + pos]; }
-};
-
-// DEFER = false: one pass, the states that need the truncating pseudo-inverse take that route in line.  For random
-// UR5 6-DOF states that is 3.8 % of the states but 70 % of the warps, each of which then serialises a long divergent
-// path for one or two lanes (41 us without those states, 77 us with them at B = 65 536).
-// DEFER = true (first launch of the two-launch mode): the instantiation has no truncating code at all; such a state
-// writes a record of its intermediate results (osc_eval MODE 1) and osc_finish_kernel completes it.
-template <typename T, int N, bool ORTHO, int KD, bool KSMEM, bool DEFER>
+// One pass over the batch.  The states whose task-space inertia needs the truncating pseudo-inverse (3.8 % of
+// uniformly random UR5 6-DOF states: 70 % of the warps hold one) are finished by their warp cooperatively
+// (abrb_coop.cuh): every lane reaches WarpCoop::pinv together.
+template <typename T, int N, bool ORTHO, int KD, bool KSMEM>
 __global__ void __launch_bounds__(kBlock, MinBlocks<T>::value)
 osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
            const __grid_constant__ OscArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef KinSel<T, N, ORTHO, KSMEM> KS;
-  typedef WarpSmem<T, N, ORTHO, KSMEM, N> WS;
+  typedef OscSmem<T, N, ORTHO, KD, KSMEM> WS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T *region = reinterpret_cast<T *>(smem_raw) + warp * WS::kElems;
   T *stage = region + WS::kKin;
   typename KS::type K;
   KS::bind(K, region, lane);
+  WarpCoop<T, N, KD, typename KS::type> coop{region + WS::kKin + WS::kTile, region, lane};
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
-    // no early exit: every thread of the CTA takes part in the phase barriers; idle lanes / warps redo a valid state
+    // no early exit: every lane of a warp takes part in the cooperative step; idle lanes / warps redo a valid state
     const int64_t warp_b0 = base + warp * 32;
     const int64_t rem = a.B - warp_b0;
     const int nvalid = rem < 32 ? (rem > 0 ? (int)rem : 0) : 32;
     const int64_t bb = warp_b0 + (lane < nvalid ? lane : nvalid - 1);
     const int64_t b = bb < a.B ? (bb >= 0 ? bb : 0) : a.B - 1;
-    T q[N], dq[N], tg[6], tv[6], u[N], tr[N];
+    T q[N], dq[N], tg[6], tv[6], ie[6], u[N], tr[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       q[k] = a.q[b * N + k];
@@ -242,61 +228,30 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
     for (int c = 0; c < 6; ++c) {
       tg[c] = a.target[b * a.target_stride + c];
       tv[c] = a.tv != nullptr ? a.tv[b * a.tv_stride + c] : T(0);
+      ie[c] = a.ierr != nullptr ? a.ierr[b * 6 + c] : T(0);
     }
-    if (DEFER) {
-      // lanes that only duplicate a valid state (ragged last warp) must not queue it a second time: they get a
-      // state index of -1 and are skipped by the finishing kernel
-      DevRecord<T> rec{a.queue, a.records, a.rec_stride, lane < nvalid ? b : (int64_t)-1, 0};
-      osc_eval<T, N, KD, false, 1>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, u, tr, (T *)nullptr, K, rec);
-    } else {
-      osc_state<T, N, KD, false>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, u, tr, nullptr, K);
-    }
-    store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);  // deferred states: placeholder, rewritten below
+    osc_eval<T, N, KD, false>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, a.ierr != nullptr ? ie : nullptr, u, tr,
+                              (T *)nullptr, K, coop);
+    if (a.u) store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);
     if (a.train) store_records<T, N>(a.train, warp_b0, nvalid, tr, stage, lane);
+    if (a.ierr) store_records<T, 6>(a.ierr, warp_b0, nvalid, ie, stage, lane);
+    // fused all-gather: this tile's rows go to every rank's gathered array while the other warps still compute
+    for (int p = 0; p < a.g.n_peer; ++p)
+      store_records<T, N>(static_cast<T *>(a.g.peer_u[p]), a.g.row0 + warp_b0, nvalid, u, stage, lane);
   }
-}
-
-// Second launch of the two-launch mode: finishes the deferred states from their records (osc_eval MODE 2: truncating
-// pseudo-inverse, J^T, the null-space filter).  One warp per CTA so that the ~2.5 k deferred states of a 65 536-state
-// UR5 batch spread over as many SMs as possible (the launch is latency bound).  The last CTA to finish re-arms the
-// queue for the next call.
-constexpr int kFinishBlock = 32;
-template <typename T, int N, bool ORTHO, int KD, bool KSMEM>
-__global__ void __launch_bounds__(kFinishBlock)
-osc_finish_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
-                  const __grid_constant__ OscArgs<T> a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  typedef KinSel<T, N, ORTHO, KSMEM> KS;
-  const int lane = threadIdx.x;
-  T *region = reinterpret_cast<T *>(smem_raw);
-  typename KS::type K;
-  KS::bind(K, region, lane);
-  const int count = *static_cast<volatile int *>(a.queue);
-  for (int base = blockIdx.x * kFinishBlock; base < count; base += gridDim.x * kFinishBlock) {
-    const int i = base + lane;
-    const bool in_range = i < count;
-    const int pos = in_range ? i : count - 1;
-    const int64_t b = a.queue[4 + pos];
-    T u[N], tr[N];
-    DevRecord<T> rec{a.queue, a.records, a.rec_stride, b, pos};
-    osc_eval<T, N, KD, false, 2>(P, O, (const T *)nullptr, (const T *)nullptr, (const T *)nullptr, (const T *)nullptr, u,
-                                 tr, (T *)nullptr, K, rec);
-    if (in_range && b >= 0) {
-#pragma unroll
-      for (int k = 0; k < N; ++k) {
-        a.u[b * N + k] = u[k];
-        if (a.train) a.train[b * N + k] = tr[k];
+  if (a.g.n_peer > 0) {
+    // completion: once every CTA's peer stores are visible system-wide, the last CTA publishes this launch's epoch
+    // in every rank's flag array; abrb_gather_wait() on the consumer side spins on those flags
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned done = atomicAdd(a.g.cta_counter, 1u);
+      if (done == gridDim.x - 1) {
+        *a.g.cta_counter = 0u;
+        __threadfence_system();
+        for (int p = 0; p < a.g.n_peer; ++p)
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.g.peer_flag[p]), "l"(a.g.epoch) : "memory");
       }
-    }
-  }
-  __syncwarp();
-  if (lane == 0) {
-    __threadfence();
-    const unsigned t = atomicAdd(reinterpret_cast<unsigned *>(a.queue + 1), 1u);
-    if (t == gridDim.x - 1) {  // every CTA has read `count` before it took its ticket
-      a.queue[0] = 0;
-      a.queue[1] = 0;
-      __threadfence();
     }
   }
 }
@@ -306,6 +261,7 @@ struct RolloutArgs {
   T *q, *dq;
   const T *target;
   T *q_traj, *dq_traj, *u_traj;
+  T *ierr;  // (B, 6) integrated task-space error, in/out (ki != 0), or nullptr
   int64_t B;
   int target_stride, steps;
   T dt;
@@ -318,29 +274,34 @@ rollout_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ O
                const __grid_constant__ RolloutArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef KinSel<T, N, ORTHO, KSMEM> KS;
-  typedef WarpSmem<T, N, ORTHO, KSMEM, N> WS;
+  typedef OscSmem<T, N, ORTHO, KD, KSMEM> WS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T *region = reinterpret_cast<T *>(smem_raw) + warp * WS::kElems;
   T *stage = region + WS::kKin;
   typename KS::type K;
   KS::bind(K, region, lane);
+  WarpCoop<T, N, KD, typename KS::type> coop{region + WS::kKin + WS::kTile, region, lane};
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
-    // no early exit (phase barriers inside osc_state): idle lanes / warps redo a valid state and store nothing
+    // no early exit (cooperative step inside osc_eval): idle lanes / warps redo a valid state and store nothing
     const int64_t warp_b0 = base + warp * 32;
     const int64_t rem = a.B - warp_b0;
     const int nvalid = rem < 32 ? (rem > 0 ? (int)rem : 0) : 32;
     const int64_t bb = warp_b0 + (lane < nvalid ? lane : nvalid - 1);
     const int64_t b = bb < a.B ? (bb >= 0 ? bb : 0) : a.B - 1;
-    T q[N], dq[N], tg[6], u[N], acc[N];
+    T q[N], dq[N], tg[6], ie[6], u[N], acc[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       q[k] = a.q[b * N + k];
       dq[k] = a.dq[b * N + k];
     }
 #pragma unroll
-    for (int c = 0; c < 6; ++c) tg[c] = a.target[b * a.target_stride + c];
+    for (int c = 0; c < 6; ++c) {
+      tg[c] = a.target[b * a.target_stride + c];
+      ie[c] = a.ierr != nullptr ? a.ierr[b * 6 + c] : T(0);
+    }
     for (int t = 0; t < a.steps; ++t) {
-      osc_state<T, N, KD, true>(P, O, q, dq, tg, nullptr, u, nullptr, acc, K);
+      osc_eval<T, N, KD, true>(P, O, q, dq, tg, (const T *)nullptr, a.ierr != nullptr ? ie : nullptr, u, (T *)nullptr,
+                               acc, K, coop);
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         dq[k] += acc[k] * a.dt;
@@ -353,6 +314,7 @@ rollout_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ O
     }
     store_records<T, N>(a.q, warp_b0, nvalid, q, stage, lane);
     store_records<T, N>(a.dq, warp_b0, nvalid, dq, stage, lane);
+    if (a.ierr) store_records<T, 6>(a.ierr, warp_b0, nvalid, ie, stage, lane);
   }
 }
 
@@ -608,35 +570,14 @@ int osc_go(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
   a.tv = static_cast<const T *>(c.tv);
   a.u = static_cast<T *>(c.u);
   a.train = static_cast<T *>(c.train);
+  a.ierr = static_cast<T *>(c.ierr);
   a.B = c.B;
   a.target_stride = c.target_stride;
   a.tv_stride = c.tv_stride;
-  a.queue = c.queue;
-  a.records = static_cast<T *>(c.records);
-  a.rec_stride = c.rec_stride;
+  if (c.gather != nullptr) a.g = *c.gather;
   constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32 || ABRB_ROLLED;  // rolled loops index the scratch at run time
-  const size_t smem = (size_t)kWarps * WarpSmem<T, N, ORTHO, KSMEM, N>::kElems * sizeof(T);
-  if constexpr (KD == 6) {
-    if (c.queue != nullptr && c.records != nullptr) {
-      // two launches: everything but the truncating-pinv states, then those states densely packed
-      auto k1 = osc_kernel<T, N, ORTHO, 6, KSMEM, true>;
-      auto k2 = osc_finish_kernel<T, N, ORTHO, 6, KSMEM>;
-      const size_t smem2 = (size_t)WarpSmem<T, N, ORTHO, KSMEM, N>::kElems * sizeof(T);
-      cudaError_t e = set_smem(k1, smem);
-      if (e == cudaSuccess) e = set_smem(k2, smem2);
-      if (e != cudaSuccess) return (int)e;
-      k1<<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, O, a);
-      count_launch();
-      e = cudaGetLastError();
-      if (e != cudaSuccess) return (int)e;
-      const int64_t want = (c.B + kFinishBlock - 1) / kFinishBlock;
-      const int64_t cap = (int64_t)num_sms() * 8;
-      k2<<<(unsigned)(want < cap ? want : cap), kFinishBlock, smem2, c.stream>>>(P, O, a);
-      count_launch();
-      return (int)cudaGetLastError();
-    }
-  }
-  auto kern = osc_kernel<T, N, ORTHO, KD, KSMEM, false>;
+  const size_t smem = (size_t)kWarps * OscSmem<T, N, ORTHO, KD, KSMEM>::kElems * sizeof(T);
+  auto kern = osc_kernel<T, N, ORTHO, KD, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, O, a);
@@ -657,12 +598,13 @@ int rollout_go(const ChainHost &h, const abrb_osc_params &p, const RolloutCall &
   a.q_traj = static_cast<T *>(c.q_traj);
   a.dq_traj = static_cast<T *>(c.dq_traj);
   a.u_traj = static_cast<T *>(c.u_traj);
+  a.ierr = static_cast<T *>(c.ierr);
   a.B = c.B;
   a.target_stride = c.target_stride;
   a.steps = c.steps;
   a.dt = T(c.dt);
   constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32 || ABRB_ROLLED;  // rolled loops index the scratch at run time
-  const size_t smem = (size_t)kWarps * WarpSmem<T, N, ORTHO, KSMEM, N>::kElems * sizeof(T);
+  const size_t smem = (size_t)kWarps * OscSmem<T, N, ORTHO, KD, KSMEM>::kElems * sizeof(T);
   auto kern = rollout_kernel<T, N, ORTHO, KD, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
   if (e != cudaSuccess) return (int)e;

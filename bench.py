@@ -8,8 +8,9 @@ configs[1], driven through OSC.generate with use_C so that {J, M, g, c_forces} a
   python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path (one JSON line on rank 0)
   python bench.py --impl reference [...]                         # the reference's CPU path on the host cores
 
-Under torchrun (N > 1) every rank owns its own B states (weak scaling, no data-path collective; --allgather adds
-the optional NCCL all-gather of the control outputs).  Timing: CUDA events on the launching stream, barrier +
+Under torchrun (N > 1) every rank owns its own B states (weak scaling, no data-path collective in the timed step);
+the optional all-gather of the control outputs is measured separately ("collective": NCCL vs the kernel's fused
+peer-store epilogue), and BASELINE configs 4 and 5 are run at their stated multi-GPU scale ("configs").  Timing: CUDA events on the launching stream, barrier +
 synchronize on both sides, max over ranks.  L2: the steps rotate over a ring of input/output buffer sets larger
 than the 126 MB L2, so every step's inputs come from HBM.
 """
@@ -254,7 +255,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": n_step, "arm": "ur5", "osc": "kp=10, ctrlr_dof=[T]*6, use_C, use_g"},
+        "config": bench_config(args.gpus),
+        "sample_per_step": n_step,
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -275,13 +277,24 @@ def time_kernel(fn, n_launch, torch, sets):
     return e0.elapsed_time(e1) * 1e-3 / n_launch
 
 
+def ncu_facts(prefix):
+    """dram bytes / FP-pipe fraction of a kernel from the committed ncu capture (profiles/ncu_traffic.json)"""
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as fh:
+            for k, v in json.load(fh).items():
+                if k.startswith(prefix):
+                    return v
+    return {}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from abr_control_b200 import _lib
+    from abr_control_b200 import _lib, parallel
     from abr_control_b200.arms import jaco2, ur5
-    from abr_control_b200.controllers import OSC, Damping
+    from abr_control_b200.controllers import OSC, AvoidObstacles, Damping
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -290,13 +303,23 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    nccl_log = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if rank == 0 and "NCCL_DEBUG" not in os.environ:  # the transport line of the collective record
+            nccl_log = os.path.join(tempfile.gettempdir(), f"abrb_nccl_{os.getpid()}.log")
+            os.environ.update(NCCL_DEBUG="INFO", NCCL_DEBUG_SUBSYS="INIT,GRAPH", NCCL_DEBUG_FILE=nccl_log)
         dist.init_process_group("nccl", device_id=dev)
     B, n = B_PER_GPU, 6
     rc = ur5.Config()
     ctrlr = OSC(rc, **OSC_KW)
     L = _lib.lib()
+
+    def max_over_ranks(seconds):
+        t = torch.tensor([seconds], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ring of buffer sets > L2 (126 MB): each set = q, dq, target in (144 B/state) + u out (48 B/state)
     n_sets = 48
@@ -305,22 +328,30 @@ def run_ours(args):
         q, dq, tg = synth(B, n, 1000 * rank + s)
         sets.append(tuple(torch.as_tensor(a, device=dev) for a in (q, dq, tg)))
     ring_mb = n_sets * B * (18 + 6) * 8 / 1e6
-    gather_buf = torch.empty((world * B, n), dtype=torch.float64, device=dev) if (args.allgather and world > 1) else None
-
     outs = [torch.empty((B, n), dtype=torch.float64, device=dev) for _ in range(n_sets)]
 
     def step(i):
         q, dq, tg = sets[i % n_sets]
-        u = ctrlr.generate_into(q, dq, tg, outs[i % n_sets])  # public allocation-free API: one ctypes call
-        if gather_buf is not None:
-            dist.all_gather_into_tensor(gather_buf, u)
-        return u
+        return ctrlr.generate_into(q, dq, tg, outs[i % n_sets])  # public allocation-free API: one ctypes call
 
     def fence():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def timed(fn, n_iter, warm):
+        """device-event seconds per iteration of fn(i), barrier + synchronize on both sides, max over ranks"""
+        for i in range(warm):
+            fn(i)
+        fence()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_iter):
+            fn(i)
+        e1.record()
+        fence()
+        return max_over_ranks(e0.elapsed_time(e1) * 1e-3) / n_iter
 
     for i in range(max(args.warmup, 3)):
         step(i)
@@ -334,35 +365,162 @@ def run_ours(args):
     e1.record()
     fence()
     launches = L.abrb_launch_count() - n0
-    elapsed = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
-    t = float(elapsed.item())
+    t = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
     clocks = sampler.stop() if sampler else None
     value = world * B * args.steps / t
 
-    # ---- end to end through the public API with pinned HOST buffers (H2D + kernel + D2H inside every call)
-    hq, hdq, htg = (torch.as_tensor(a).pin_memory() for a in synth(B, n, 77 + rank))
-    nq, ndq, ntg = hq.numpy(), hdq.numpy(), htg.numpy()
-    ctrlr.record_training_signal = False  # the side channel for DynamicsAdaptation is not part of the metric
-    for _ in range(3):
-        ctrlr.generate(nq, ndq, ntg)
-    fence()
-    # nine short blocks, median block: host-side copies share the box with whatever else runs on its cores
-    e2e_blocks = 9
-    per_block = max(2, min(args.steps, 200) // e2e_blocks)
-    e2e_steps = e2e_blocks * per_block
-    block_t = []
-    for _ in range(e2e_blocks):
-        t0 = time.perf_counter()
-        for _ in range(per_block):
-            u_host = ctrlr.generate(nq, ndq, ntg)
-        block_t.append(time.perf_counter() - t0)
-    t_e2e = torch.tensor(sorted(block_t)[e2e_blocks // 2:e2e_blocks // 2 + 1], device=dev, dtype=torch.float64)
+    # ---- the one collective of the path (BASELINE config 5 / SURVEY S8e): all-gather of u so that every rank holds the
+    #      (world * B, n) array.  Measured three ways with device events, max over ranks: NCCL all-gather alone, the
+    #      kernel followed by NCCL all-gather, and the kernel whose epilogue stores into every rank's gathered array
+    #      over NVLink peer memory (parallel.PeerGather) followed by the arrival wait.
+    collective = None
+    multi = {}
     if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * per_block / float(t_e2e.item())
-    e2e_spread = [B * per_block / t for t in (max(block_t), min(block_t))]  # this rank's slowest / fastest block
+        n_it = max(100, min(args.steps, 400))
+        gbuf = torch.empty((world * B, n), dtype=torch.float64, device=dev)
+        t_ag = timed(lambda i: dist.all_gather_into_tensor(gbuf, outs[i % n_sets]), n_it, 20)
+
+        def step_nccl(i):
+            dist.all_gather_into_tensor(gbuf, step(i))
+
+        t_seq = timed(step_nccl, n_it, 20)
+        pg = parallel.PeerGather(world * B, n, torch.float64)
+
+        def step_fused(i):
+            q, dq, tg = sets[i % n_sets]
+            return pg.generate(ctrlr, q, dq, tg)
+
+        t_fused = timed(step_fused, n_it, 20)
+        full = step_fused(0)  # parity of the fused gather: every rank's block equals an NCCL gather of the same step
+        dist.all_gather_into_tensor(gbuf, step(0))
+        torch.cuda.synchronize()
+        same = bool(torch.equal(full, gbuf)) and pg.status() == 0
+        payload = B * n * 8
+        transport = None
+        if nccl_log and os.path.exists(nccl_log):
+            with open(nccl_log) as fh:
+                via = sorted({ln.split(" via ")[1].split()[0] for ln in fh if " via " in ln})
+            transport = ",".join(via) or None
+        collective = {
+            "what": "all-gather of u (float64, %d x %d per rank) so that every rank holds the (%d, %d) array" % (B, n, world * B, n),
+            "payload_bytes_per_rank": payload,
+            "nccl_allgather_alone_us": t_ag * 1e6,
+            "nccl_bus_GBps": payload * (world - 1) / t_ag / 1e9,
+            "nccl_transport": transport,
+            "kernel_only_us": t / args.steps * 1e6,
+            "kernel_then_nccl_allgather_us": t_seq * 1e6,
+            "kernel_with_fused_peer_store_us": t_fused * 1e6,
+            "fused_nvlink_bytes_out_per_rank": payload * (world - 1),
+            "fused_nvlink_GBps_out_per_rank": payload * (world - 1) / t_fused / 1e9,
+            "fused_matches_nccl": same,
+            "evals_per_s_with_nccl_gather": world * B / t_seq,
+            "evals_per_s_with_fused_gather": world * B / t_fused,
+            "iterations": n_it,
+        }
+        pg.close()
+        # ---- BASELINE config 5 at its stated scale: Jaco2 OSC x,y,z + vmax + AvoidObstacles + Damping, fp32,
+        #      131072 states per GPU (1 048 576 over 8), output gathered on every rank by the fused epilogue
+        B5 = 131072
+        rc5 = jaco2.Config()
+        c5 = OSC(rc5, kp=200, vmax=[0.5, 0], ctrlr_dof=[True, True, True, False, False, False],
+                 null_controllers=[AvoidObstacles(rc5, obstacles=[[0.09596, -0.2661, 0.64204, 0.05]], threshold=0.2),
+                                   Damping(rc5, kv=10)])
+        s5 = []
+        for s in range(12):
+            q, dq, tg = synth(B5, 6, 7000 + 100 * rank + s, np.float32)
+            s5.append(tuple(torch.as_tensor(a, device=dev) for a in (q, dq, tg)))
+        u5 = torch.empty((B5, 6), dtype=torch.float32, device=dev)
+        t5 = timed(lambda i: c5.generate_into(*s5[i % 12], u5), 40, 5)
+        pg5 = parallel.PeerGather(world * B5, 6, torch.float32)
+        t5g = timed(lambda i: pg5.generate(c5, *s5[i % 12]), 40, 5)
+        g5 = torch.empty((world * B5, 6), dtype=torch.float32, device=dev)
+
+        def step5_nccl(i):
+            dist.all_gather_into_tensor(g5, c5.generate_into(*s5[i % 12], u5))
+
+        t5n = timed(step5_nccl, 40, 5)
+        ok5 = pg5.status() == 0
+        pg5.close()
+        multi["config5_jaco2_avoid_f32"] = {
+            "states_per_gpu": B5, "global_states": world * B5, "us_per_step_no_gather": t5 * 1e6,
+            "us_per_step_fused_gather": t5g * 1e6, "us_per_step_nccl_gather": t5n * 1e6,
+            "evals_per_s_fused_gather": world * B5 / t5g, "evals_per_s_no_gather": world * B5 / t5,
+            "gather_payload_bytes_total": world * B5 * 6 * 4, "gather_ok": ok5}
+    # ---- BASELINE config 4 at its stated scale: UR5 OSC(kp=10) closed-loop rollouts, 512 trajectories per GPU
+    #      (4096 over 8) x 128 steps, dt = 1e-3, one launch per rollout; trajectories shard, nothing is exchanged
+    traj_per_gpu = 4096 // max(world, 1) if world > 1 else 4096
+    c4 = OSC(rc, kp=10.0)
+    q4, dq4, tg4 = (torch.as_tensor(a, device=dev) for a in synth(traj_per_gpu, 6, 4242 + rank))
+    dq4 = dq4 * 0.1
+    t4 = timed(lambda i: c4.rollout(q4, dq4, tg4, steps=128, dt=1e-3, record=()), 5, 2)
+    multi["config4_ur5_rollout_f64"] = {
+        "trajectories_per_gpu": traj_per_gpu, "global_trajectories": traj_per_gpu * world, "horizon": 128,
+        "ms_per_rollout": t4 * 1e3, "us_per_step": t4 / 128 * 1e6, "osc_evals_per_s": world * traj_per_gpu * 128 / t4,
+        "note": "latency bound (sequential depth 128); trajectories shard over the GPUs, nothing is exchanged"}
+
+    # ---- end to end through the public API with pinned HOST buffers (H2D + kernel + D2H inside every call).
+    #      `sync`: OSC.generate(q, dq, target) call after call, each one waits for its own result.
+    #      `pipelined`: OSC.generate_async on the two pipeline slots alternately, each result awaited before its slot is
+    #      reused -- batch k+1's upload runs under batch k's kernel and download (every batch still crosses PCIe both ways).
+    n_host = 4
+    host = []
+    for s in range(n_host):
+        host.append(tuple(torch.as_tensor(a).pin_memory().numpy() for a in synth(B, n, 77 + 10 * rank + s)))
+    ctrlr.record_training_signal = False  # the reference also stores training_signal (osc.py:297); not copied back here
+    for s in range(3):
+        ctrlr.generate(*host[s % n_host])
+    fence()
+    calls = max(100, min(args.steps, 400))
+    blocks = 5
+    per_block = calls // blocks
+    sync_t, pipe_t = [], []
+    for _ in range(blocks):
+        t0 = time.perf_counter()
+        for i in range(per_block):
+            u_host = ctrlr.generate(*host[i % n_host])
+        sync_t.append(time.perf_counter() - t0)
+    fence()
+    for _ in range(blocks):
+        t0 = time.perf_counter()
+        pend = [None, None]
+        for i in range(per_block):
+            sl = i & 1
+            if pend[sl] is not None:
+                u_host = pend[sl].wait()
+            pend[sl] = ctrlr.generate_async(*host[i % n_host], slot=sl)
+        for p_ in pend:
+            if p_ is not None:
+                u_host = p_.wait()
+        pipe_t.append(time.perf_counter() - t0)
+    fence()
+    t_sync = max_over_ranks(float(np.median(sync_t)))
+    t_pipe = max_over_ranks(float(np.median(pipe_t)))
+    # pinned-copy peaks of this box (what PCIe gives a plain cudaMemcpyAsync), for the achieved-GB/s figure
+    hbuf = torch.empty(B * 18, dtype=torch.float64).pin_memory()
+    dbuf = torch.empty(B * 18, dtype=torch.float64, device=dev)
+    def copy_rate(fn, nbytes):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            fn()
+        torch.cuda.synchronize()
+        return nbytes * 20 / (time.perf_counter() - t0) / 1e9
+    h2d_peak = copy_rate(lambda: dbuf.copy_(hbuf, non_blocking=True), B * 18 * 8)
+    d2h_peak = copy_rate(lambda: hbuf.copy_(dbuf, non_blocking=True), B * 18 * 8)
+    e2e = {
+        "value": world * B * per_block / t_pipe, "unit": UNIT, "h2d_bytes_per_step": int(B * 18 * 8),
+        "d2h_bytes_per_step": int(B * 6 * 8), "calls": per_block * blocks, "blocks": blocks,
+        "mode": "pipelined: OSC.generate_async on two slots (abrb_osc_generate_host_async_f64 + abrb_osc_host_wait); every "
+                "batch is copied host->device and its u device->host inside the timed region, wall clock, median block",
+        "sync_value": world * B * per_block / t_sync,
+        "sync_mode": "OSC.generate(q, dq, target) on pinned host NumPy buffers, one blocking call per batch",
+        "block_range_pipelined": [B * per_block / x for x in (max(pipe_t), min(pipe_t))],
+        "block_range_sync": [B * per_block / x for x in (max(sync_t), min(sync_t))],
+        "pcie_h2d_GBps_achieved": B * 18 * 8 * per_block / float(np.median(pipe_t)) / 1e9,
+        "pcie_h2d_GBps_pinned_copy_peak": h2d_peak, "pcie_d2h_GBps_pinned_copy_peak": d2h_peak,
+        "training_signal_copied": False,
+    }
 
     if rank != 0:
         if world > 1:
@@ -370,41 +528,42 @@ def run_ours(args):
         return
     hbm_peak, peak_src = peaks()
     bytes_per_state = (6 + 6 + 6) * 8 + 6 * 8  # q, dq, target in; u out (fp64)
-    kernel_s = t / args.steps if gather_buf is None else None
-    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
-        with open(tp) as fh:
-            for k, v in json.load(fh).items():
-                if k.startswith("osc:osc_kernel<double, 6"):
-                    traffic = v["dram_mb_per_launch"] * 1e6  # bytes per launch (profiles/<tag>_osc.txt)
+    kernel_s = t / args.steps
+    facts = ncu_facts("osc:osc_kernel<double, 6")
+    traffic = facts.get("dram_mb_per_launch")
+    traffic = traffic * 1e6 if traffic is not None else None
 
     extra = {}
     quick = bool(os.environ.get("ABRB_BENCH_QUICK"))  # tuning knob: headline + e2e only
     if world == 1 and not quick:
-        # the other single-GPU kernels, same timing discipline (explain the headline; not bench lines themselves)
-        def rbd_sets(want, dtype):
+        # the other single-GPU kernels, same timing discipline (explain the headline; not bench lines themselves).
+        # rbd kernels: inputs AND outputs rotate over a ring larger than L2, so every launch's outputs go to HBM
+        shp = lambda Bx: dict(J=(Bx, 6, n), M=(Bx, n, n), g=(Bx, n), C=(Bx, n, n))  # noqa: E731
+
+        def rbd_ring(Bx, want, dtype, ring_bytes=320e6):
+            es = 8 if dtype == torch.float64 else 4
+            per_set = Bx * (12 + sum(int(np.prod(shp(Bx)[k][1:])) for k in want)) * es
+            count = max(3, int(np.ceil(ring_bytes / per_set)))
             out = []
-            for s in range(24):
-                q, dq, _ = synth(B, n, 5000 + s, np.float64 if dtype == torch.float64 else np.float32)
-                out.append((torch.as_tensor(q, device=dev), torch.as_tensor(dq, device=dev)))
-            return out
+            for s in range(count):
+                q, dq, _ = synth(Bx, n, 5000 + s, np.float64 if dtype == torch.float64 else np.float32)
+                o = {k: torch.empty(shp(Bx)[k], dtype=dtype, device=dev) for k in want}
+                out.append((torch.as_tensor(q, device=dev), torch.as_tensor(dq, device=dev), o))
+            return out, count * per_set
 
-        shp = dict(J=(B, 6, n), M=(B, n, n), g=(B, n), C=(B, n, n))
-
-        def mk_rbd(rcx, want, dtype=torch.float64):
-            o = {k: torch.empty(shp[k], dtype=dtype, device=dev) for k in want}
-            return lambda s: rcx.eval_into(s[0], s[1], o)
-
-        rs = rbd_sets(None, torch.float64)
-        for key, want, nbytes in (("rbd_ur5_JMgC_f64", ("J", "M", "g", "C"), 1008), ("rbd_ur5_JMg_f64", ("J", "M", "g"), 672)):
-            dt = time_kernel(mk_rbd(rc, want), 200, torch, rs)
-            extra[key] = {"states_per_s": B / dt, "us_per_launch": dt * 1e6, "bytes_per_state": nbytes,
-                          "achieved_gbs": B * nbytes / dt / 1e9, "frac_hbm": B * nbytes / dt / 1e9 / hbm_peak, "B": B}
-        rs32 = rbd_sets(None, torch.float32)
-        dt = time_kernel(mk_rbd(rc, ("J", "M", "g"), torch.float32), 200, torch, rs32)
-        extra["rbd_ur5_JMg_f32"] = {"states_per_s": B / dt, "us_per_launch": dt * 1e6, "bytes_per_state": 336,
-                                    "achieved_gbs": B * 336 / dt / 1e9, "frac_hbm": B * 336 / dt / 1e9 / hbm_peak, "B": B}
+        for key, want, nbytes, dtype, Bx in (("rbd_ur5_JMgC_f64", ("J", "M", "g", "C"), 1008, torch.float64, B),
+                                             ("rbd_ur5_JMg_f64", ("J", "M", "g"), 672, torch.float64, B),
+                                             ("rbd_ur5_JMg_f32", ("J", "M", "g"), 336, torch.float32, B),
+                                             ("rbd_ur5_JMgC_f64_B262144", ("J", "M", "g", "C"), 1008, torch.float64, 262144),
+                                             ("rbd_ur5_JMg_f64_B262144", ("J", "M", "g"), 672, torch.float64, 262144)):
+            ring, ring_b = rbd_ring(Bx, want, dtype)
+            dt = time_kernel(lambda s: rc.eval_into(s[0], s[1], s[2]), 200 if Bx == B else 60, torch, ring)
+            f = ncu_facts("rbd:" + key)
+            extra[key] = {"states_per_s": Bx / dt, "us_per_launch": dt * 1e6, "bytes_per_state": nbytes,
+                          "achieved_gbs": Bx * nbytes / dt / 1e9, "frac_hbm": Bx * nbytes / dt / 1e9 / hbm_peak, "B": Bx,
+                          "ring_mb_in_and_out": ring_b / 1e6, "dram_mb_per_launch_ncu": f.get("dram_mb_per_launch"),
+                          "fp_pipe_frac_ncu": f.get("fp_pipe_frac")}
+            del ring
         # BASELINE config 3: Jaco2 OSC 5-DOF + Damping, fp32, B = 262144
         B3 = 262144
         rc3 = jaco2.Config()
@@ -415,10 +574,11 @@ def run_ours(args):
             s3.append(tuple(torch.as_tensor(a, device=dev) for a in (q, dq, tg)))
         u3 = torch.empty((B3, 6), dtype=torch.float32, device=dev)
         dt = time_kernel(lambda s: c3.generate_into(s[0], s[1], s[2], u3), 100, torch, s3)
+        f = ncu_facts("osc:osc_kernel<float, 6, 0, 6")
         extra["osc_jaco2_cfg3_f32_B262144"] = {"evals_per_s": B3 / dt, "us_per_launch": dt * 1e6, "bytes_per_state": 96,
-                                               "achieved_gbs": B3 * 96 / dt / 1e9, "frac_hbm": B3 * 96 / dt / 1e9 / hbm_peak}
+                                               "achieved_gbs": B3 * 96 / dt / 1e9, "frac_hbm": B3 * 96 / dt / 1e9 / hbm_peak,
+                                               "fp_pipe_frac_ncu": f.get("fp_pipe_frac")}
         # BASELINE config 5 (per-GPU share): Jaco2 OSC xyz + vmax + AvoidObstacles(1 obstacle) + Damping, fp32, B = 131072
-        from abr_control_b200.controllers import AvoidObstacles
         B5 = 131072
         c5 = OSC(rc3, kp=200, vmax=[0.5, 0], ctrlr_dof=[True, True, True, False, False, False],
                  null_controllers=[AvoidObstacles(rc3, obstacles=[[0.09596, -0.2661, 0.64204, 0.05]], threshold=0.2),
@@ -427,22 +587,7 @@ def run_ours(args):
         u5 = torch.empty((B5, 6), dtype=torch.float32, device=dev)
         dt = time_kernel(lambda s: c5.generate_into(s[0], s[1], s[2], u5), 50, torch, s5)
         extra["osc_jaco2_cfg5_avoid_f32_B131072"] = {"evals_per_s": B5 / dt, "us_per_launch": dt * 1e6, "bytes_per_state": 96}
-        # BASELINE config 4: UR5 OSC(kp=10) closed-loop rollout, 4096 trajectories x 128 steps, dt = 1e-3 (one launch)
-        c4 = OSC(rc, kp=10.0)
-        q4, dq4, tg4 = (torch.as_tensor(a, device=dev) for a in synth(4096, 6, 4242))
-        dq4 = dq4 * 0.1
-        for _ in range(2):
-            c4.rollout(q4, dq4, tg4, steps=128, dt=1e-3, record=())
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            c4.rollout(q4, dq4, tg4, steps=128, dt=1e-3, record=())
-        e1.record()
-        torch.cuda.synchronize()
-        dt = e0.elapsed_time(e1) * 1e-3 / 5
-        extra["rollout_ur5_cfg4_f64_4096x128"] = {"osc_evals_per_s": 4096 * 128 / dt, "ms_per_rollout": dt * 1e3,
-                                                   "us_per_step": dt / 128 * 1e6, "note": "latency bound: 32 warps per 148 SMs"}
+        extra["rollout_ur5_cfg4_f64_4096x128"] = multi["config4_ur5_rollout_f64"]
         ctrl32 = OSC(ur5.Config(), **OSC_KW)
         s32 = [tuple(t_.float() for t_ in s) for s in sets[:24]]
         u32b = torch.empty((B, 6), dtype=torch.float32, device=dev)
@@ -463,31 +608,37 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "arm": "ur5", "batch_per_gpu": B, "global_batch": world * B,
-                   "osc": "kp=10, ctrlr_dof=[T]*6, use_C=True, use_g=True, orientation_algorithm=0",
-                   "parallelism": f"batch sharded over {world} GPU(s), no data-path collective" +
-                                  (" + NCCL all-gather of u" if gather_buf is not None else ""),
-                   "l2": f"inputs rotate over a ring of {n_sets} buffer sets ({ring_mb:.0f} MB > 126 MB L2)"},
+        "config": bench_config(world),
         "clocks": clocks,
         "gpu_launches": int(launches),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * 18 * 8), "d2h_bytes_per_step": int(B * 6 * 8),
-                "steps": e2e_steps, "blocks": e2e_blocks, "block_range": e2e_spread,
-                "how": "OSC.generate(q, dq, target) on pinned host NumPy buffers -> abrb_osc_generate_host_f64 (H2D of q, dq, "
-                       "target / kernel / D2H of u into a page-locked result, stream sync inside every call); wall clock, "
-                       "median of the nine blocks"},
-        "roofline": {"bound": "hbm", "achieved": (B * bytes_per_state / kernel_s / 1e9) if kernel_s else None,
+        "e2e": e2e,
+        "roofline": {"bound": "hbm", "achieved": B * bytes_per_state / kernel_s / 1e9,
                      "peak": hbm_peak, "unit": "GB/s",
-                     "frac": (B * bytes_per_state / kernel_s / 1e9 / hbm_peak) if kernel_s else None, "traffic": traffic,
+                     "frac": B * bytes_per_state / kernel_s / 1e9 / hbm_peak, "traffic": traffic,
                      "kernel": "osc_kernel<double,6,ORTHO,KD=6>", "algorithmic_bytes_per_state": bytes_per_state,
                      "peak_source": peak_src,
+                     "fp_pipe_frac": facts.get("fp_pipe_frac"),
+                     "fp_pipe_frac_source": "sm__inst_executed_pipe_fp64 (pct of peak) of the committed ncu capture, profiles/",
                      "note": "192 B/state against ~10^4 fp64 flops/state: this kernel is FP64-pipe bound, not HBM bound "
-                             "(SURVEY.md S8d); the HBM-bound figures are the rbd_* kernels under 'kernels'"},
+                             "(SURVEY.md S8d): fp_pipe_frac is the fraction that binds; the HBM-bound figures are the "
+                             "rbd_* kernels under 'kernels'"},
+        "collective": collective,
+        "configs": multi,
         "kernels": extra,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_config(world):
+    """the workload description shared by both arms (the driver compares the dicts)"""
+    return {"workload": WORKLOAD, "arm": "ur5", "batch_per_gpu": B_PER_GPU, "global_batch": world * B_PER_GPU,
+            "osc": "kp=10, ctrlr_dof=[T]*6, use_C=True, use_g=True, orientation_algorithm=0",
+            "parallelism": f"batch sharded over {world} GPU(s), no data-path collective in the timed step "
+                           "(the optional all-gather of u is measured separately under 'collective')",
+            "l2": "inputs rotate over a ring of 48 buffer sets (604 MB > 126 MB L2)"}
 
 
 def main():
@@ -508,7 +659,6 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--allgather", action="store_true", help="all-gather u across ranks every step (config 5 style)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -13,8 +13,8 @@
  * Conventions
  *   - plain C types only; no torch / CUDA types in signatures (`stream` is a cudaStream_t passed as void*,
  *     NULL = the legacy default stream);
- *   - unless the name ends in `_host`, every data pointer is a DEVICE pointer on the current CUDA device,
- *     16-byte aligned, row-major, batch-major: q is (B, n_joints), J is (B, 6, n_joints), M is (B, n, n) ...
+ *   - unless the name contains `_host`, every data pointer is a DEVICE pointer on the current CUDA device,
+ *     aligned to its element type (any row of a contiguous array is a valid start), row-major, batch-major: q is (B, n_joints), J is (B, 6, n_joints), M is (B, n, n) ...
  *     exactly the per-state shapes the reference returns, stacked;
  *   - the library never allocates or frees caller buffers; device-pointer calls are asynchronous with
  *     respect to the host (enqueued on `stream`); `_host` calls copy in, run, copy out and synchronise;
@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ABRB_VERSION 100 /* 0.1.0 */
+#define ABRB_VERSION 200 /* 0.2.0: integrated_error arguments, asynchronous host slots, peer-gather epilogue */
 #define ABRB_MAX_JOINTS 7
 #define ABRB_MAX_NULL 4
 #define ABRB_MAX_OBSTACLES 16
@@ -148,40 +148,95 @@ typedef struct abrb_osc_params {
 
 typedef struct abrb_osc abrb_osc;
 
-/* ki != 0 needs per-state integrator memory and is reported as ABRB_EUNSUP in this version. */
 int abrb_osc_create(const abrb_model *m, const abrb_osc_params *p, abrb_osc **out);
 int abrb_osc_destroy(abrb_osc *c);
 
-/* Execution options of one controller (no effect on results beyond rounding).  Names:
- *   "two_launch_min"  batch size from which abrb_osc_generate_* runs the 6-row task space as two launches (all
- *                     states but those on the truncating pinv route, then those from an index queue); 0 = never
- *                     (default; the environment variable ABRB_OSC_DEFER_MIN sets another default).
- * Returns ABRB_EINVAL for an unknown name. */
+/* Execution options of one controller (no effect on results).  Names:
+ *   "host_chunk_states"  states per pipeline chunk of the *_host entry points; 0 = automatic (default; the
+ *                        environment variable ABRB_HOST_CHUNK sets another default).
+ * Returns ABRB_EINVAL for an unknown name.  Not thread safe against concurrent generate calls on the same handle. */
 int abrb_osc_set_option(abrb_osc *c, const char *name, double value);
 
 /* OSC.generate(q, dq, target, target_velocity=None, ref_frame="EE", xyz_offset=None) for B states.
- *   target          (B,6) if target_stride == 6, or one (6,) row broadcast to all states if target_stride == 0
- *   target_velocity NULL (the reference's `np.all(target_velocity == 0)` joint-space damping branch,
- *                   osc.py:275-278) or (B,6)/(6,) per tv_stride (task-space branch, osc.py:279-282)
- *   u               (B,n) out;   training_signal (B,n) out or NULL (osc.py:297)
- *   frame_id/x_off  ref_frame and xyz_offset (x_off: 3 host doubles or NULL) */
+ *   target           (B,6) if target_stride == 6, or one (6,) row broadcast to all states if target_stride == 0
+ *   target_velocity  NULL (the reference's `np.all(target_velocity == 0)` joint-space damping branch,
+ *                    osc.py:275-278) or (B,6)/(6,) per tv_stride (task-space branch, osc.py:279-282)
+ *   u                (B,n) out;   training_signal (B,n) out or NULL (osc.py:297)
+ *   integrated_error (B,6) in/out: the reference's per-controller `self.integrated_error` (osc.py:81-82), one row per
+ *                    state, updated as osc.py:262-264 (`integrated_error += u_task; u_task += ki * integrated_error`).
+ *                    Must be given if and only if the controller was created with ki != 0 (else ABRB_EINVAL); the
+ *                    caller owns it and zeroes it to reset the integrator.
+ *   frame_id/x_off   ref_frame and xyz_offset (x_off: 3 host doubles or NULL) */
 int abrb_osc_generate_f64(const abrb_osc *c, int frame_id, const double *x_off, const double *q,
                           const double *dq, const double *target, int target_stride,
                           const double *target_velocity, int tv_stride, double *u,
-                          double *training_signal, int64_t B, void *stream);
+                          double *training_signal, double *integrated_error, int64_t B, void *stream);
 int abrb_osc_generate_f32(const abrb_osc *c, int frame_id, const double *x_off, const float *q,
                           const float *dq, const float *target, int target_stride,
                           const float *target_velocity, int tv_stride, float *u,
-                          float *training_signal, int64_t B, void *stream);
+                          float *training_signal, float *integrated_error, int64_t B, void *stream);
 /* HOST-pointer variants (H2D + kernel + D2H + sync inside) */
 int abrb_osc_generate_host_f64(const abrb_osc *c, int frame_id, const double *x_off, const double *q,
                                const double *dq, const double *target, int target_stride,
                                const double *target_velocity, int tv_stride, double *u,
-                               double *training_signal, int64_t B);
+                               double *training_signal, double *integrated_error, int64_t B);
 int abrb_osc_generate_host_f32(const abrb_osc *c, int frame_id, const double *x_off, const float *q,
                                const float *dq, const float *target, int target_stride,
                                const float *target_velocity, int tv_stride, float *u,
-                               float *training_signal, int64_t B);
+                               float *training_signal, float *integrated_error, int64_t B);
+/* Asynchronous HOST-pointer variants for control loops that evaluate batch after batch: the call enqueues the H2D
+ * copies, the kernel and the D2H copies of one batch on pipeline slot `slot` (0 or 1) of the calling thread and
+ * returns; abrb_osc_host_wait(c, slot) blocks until that batch's outputs are in the caller's buffers.  With the two
+ * slots used alternately, batch k+1's H2D runs under batch k's kernel and D2H (PCIe is full duplex), so a stream of
+ * calls costs max(H2D, kernel, D2H) per batch instead of their sum.  The host buffers (page-locked for real
+ * asynchrony) must stay valid and untouched until the wait; enqueueing on a slot first waits for its previous batch.
+ * The synchronous variants above are slot 0 + wait. */
+int abrb_osc_generate_host_async_f64(const abrb_osc *c, int frame_id, const double *x_off, const double *q,
+                                     const double *dq, const double *target, int target_stride,
+                                     const double *target_velocity, int tv_stride, double *u,
+                                     double *training_signal, double *integrated_error, int64_t B, int slot);
+int abrb_osc_generate_host_async_f32(const abrb_osc *c, int frame_id, const double *x_off, const float *q,
+                                     const float *dq, const float *target, int target_stride,
+                                     const float *target_velocity, int tv_stride, float *u,
+                                     float *training_signal, float *integrated_error, int64_t B, int slot);
+int abrb_osc_host_wait(const abrb_osc *c, int slot);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fused all-gather of the control outputs across the GPUs of one box (BASELINE config 5): one
+ * process per GPU, every rank evaluates its own row block, and the OSC kernel's epilogue stores each finished tile of
+ * `u` straight into the gathered (B_total, n) array of EVERY rank through NVLink peer memory (buffers mapped with CUDA
+ * IPC) — the exchange overlaps the arithmetic instead of following it as a separate NCCL collective.
+ *   abrb_gather_create   allocates this rank's region: n_buffers gathered arrays of bytes_per_buffer each (use two and
+ *                        alternate them call by call: a fast rank may already write call k+1 while a slow one still
+ *                        reads call k) plus the completion flags
+ *   abrb_gather_export / abrb_gather_import   exchange the 64-byte CUDA IPC handles (any transport: MPI,
+ *                        torch.distributed.all_gather_object, a file); every rank imports every other rank once
+ *   abrb_osc_generate_gather_*   abrb_osc_generate_* whose rows additionally land at row `row0` of buffer
+ *                        `buffer_index` on every rank (`u` may be NULL if only the gathered copy is wanted); all ranks
+ *                        must make the same sequence of gather calls
+ *   abrb_gather_wait     enqueues, on `stream`, a wait until every rank's rows of the latest gather call have arrived
+ *                        in this rank's buffer (device-side spin on the flags; gives up after ~3 s and sets the status)
+ *   abrb_gather_buffer   device pointer of this rank's gathered array `buffer_index`
+ *   abrb_gather_status   0, or 1 if a wait ever timed out (call after synchronising the stream)
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct abrb_gather abrb_gather;
+int abrb_gather_create(int rank, int world, int64_t bytes_per_buffer, int n_buffers, abrb_gather **out);
+int abrb_gather_destroy(abrb_gather *g);
+int abrb_gather_export(const abrb_gather *g, unsigned char handle[64]);
+int abrb_gather_import(abrb_gather *g, int peer_rank, const unsigned char handle[64]);
+void *abrb_gather_buffer(const abrb_gather *g, int buffer_index);
+int abrb_gather_wait(abrb_gather *g, void *stream);
+int abrb_gather_status(const abrb_gather *g);
+int abrb_osc_generate_gather_f64(const abrb_osc *c, int frame_id, const double *x_off, const double *q,
+                                 const double *dq, const double *target, int target_stride,
+                                 const double *target_velocity, int tv_stride, double *u, double *training_signal,
+                                 double *integrated_error, int64_t B, abrb_gather *g, int buffer_index, int64_t row0,
+                                 void *stream);
+int abrb_osc_generate_gather_f32(const abrb_osc *c, int frame_id, const double *x_off, const float *q,
+                                 const float *dq, const float *target, int target_stride,
+                                 const float *target_velocity, int tv_stride, float *u, float *training_signal,
+                                 float *integrated_error, int64_t B, abrb_gather *g, int buffer_index, int64_t row0,
+                                 void *stream);
 
 /* Standalone secondary controller: Damping / RestingConfig / AvoidObstacles / AvoidJointLimits
  * `.generate(q, dq)` -> (B,n). */
@@ -216,13 +271,16 @@ int abrb_floating_generate_f32(const abrb_model *m, int task_space, int dynamic,
  * has no plant for UR5/Jaco2, this one uses the same M, g, C the controller uses).
  *   q, dq   (B,n) in/out (final state);  target (B,6) or (6,) per target_stride
  *   q_traj / dq_traj / u_traj: NULL or (steps, B, n) outputs
+ *   integrated_error: (B,6) in/out, given if and only if ki != 0 (as for abrb_osc_generate_*)
  * ------------------------------------------------------------------------------------------------- */
 int abrb_osc_rollout_f64(const abrb_osc *c, int frame_id, const double *x_off, double *q, double *dq,
                          const double *target, int target_stride, int steps, double dt,
-                         double *q_traj, double *dq_traj, double *u_traj, int64_t B, void *stream);
+                         double *q_traj, double *dq_traj, double *u_traj, double *integrated_error, int64_t B,
+                         void *stream);
 int abrb_osc_rollout_f32(const abrb_osc *c, int frame_id, const double *x_off, float *q, float *dq,
                          const float *target, int target_stride, int steps, double dt,
-                         float *q_traj, float *dq_traj, float *u_traj, int64_t B, void *stream);
+                         float *q_traj, float *dq_traj, float *u_traj, float *integrated_error, int64_t B,
+                         void *stream);
 
 /* Kernel launch counter for this process (every launch of a libabrb kernel increments it). */
 int64_t abrb_launch_count(void);

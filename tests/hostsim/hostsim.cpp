@@ -46,14 +46,14 @@ void rbd_loop(const ChainHost &h, int frame, const double *xoff, const double *q
 template <typename T, int N, bool ORTHO>
 void osc_loop(const ChainHost &h, const abrb_osc_params &p, int frame, const double *xoff, const double *q,
               const double *dq, const double *target, int tstride, const double *tv, int tvstride, int64_t B,
-              double *u, double *train, double *ddq) {
+              double *u, double *train, double *ddq, double *ierr) {
   ChainK<T, N> P;
   fill_chain<T, N>(h, P);
   OscK<T, N> O;
   fill_osc<T, N>(p, frame, xoff, O);
   const bool kd6 = (O.dof_mask & 56u) != 0;
   for (int64_t b = 0; b < B; ++b) {
-    T qq[N], dd[N], tg[6], tvv[6], uu[N], tr[N], acc[N];
+    T qq[N], dd[N], tg[6], tvv[6], uu[N], tr[N], acc[N], ie[6];
     for (int k = 0; k < N; ++k) {
       qq[k] = T(q[b * N + k]);
       dd[k] = T(dq[b * N + k]);
@@ -61,65 +61,19 @@ void osc_loop(const ChainHost &h, const abrb_osc_params &p, int frame, const dou
     for (int c = 0; c < 6; ++c) {
       tg[c] = T(target[b * tstride + c]);
       tvv[c] = tv ? T(tv[b * tvstride + c]) : T(0);
+      ie[c] = ierr ? T(ierr[b * 6 + c]) : T(0);
     }
     Kin<T, N, ORTHO> K;
     if (kd6)
-      osc_state<T, N, 6, true>(P, O, qq, dd, tg, tv ? tvv : nullptr, uu, tr, acc, K);
+      osc_state<T, N, 6, true>(P, O, qq, dd, tg, tv ? tvv : nullptr, ierr ? ie : nullptr, uu, tr, acc, K);
     else
-      osc_state<T, N, 3, true>(P, O, qq, dd, tg, tv ? tvv : nullptr, uu, tr, acc, K);
+      osc_state<T, N, 3, true>(P, O, qq, dd, tg, tv ? tvv : nullptr, ierr ? ie : nullptr, uu, tr, acc, K);
+    for (int c = 0; c < 6; ++c)
+      if (ierr) ierr[b * 6 + c] = double(ie[c]);
     for (int k = 0; k < N; ++k) {
       u[b * N + k] = double(uu[k]);
       if (train) train[b * N + k] = double(tr[k]);
       if (ddq) ddq[b * N + k] = double(acc[k]);
-    }
-  }
-}
-
-// The two halves of the two-launch mode (osc_eval MODE 1 -> record -> MODE 2 on a FRESH scratch), state by state.
-template <typename T>
-struct HostRecord {
-  std::vector<T> v;
-  bool used = false;
-  void begin() { used = true; }
-  void put(int i, T x) {
-    if ((size_t)i >= v.size()) v.resize(i + 1);
-    v[i] = x;
-  }
-  T get(int i) const { return v[i]; }
-};
-
-template <typename T, int N, bool ORTHO>
-void osc_split_loop(const ChainHost &h, const abrb_osc_params &p, int frame, const double *xoff, const double *q,
-                    const double *dq, const double *target, int tstride, const double *tv, int tvstride, int64_t B,
-                    double *u, double *train, int64_t *n_deferred) {
-  ChainK<T, N> P;
-  fill_chain<T, N>(h, P);
-  OscK<T, N> O;
-  fill_osc<T, N>(p, frame, xoff, O);
-  *n_deferred = 0;
-  for (int64_t b = 0; b < B; ++b) {
-    T qq[N], dd[N], tg[6], tvv[6], uu[N], tr[N];
-    for (int k = 0; k < N; ++k) {
-      qq[k] = T(q[b * N + k]);
-      dd[k] = T(dq[b * N + k]);
-    }
-    for (int c = 0; c < 6; ++c) {
-      tg[c] = T(target[b * tstride + c]);
-      tvv[c] = tv ? T(tv[b * tvstride + c]) : T(0);
-    }
-    HostRecord<T> rec;
-    Kin<T, N, ORTHO> K;
-    if (osc_eval<T, N, 6, false, 1>(P, O, qq, dd, tg, tv ? tvv : nullptr, uu, tr, (T *)nullptr, K, rec)) {
-      ++*n_deferred;
-      if ((int)rec.v.size() != OscRecord<N, 6>::kLen) std::abort();
-      Kin<T, N, ORTHO> K2;
-      for (int k = 0; k < N; ++k) uu[k] = tr[k] = T(-777);
-      osc_eval<T, N, 6, false, 2>(P, O, (const T *)nullptr, (const T *)nullptr, (const T *)nullptr, (const T *)nullptr,
-                                  uu, tr, (T *)nullptr, K2, rec);
-    }
-    for (int k = 0; k < N; ++k) {
-      u[b * N + k] = double(uu[k]);
-      if (train) train[b * N + k] = double(tr[k]);
     }
   }
 }
@@ -260,23 +214,13 @@ int hs_rbd(const abrb_chain_desc *d, int f32, int force_general, int frame, cons
 
 int hs_osc(const abrb_chain_desc *d, const abrb_osc_params *p, int f32, int force_general, int frame,
            const double *xoff, const double *q, const double *dq, const double *target, int tstride, const double *tv,
-           int tvstride, int64_t B, double *u, double *train, double *ddq) {
+           int tvstride, int64_t B, double *u, double *train, double *ddq, double *ierr) {
   ChainHost h;
   if (!chain_from_desc(*d, h).empty()) return ABRB_EINVAL;
   if (!check_osc(h.n, *p).empty()) return ABRB_EUNSUP;
+  if ((p->ki != 0.0) != (ierr != nullptr)) return ABRB_EINVAL;
   const bool ortho = h.ortho && !force_general;
-  DISPATCH_N(osc_loop, h, *p, frame, xoff, q, dq, target, tstride, tv, tvstride, B, u, train, ddq);
-  return 0;
-}
-
-int hs_osc_split(const abrb_chain_desc *d, const abrb_osc_params *p, int f32, int force_general, int frame,
-                 const double *xoff, const double *q, const double *dq, const double *target, int tstride,
-                 const double *tv, int tvstride, int64_t B, double *u, double *train, int64_t *n_deferred) {
-  ChainHost h;
-  if (!chain_from_desc(*d, h).empty()) return ABRB_EINVAL;
-  if (!check_osc(h.n, *p).empty()) return ABRB_EUNSUP;
-  const bool ortho = h.ortho && !force_general;
-  DISPATCH_N(osc_split_loop, h, *p, frame, xoff, q, dq, target, tstride, tv, tvstride, B, u, train, n_deferred);
+  DISPATCH_N(osc_loop, h, *p, frame, xoff, q, dq, target, tstride, tv, tvstride, B, u, train, ddq, ierr);
   return 0;
 }
 
@@ -320,40 +264,22 @@ int hs_ik(const abrb_chain_desc *d, int f32, int force_general, double max_dx, d
 
 int hs_frame_id(int n, const char *name) { return parse_frame(n, name); }
 
-// x = pinv(S, rcond) y for a 6x6 (K=6) or 3x3 (K=3) symmetric S with identity rows outside `active`.
-// which = 0: cheap route (returns 1 if it was conclusive, 0 if it asked for the fallback); which = 1: Jacobi.
-int hs_pinv(int K, const double *S, unsigned active, double rcond, const double *y, double *x, int which, int f32) {
-  auto run = [&](auto tag, auto kc) -> int {
-    typedef decltype(tag) T;
-    constexpr int KK = decltype(kc)::value;
-    T Sm[KK][KK], Sc[KK][KK], Si[KK], Sf[KK * KK], Lf[KK * KK], yi[KK], xo[KK];
-    T tr = 0;
-    for (int a = 0; a < KK; ++a) {
-      yi[a] = T(y[a]);
-      for (int b = 0; b < KK; ++b) Sm[a][b] = Sc[a][b] = T(S[a * KK + b]);
-      if ((active >> a) & 1u) tr += Sm[a][a];
-    }
-    const bool pd = chol<T, KK>(Sc, Si);
-    for (int a = 0; a < KK; ++a)
-      for (int b = 0; b < KK; ++b) {
-        Sf[a * KK + b] = (a == b && !((active >> a) & 1u)) ? tr : Sm[a][b];
-        Lf[a * KK + b] = Sc[a][b];
-      }
-    int ok = 1;
-    if (which == 0) {
-      T Sb[KK][KK];
-      for (int a = 0; a < KK; ++a)
-        for (int b = 0; b < KK; ++b) Sb[a][b] = Sf[a * KK + b];
-      ok = pd && pinv_solve_fast<T, KK>(Sb, Sc, Si, active, T(rcond), yi, xo);
-    } else {
-      for (int a = 0; a < KK * KK; ++a) Sf[a] = T(S[a]);
-      pinv_apply_sym<T, KK>(Sf, active, T(rcond), yi, xo);
-    }
-    for (int a = 0; a < KK; ++a) x[a] = ok ? double(xo[a]) : 0.0;
-    return ok;
-  };
-  if (K == 6) return f32 ? run(float(0), std::integral_constant<int, 6>()) : run(double(0), std::integral_constant<int, 6>());
-  if (K == 3) return f32 ? run(float(0), std::integral_constant<int, 3>()) : run(double(0), std::integral_constant<int, 3>());
-  return -1;
+// x = pinv(A A^T, rcond) y for a K x 6 matrix A (K = 6 or 3) through the one-sided Jacobi route of the OSC kernels
+// (which = 0, pinv_rows_jacobi_seq: the sequential walk over the schedule the warp-cooperative device code runs in
+// parallel), or x = pinv(S, rcond) y for a symmetric K x K matrix S through the cyclic Jacobi routine (which = 1).
+int hs_pinv(int K, const double *A_or_S, unsigned active, double rcond, const double *y, double *x, int which) {
+  if (K != 6 && K != 3) return -1;
+  if (which == 0) {
+    double zero[6] = {0, 0, 0, 0, 0, 0}, xz[6];
+    if (K == 6) pinv_rows_jacobi_seq<6, 6>(A_or_S, rcond, y, zero, false, x, xz);
+    else pinv_rows_jacobi_seq<6, 3>(A_or_S, rcond, y, zero, false, x, xz);
+    return 1;
+  }
+  double Sf[36], yi[6];
+  for (int a = 0; a < K * K; ++a) Sf[a] = A_or_S[a];
+  for (int a = 0; a < K; ++a) yi[a] = y[a];
+  if (K == 6) pinv_apply_sym<double, 6>(Sf, active, rcond, yi, x);
+  else pinv_apply_sym<double, 3>(Sf, active, rcond, yi, x);
+  return 1;
 }
 }

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"libabrb.so does not export {n}"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
-    assert lib.abrb_version() == 100
+    assert lib.abrb_version() == 200
 
 
 def test_struct_layouts_match_the_header():
@@ -72,9 +72,7 @@ def test_model_handles_and_error_codes_without_compute():
     bad.n_joints = 9
     assert lib.abrb_model_create(C.byref(bad), C.byref(h2)) == _abi.ESHAPE
     # controller parameter checks mirror the reference's exceptions
-    p = _abi.osc_params(6, kp=10, ki=0.5)
     hc = C.c_void_p()
-    assert lib.abrb_osc_create(h, C.byref(p), C.byref(hc)) == _abi.EUNSUP
     p = _abi.osc_params(6, kp=10, orientation_algorithm=3)
     assert lib.abrb_osc_create(h, C.byref(p), C.byref(hc)) == _abi.EUNSUP
     assert b"Invalid algorithm number" in lib.abrb_last_error()
@@ -85,10 +83,22 @@ def test_model_handles_and_error_codes_without_compute():
     assert lib.abrb_rbd_eval_f64(h, 99, None, None, None, 4, C.byref(out), None) == _abi.EFRAME
     assert lib.abrb_rbd_eval_f64(h, 13, None, None, None, -1, C.byref(out), None) == _abi.EINVAL
     assert lib.abrb_rbd_eval_f64(h, 13, None, None, None, 0, C.byref(out), None) == 0  # empty batch is a no-op
-    assert lib.abrb_osc_generate_f64(hc, 13, None, None, None, None, 6, None, 0, None, None, 0, None) == 0
-    assert lib.abrb_osc_generate_f64(hc, 13, None, None, None, None, 5, None, 0, None, None, 8, None) == _abi.EINVAL
-    assert lib.abrb_osc_set_option(hc, b"two_launch_min", 65536.0) == 0
+    assert lib.abrb_osc_generate_f64(hc, 13, None, None, None, None, 6, None, 0, None, None, None, 0, None) == 0
+    assert lib.abrb_osc_generate_f64(hc, 13, None, None, None, None, 5, None, 0, None, None, None, 8, None) == _abi.EINVAL
+    # integrated_error goes with ki != 0 and only with it (osc.py:81-82, :262-264)
+    dummy = (C.c_double * 48)()
+    assert lib.abrb_osc_generate_f64(hc, 13, None, None, None, None, 6, None, 0, None, None, dummy, 8, None) == _abi.EINVAL
+    assert b"integrated_error" in lib.abrb_last_error()
+    pk = _abi.osc_params(6, kp=10, ki=0.5)
+    hk = C.c_void_p()
+    assert lib.abrb_osc_create(h, C.byref(pk), C.byref(hk)) == 0
+    assert lib.abrb_osc_generate_f64(hk, 13, None, None, None, None, 6, None, 0, None, None, None, 8, None) == _abi.EINVAL
+    assert lib.abrb_osc_rollout_f64(hk, 13, None, None, None, None, 6, 4, 1e-3, None, None, None, None, 8, None) == _abi.EINVAL
+    assert lib.abrb_osc_generate_host_async_f64(hc, 13, None, None, None, None, 6, None, 0, None, None, None, 8, 2) == _abi.EINVAL
+    assert lib.abrb_osc_host_wait(hc, 0) == 0 and lib.abrb_osc_host_wait(hc, 5) == _abi.EINVAL
+    assert lib.abrb_osc_set_option(hc, b"host_chunk_states", 32768.0) == 0
     assert lib.abrb_osc_set_option(hc, b"no_such_option", 1.0) == _abi.EINVAL
+    assert lib.abrb_osc_destroy(hk) == 0
     assert lib.abrb_osc_destroy(hc) == 0 and lib.abrb_model_destroy(h) == 0
     jaco = _abi.chain_desc_from_dict(_abi.load_arm_json("jaco2"))
     assert lib.abrb_model_create(C.byref(jaco), C.byref(h)) == 0

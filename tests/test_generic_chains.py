@@ -87,7 +87,7 @@ def test_osc_on_random_chains(hostsim, n, dof, ortho):
     u, tr, acc = np.zeros((B, n)), np.zeros((B, n)), np.zeros((B, n))
     rc = hostsim.hs_osc(C.byref(cd), C.byref(p), 0, 0, hostsim.hs_frame_id(n, b"EE"), None, P(np.ascontiguousarray(q)),
                         P(np.ascontiguousarray(dq)), P(np.ascontiguousarray(target)), 6, None, 6, C.c_int64(B), P(u), P(tr),
-                        P(acc))
+                        P(acc), None)
     assert rc == 0
     scale = np.abs(ref).max(axis=1, keepdims=True)
     assert np.max(np.abs(u - ref) / scale) < 1e-8

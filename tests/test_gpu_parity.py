@@ -289,8 +289,7 @@ def test_single_state_contract():
     assert np.abs(u - ref).max() < 1e-9 * np.abs(ref).max()
     u *= -1  # CoppeliaSim.send_forces negates in place (interfaces/coppeliasim.py:204)
     assert ctrlr.training_signal.shape == (6,)
-    with pytest.raises(NotImplementedError):
-        OSC(rc, ki=0.1)
+    assert OSC(rc, ki=0.1).integrated_error.shape == (6,)  # osc.py:81-82
     with pytest.raises(Exception, match="Invalid algorithm number"):
         OSC(rc, orientation_algorithm=2)
 
@@ -372,42 +371,128 @@ def test_large_batch_deferred_pinv_states():
         assert np.allclose(small, u[slow[:64]], rtol=1e-9 if dtype == np.float64 else 1e-4, atol=0)
 
 
-def test_two_launch_mode_matches_single_launch():
-    """Optional two-launch mode of the 6-row OSC path (everything but the truncating-pinv states, then those states
-    from an index queue; abr_control_b200/csrc/kernels.cu, abrb_osc_set_option "two_launch_min").  It must agree with
-    the single-launch mode (the same rows in chunks below the threshold) for every row, repeatedly (the queue re-arms
-    itself), for batch sizes that grow, shrink and are not multiples of the warp size, with and without the
-    training-signal output."""
+def test_cooperative_pinv_every_lane_and_ragged_batches():
+    """The warp-cooperative truncating pseudo-inverse (abr_control_b200/csrc/abrb_coop.cuh) when EVERY lane of every warp
+    needs it (a 3-joint arm asked to control 6 task DOF: J M^-1 J^T is rank deficient for every state, osc.py:91-98),
+    i.e. eight passes of four states per warp, with batch sizes that leave ragged last warps / CTAs, fp64 and fp32,
+    with a secondary controller (two right-hand sides) — against the oracle."""
+    from oracle import osc_oracle
+
+    rng = np.random.default_rng(41)
+    for arm, n, dof in (("threejoint", 3, [True] * 6), ("twojoint", 2, [True, True, False, False, False, True]),
+                        ("threejoint", 3, [True, True, True, False, False, False])):
+        case = dict(arm=arm, osc=dict(kp=20, ctrlr_dof=dof), null=[("Damping", dict(kv=5))])
+        for B in (1, 31, 33, 127, 129, 300):
+            q, dq = rng.uniform(0.2, 2 * np.pi - 0.2, (B, n)), rng.uniform(-2, 2, (B, n))
+            target = rng.uniform(-1, 1, (B, 6))
+            ref, _ = osc_oracle.run_case(case, q, dq, target)
+            scale = np.abs(ref).max(axis=1, keepdims=True)
+            for dtype, tol in ((np.float64, 1e-8), (np.float32, 5e-3)):
+                ctrlr = _build_ctrl(_cfg(arm, dtype=dtype), case)
+                u = ctrlr.generate(q.astype(dtype), dq.astype(dtype), target.astype(dtype))
+                err = (np.abs(u - ref) / scale).max(axis=1)
+                assert np.isfinite(u).all() and np.quantile(err, 0.9) < tol and np.median(err) < tol * 0.1, (arm, dof, B, dtype, err.max())
+    # one waiting lane per warp at most: UR5 rows picked so that exactly the chosen lanes are singular
+    case = dict(arm="ur5", osc=dict(kp=50, ctrlr_dof=[True] * 6, use_C=True))
+    q = rng.uniform(0.3, 6.0, (256, 6))
+    q[5::32, 2] = 0.0  # elbow stretched: J loses rank
+    q[5::32, 4] = 0.0
+    dq, target = rng.uniform(-1, 1, (256, 6)), rng.uniform(-1, 1, (256, 6))
+    ref, _ = osc_oracle.run_case(case, q, dq, target)
+    u = _build_ctrl(_cfg("ur5"), case).generate(q, dq, target)
+    err = np.abs(u - ref).max(axis=1) / np.abs(ref).max(axis=1)
+    assert err.max() < 1e-6 and np.median(err) < 1e-12
+
+
+def test_unaligned_row_slices_are_accepted():
+    """Row slices of contiguous arrays start at element-aligned (not 16-byte aligned) addresses: q[1:] of an fp32 (B, 6)
+    tensor is 24 bytes in.  The kernels only need element alignment (scalar loads and stores)."""
     import torch
 
-    rng = np.random.default_rng(23)
-    case = dict(arm="ur5", osc=dict(kp=50, ctrlr_dof=[True] * 6, use_C=True), null=[("Damping", dict(kv=10))])
+    rc = _cfg("ur5", dtype=np.float32)
+    ctrlr = _build_ctrl(rc, dict(arm="ur5", osc=dict(kp=10, ctrlr_dof=[True] * 6)))
+    rng = np.random.default_rng(2)
+    q, dq, tg = (torch.as_tensor(rng.uniform(0, 6, (1001, 6)), device="cuda", dtype=torch.float32) for _ in range(3))
+    full = ctrlr.generate(q, dq, tg)
+    for lo in (1, 3, 501):
+        part = ctrlr.generate(q[lo:], dq[lo:], tg[lo:])
+        assert torch.equal(part, full[lo:])
+        out = torch.empty_like(q)
+        ctrlr.generate_into(q[lo:], dq[lo:], tg[lo:], out[lo:])
+        assert torch.equal(out[lo:], full[lo:])
+    M = rc.M(q[1:])
+    assert torch.equal(M, rc.M(q)[1:])
+
+
+def test_ki_integrator_sequences():
+    """ki != 0 (osc.py:81-82, :262-264): per-state integrated task-space error over a 12-call sequence, fp64 and fp32,
+    CUDA tensors and host arrays, against oracle controllers stepped the same way (one per state stream); the
+    single-state path keeps the reference's `integrated_error` attribute."""
+    import torch
+
+    from oracle import osc_oracle as oo
+
+    case = dict(arm="ur5", osc=dict(kp=30, ki=0.7, ctrlr_dof=[True] * 6, use_C=True), null=[("Damping", dict(kv=10))])
+    Bq, T = 40, 12
     for dtype, tol in ((np.float64, 1e-9), (np.float32, 2e-3)):
-        rc = _cfg("ur5", dtype=dtype)
-        ctrlr = _build_ctrl(rc, case)
-        ctrlr.set_option("two_launch_min", 16384)
-        for B in (20000, 40003, 16384):
-            q = rng.uniform(0, 2 * np.pi, (B, 6)).astype(dtype)
-            dq = rng.uniform(0, 5, (B, 6)).astype(dtype)
-            target = rng.uniform(-1, 1, (B, 6)).astype(dtype)
-            tv = rng.uniform(-0.5, 0.5, (B, 6)).astype(dtype)
-            for kw in ({}, {"target_velocity": tv}):
-                tq, tdq, tt = (torch.as_tensor(a, device="cuda") for a in (q, dq, target))
-                kwd = {k: torch.as_tensor(v, device="cuda") for k, v in kw.items()}
-                big = ctrlr.generate(tq, tdq, tt, **kwd)
-                big_train = ctrlr.training_signal.clone()
-                again = ctrlr.generate(tq, tdq, tt, **kwd)
-                assert torch.equal(big, again)  # deterministic, and the queue was re-armed
-                parts, parts_train = [], []
-                for s0 in range(0, B, 4096):
-                    sl = slice(s0, min(B, s0 + 4096))
-                    parts.append(ctrlr.generate(tq[sl], tdq[sl], tt[sl], **{k: v[sl] for k, v in kwd.items()}))
-                    parts_train.append(ctrlr.training_signal.clone())
-                ref, ref_train = torch.cat(parts), torch.cat(parts_train)
-                scale = ref.abs().amax(dim=1, keepdim=True)
-                assert float(((big - ref).abs() / scale).max()) < tol
-                assert float(((big_train - ref_train).abs() / scale).max()) < tol
-                assert bool(torch.isfinite(big).all())
+        for kind in ("torch", "numpy"):
+            rng = np.random.default_rng(9)
+            refs = []
+            for b in range(Bq):
+                rco = oo.RobotOracle("ur5", "fp64")
+                refs.append(oo.OSC(rco, null_controllers=[oo.Damping(rco, kv=10)], **case["osc"]))
+            ctrlr = _build_ctrl(_cfg("ur5", dtype=dtype), case)
+            for t in range(T):
+                q, dq, tg = rng.uniform(0, 2 * np.pi, (Bq, 6)), rng.uniform(0, 2, (Bq, 6)), rng.uniform(-1, 1, (Bq, 6))
+                ref = np.array([refs[b].generate(q[b], dq[b], tg[b]) for b in range(Bq)])
+                args = [a.astype(dtype) for a in (q, dq, tg)]
+                if kind == "torch":
+                    u = ctrlr.generate(*[torch.as_tensor(a, device="cuda") for a in args]).cpu().numpy()
+                else:
+                    u = ctrlr.generate(*args)
+                err = np.abs(u - ref).max(axis=1) / np.abs(ref).max(axis=1)
+                assert np.median(err) < tol and np.quantile(err, 0.9) < tol * 50, (dtype, kind, t, err.max())
+            (buf,) = ctrlr.integrated_error_batch.values()
+            got = buf.cpu().numpy() if kind == "torch" else buf
+            assert np.abs(got - np.array([c.err_sum for c in refs])).max() < (1e-10 if dtype == np.float64 else 1e-3)
+            ctrlr.reset_integrated_error()
+            assert not np.asarray(buf.cpu() if kind == "torch" else buf).any()
+    # single state: the reference's attribute
+    ctrlr = _build_ctrl(_cfg("ur5"), case)
+    rco = oo.RobotOracle("ur5", "fp64")
+    ref = oo.OSC(rco, null_controllers=[oo.Damping(rco, kv=10)], **case["osc"])
+    rng = np.random.default_rng(1)
+    for t in range(5):
+        q, dq, tg = rng.uniform(0, 6, 6), rng.uniform(0, 1, 6), rng.uniform(-1, 1, 6)
+        u, r = ctrlr.generate(q, dq, tg), ref.generate(q, dq, tg)
+        assert np.abs(u - r).max() < 1e-9 * np.abs(r).max()
+        assert np.abs(ctrlr.integrated_error - ref.err_sum).max() < 1e-12
+
+
+def test_config5_obstacle_avoidance_on_a_large_random_batch():
+    """BASELINE config 5 (Jaco2 OSC x,y,z + vmax + AvoidObstacles + Damping,
+    /root/reference/examples/CoppeliaSim/force_osc_xyz_avoid_obstacle.py:17-28) on 8192 uniformly random states, fp32
+    and fp64: EVERY state whose obstacle term is active and a sample of the others against the oracle."""
+    from oracle import osc_oracle as oo
+
+    rng = np.random.default_rng(55)
+    B = 8192
+    q, dq, target = rng.uniform(0, 2 * np.pi, (B, 6)), rng.uniform(0, 5, (B, 6)), rng.uniform(-1, 1, (B, 6))
+    obstacle = [0.09596, -0.2661, 0.64204, 0.05]
+    case = dict(arm="jaco2", osc=dict(kp=200, vmax=[0.5, 0], ctrlr_dof=[True, True, True, False, False, False]),
+                null=[("AvoidObstacles", dict(obstacles=[obstacle], threshold=0.2)), ("Damping", dict(kv=10))])
+    rco = oo.RobotOracle("jaco2", "fp64")
+    avoid = oo.AvoidObstacles(rco, obstacles=[obstacle], threshold=0.2)
+    active = np.array([np.any(avoid.generate(q[i]) != 0) for i in range(B)])
+    assert 200 < active.sum() < 6000  # the obstacle sits inside the arm's workspace
+    pick = np.concatenate([np.where(active)[0], np.where(~active)[0][::16]])
+    ref, _ = oo.run_case(case, q[pick], dq[pick], target[pick])
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    for dtype, med, p99 in ((np.float64, 1e-12, 1e-8), (np.float32, 2e-5, 5e-3)):
+        ctrlr = _build_ctrl(_cfg("jaco2", dtype=dtype), case)
+        u = ctrlr.generate(q.astype(dtype), dq.astype(dtype), target.astype(dtype))
+        err = (np.abs(u[pick] - ref) / scale).max(axis=1)
+        assert np.isfinite(u).all() and np.median(err) < med and np.quantile(err, 0.99) < p99, (dtype, np.median(err), err.max())
 
 
 def test_full_size_properties():
@@ -485,3 +570,114 @@ def test_rollout_matches_stepwise():
         qs = qs + dqs * dt
         assert np.abs(traj["u"][t] - u).max() < 1e-7 * max(1.0, np.abs(u).max())
     assert np.abs(qf - qs).max() < 1e-9 and np.abs(dqf - dqs).max() < 1e-7
+
+
+@pytest.mark.parametrize("name,osc_kw", [("xyz", dict(kp=10)), ("6dof_C_ki", dict(kp=10, ki=0.2, ctrlr_dof=[True] * 6, use_C=True))])
+def test_rollout_vs_oracle_stepped_loop(name, osc_kw):
+    """BASELINE config 4's kernel against the ORACLE stepped the same way: u from oracle/osc_oracle.py, plant
+    ddq = M^-1 (u + g - C dq) from oracle/rbd_oracle.py, semi-implicit Euler as
+    /root/reference/abr_control/arms/twojoint/arm_sim.py:131-132 (dq += ddq dt; q += dq dt), 48 trajectories x 32 steps."""
+    from oracle import osc_oracle as oo
+    from oracle import rbd_oracle
+
+    Bq, steps, dt = 48, 32, 1e-3
+    q, dq, target, _ = cases.states("ur5", Bq)
+    dq = dq * 0.1
+    ctrlr = _build_ctrl(_cfg("ur5"), dict(arm="ur5", osc=osc_kw))
+    qf, dqf, traj = ctrlr.rollout(q, dq, target, steps=steps, dt=dt)
+    ch = rbd_oracle.ChainOracle("ur5")
+    refs = [oo.OSC(oo.RobotOracle("ur5", "fp64"), **osc_kw) for _ in range(Bq)]
+    qs, dqs = q.copy(), dq.copy()
+    for t in range(steps):
+        u = np.array([refs[b].generate(qs[b], dqs[b], target[b]) for b in range(Bq)])
+        rhs = u + ch.g(qs) - np.einsum("bij,bj->bi", ch.C(qs, dqs), dqs)
+        ddq = np.linalg.solve(ch.M(qs), rhs[..., None])[..., 0]
+        dqs = dqs + ddq * dt
+        qs = qs + dqs * dt
+        # the closed loop amplifies rounding differences slowly: compare each step's u on the oracle's own state history
+        assert np.abs(traj["u"][t] - u).max() < 1e-6 * max(1.0, np.abs(u).max()), t
+        assert np.abs(traj["q"][t] - qs).max() < 1e-8 and np.abs(traj["dq"][t] - dqs).max() < 1e-6, t
+    assert np.abs(qf - qs).max() < 1e-8 and np.abs(dqf - dqs).max() < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Chains that are not one of the four reference arms: every joint count the library is built for, orthonormal and
+# sheared constant frames (SURVEY.md S8f row 4, the generic `_calc_T` contract of base_config.py:729-737), on the
+# device through the C ABI — the same cases tests/test_generic_chains.py runs through the host instantiation.
+@pytest.mark.parametrize("ortho", [True, False])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7])
+def test_random_chains_rigid_body_quantities_on_the_device(n, ortho):
+    from abr_control_b200.arms.base_config import BaseConfig
+    from oracle import rbd_oracle as ro
+    from test_generic_chains import random_chain
+
+    desc = random_chain(n, ortho, 100 * n + ortho)
+    c = ro.ChainOracle(desc)
+    rng = np.random.default_rng(n)
+    q, dq = rng.uniform(0, 2 * np.pi, (70, n)), rng.uniform(-3, 3, (70, n))
+    for dtype, tol in ((np.float64, 1e-11), (np.float32, 3e-4)):
+        rc = BaseConfig(desc, dtype=dtype)
+        assert rc.N_JOINTS == n
+        for fr in ("EE", f"link{n}", f"joint{n - 1}", "link0", f"link{(n + 1) // 2}"):
+            o = rc.eval(q.astype(dtype), dq.astype(dtype), name=fr, want=("Tx", "R", "J", "dJ"))
+            assert np.abs(o["Tx"] - c.Tx(fr, q)).max() < tol
+            assert np.abs(o["R"] - c.R(fr, q)).max() < tol
+            assert np.abs(o["J"] - c.J(fr, q)).max() < tol
+            assert np.abs(o["dJ"] - c.dJ(fr, q, dq)).max() < tol * 30
+        o = rc.eval(q.astype(dtype), dq.astype(dtype), want=("M", "g", "C"))
+        for k, ref in (("M", c.M(q)), ("g", c.g(q)), ("C", c.C(q, dq))):
+            assert np.abs(o[k] - ref).max() < tol * 10 * max(1.0, np.abs(ref).max()), (k, dtype)
+
+
+@pytest.mark.parametrize("n,dof,ortho", [(1, [1, 0, 0, 0, 0, 0], True), (3, [1, 1, 1, 0, 0, 0], True),
+                                         (4, [1, 1, 1, 0, 1, 0], True), (5, [1, 1, 1, 1, 1, 0], True),
+                                         (5, [1, 1, 1, 1, 1, 1], False), (6, [1, 1, 1, 1, 1, 1], False),
+                                         (7, [1, 1, 1, 1, 1, 1], True), (7, [1, 1, 1, 0, 0, 0], False)])
+def test_random_chains_osc_rollout_and_controllers_on_the_device(n, dof, ortho):
+    """OSC (incl. the redundant 7-joint arm and a 5-joint arm asked for 6 task DOF: every state on the cooperative
+    pseudo-inverse route), the closed-loop rollout, Joint and Sliding on random chains vs the oracle."""
+    import torch
+
+    from abr_control_b200.arms.base_config import BaseConfig
+    from abr_control_b200.controllers import OSC, Damping, Joint, Sliding
+    from oracle import osc_oracle as oo
+    from test_generic_chains import random_chain
+
+    desc = random_chain(n, ortho, 7 * n + sum(dof), shear=2e-3)
+    case = dict(arm=desc, osc=dict(kp=25, ko=15, ctrlr_dof=[bool(d) for d in dof], use_C=True), null=[("Damping", dict(kv=4))])
+    rng = np.random.default_rng(n + 40)
+    B = 70
+    q, dq, target = rng.uniform(0, 2 * np.pi, (B, n)), rng.uniform(-2, 2, (B, n)), rng.uniform(-0.6, 0.6, (B, 6))
+    ref, _ = oo.run_case(case, q, dq, target)
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    rank_deficient = sum(dof) > n
+    for dtype, tol in ((np.float64, 1e-8), (np.float32, 2e-3)):
+        rc = BaseConfig(desc, dtype=dtype)
+        ctrlr = OSC(rc, null_controllers=[Damping(rc, kv=4)], **case["osc"])
+        u = ctrlr.generate(q.astype(dtype), dq.astype(dtype), target.astype(dtype))
+        err = (np.abs(u - ref) / scale).max(axis=1)
+        assert np.median(err) < tol and np.quantile(err, 0.9) < tol * (1e3 if rank_deficient else 30), (dtype, err.max())
+    # rollout = stepwise generate + plant with the device's own M, g, C
+    rc = BaseConfig(desc)
+    ctrlr = OSC(rc, **case["osc"])
+    q0, dq0 = q[:33], 0.1 * dq[:33]
+    qf, dqf, traj = ctrlr.rollout(q0, dq0, target[:33], steps=6, dt=1e-3)
+    qs, dqs = q0.copy(), dq0.copy()
+    for t in range(6):
+        u = ctrlr.generate(qs, dqs, target[:33])
+        d = rc.eval(qs, dqs, want=("M", "g", "C"))
+        ddq = np.linalg.solve(d["M"], (u + d["g"] - np.einsum("bij,bj->bi", d["C"], dqs))[..., None])[..., 0]
+        dqs = dqs + ddq * 1e-3
+        qs = qs + dqs * 1e-3
+        assert np.abs(traj["u"][t] - u).max() < 1e-6 * max(1.0, np.abs(u).max())
+    assert np.abs(qf - qs).max() < 1e-9
+    # Joint and Sliding (joint space) through their kernels
+    tq = rng.uniform(0, 2 * np.pi, (B, n))
+    uj = Joint(rc, kp=12, kv=3).generate(q, dq, tq)
+    refj = np.array([oo.Joint(oo.RobotOracle(desc), kp=12, kv=3).generate(q[i], dq[i], tq[i]) for i in range(B)])
+    assert np.abs(uj - refj).max() < 1e-9 * max(1.0, np.abs(refj).max())
+    if n >= 3:
+        tg3 = rng.uniform(-0.4, 0.4, (B, 3))
+        us = Sliding(rc, kd=40.0, lamb=12.0).generate(q, dq, tg3)
+        refs, _ = oo.run_sliding_case(dict(arm=desc, ctrl=dict(kd=40.0, lamb=12.0)), q, dq, tg3, None, None)
+        assert np.max(np.abs(us - refs) / np.abs(refs).max(axis=1, keepdims=True)) < 1e-8

@@ -50,15 +50,34 @@ def test_osc_options_survive_parameter_changes():
     rc = ur5.Config()
     damp = Damping(rc, kv=10)
     c = OSC(rc, kp=10, ctrlr_dof=[True] * 6, null_controllers=[damp])
-    c.set_option("two_launch_min", 65536)
+    c.set_option("host_chunk_states", 32768)
     h1 = c._native()
-    assert h1 and c._options == {"two_launch_min": 65536.0}
-    damp.kv = 5.0
-    damp._dirty()  # a secondary controller changed: the owner rebuilds its native handle ...
+    assert h1 and c._options == {"host_chunk_states": 32768.0}
+    damp.kv = 5.0  # a secondary controller changed: the owner drops its native handle ...
+    assert c._handle is None
     h2 = c._native()
-    assert h2 and c._options == {"two_launch_min": 65536.0}  # ... and re-applies its options
+    assert h2 and c._options == {"host_chunk_states": 32768.0}  # ... rebuilds it and re-applies its options
+    c.use_g = False  # the reference reads the controller's own attributes per call too (osc.py:300)
+    assert c._handle is None and c._native()
+    c.record_training_signal = False  # not a parameter of the native handle
+    assert c._handle is not None
     with pytest.raises(RuntimeError):
         c.set_option("no_such_option", 1)
+
+
+def test_ki_keeps_the_reference_attribute_and_owners_are_weak():
+    import gc
+    import weakref
+
+    rc = ur5.Config()
+    damp = Damping(rc, kv=10)
+    c = OSC(rc, kp=10, ki=0.1, null_controllers=[damp])
+    assert c.integrated_error.shape == (6,) and not c.integrated_error.any()  # osc.py:81-82
+    assert c._native()
+    r = weakref.ref(c)
+    del c
+    gc.collect()
+    assert r() is None and len(damp._owners) == 0  # a secondary controller does not keep its OSCs alive
 
 
 def test_osc_parameter_marshalling_of_joint_limits_inside_osc():

@@ -33,7 +33,7 @@ def hs_rbd(hs, arm, q, dq, frame, xoff=None, f32=0, general=0):
     return out
 
 
-def hs_osc(hs, cs, q, dq, target, tv, f32=0, general=0):
+def hs_osc(hs, cs, q, dq, target, tv, f32=0, general=0, ierr=None):
     cd = _abi.chain_desc_from_dict(_abi.load_arm_json(cs["arm"]))
     n, B = cd.n_joints, len(q)
     nulls = [_abi.null_params(k, n, **kw) for k, kw in cs.get("null", [])]
@@ -44,7 +44,7 @@ def hs_osc(hs, cs, q, dq, target, tv, f32=0, general=0):
     tvv = np.ascontiguousarray(tv) if cs.get("tv") else None
     rc = hs.hs_osc(C.byref(cd), C.byref(p), f32, general, fid, P(xo), P(np.ascontiguousarray(q)),
                    P(np.ascontiguousarray(dq)), P(np.ascontiguousarray(target)), 6, P(tvv), 6, C.c_int64(B), P(u), P(tr),
-                   P(acc))
+                   P(acc), P(ierr))
     assert rc == 0
     return u, tr, acc
 
@@ -208,33 +208,53 @@ def test_singular_states_pinv_branch(hostsim):
     assert np.max(np.abs(u - ref) / np.abs(ref).max(axis=1, keepdims=True)) < 1e-9
 
 
-def test_two_launch_halves_reproduce_the_single_pass(hostsim):
-    """osc_eval MODE 1 (stop at a truncating-pinv state and write the record) followed by MODE 2 (finish from the
-    record on a fresh scratch) must give the single-pass result for every state; the kernels of the two-launch mode
-    are exactly these two halves."""
-    rng = np.random.default_rng(5)
-    B = 1500
-    q, dq, target = rng.uniform(0, 2 * np.pi, (B, 6)), rng.uniform(0, 5, (B, 6)), rng.uniform(-1, 1, (B, 6))
-    tv = rng.uniform(-0.5, 0.5, (B, 6))
-    for cs in (dict(arm="ur5", osc=dict(kp=50, ctrlr_dof=[True] * 6, use_C=True), null=[("Damping", dict(kv=10))]),
-               dict(arm="ur5", osc=dict(kp=20, ko=30, ctrlr_dof=[True, True, True, False, True, True], use_g=False), tv=True),
-               dict(arm="jaco2", osc=dict(kp=30, ctrlr_dof=[True] * 6),
-                    null=[("AvoidObstacles", dict(obstacles=[[0.1, -0.2, 0.5, 0.08]], threshold=0.5))])):
-        cd = _abi.chain_desc_from_dict(_abi.load_arm_json(cs["arm"]))
-        nulls = [_abi.null_params(k, 6, **kw) for k, kw in cs.get("null", [])]
-        p = _abi.osc_params(6, null=nulls, **cs["osc"])
-        tvv = np.ascontiguousarray(tv) if cs.get("tv") else None
-        for f32, tol in ((0, 1e-12), (1, 1e-5)):
-            a, ta, _ = hs_osc(hostsim, cs, q, dq, target, tv, f32=f32)
-            b, tb, n_def = np.zeros((B, 6)), np.zeros((B, 6)), C.c_int64(0)
-            rc = hostsim.hs_osc_split(C.byref(cd), C.byref(p), f32, 0, hostsim.hs_frame_id(6, b"EE"), None, P(q), P(dq),
-                                      P(target), 6, P(tvv), 6, C.c_int64(B), P(b), P(tb), C.byref(n_def))
-            assert rc == 0
-            if cs["arm"] == "ur5" and all(cs["osc"]["ctrlr_dof"]):
-                assert 25 < n_def.value < 100  # ~3.8 % of uniformly random UR5 states
-            scale = np.abs(a).max(axis=1, keepdims=True)
-            assert np.max(np.abs(a - b) / scale) < tol, (cs["arm"], f32)
-            assert np.max(np.abs(ta - tb) / scale) < tol
+def test_jacobi_pinv_route_vs_numpy(hostsim):
+    """The one-sided Jacobi SVD of the rows of A (abrb_math.cuh: the sequential walk over the schedule the GPU runs
+    warp-cooperatively) against numpy.linalg.pinv(A A^T, rcond) — the call OSC._Mx makes (osc.py:143-145) — on matrices
+    with 0, 1, 2, 3 singular values below the cut-off, rank-deficient ones and zero rows (uncontrolled DOF)."""
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    for K in (6, 3):
+        for trial in range(200):
+            U, _ = np.linalg.qr(rng.normal(size=(K, K)))
+            V, _ = np.linalg.qr(rng.normal(size=(6, 6)))
+            n_small = trial % 4 if K == 6 else trial % 3
+            sv = rng.uniform(0.3, 3.0, K)
+            sv[:n_small] = rng.uniform(1e-9, 3e-3, n_small) if trial % 5 else 0.0  # squared: below 1e-4 * max
+            A = (U * sv) @ V[:K]
+            if trial % 7 == 0:
+                A[K - 1] = 0.0  # an uncontrolled row
+            y = rng.normal(size=K)
+            if trial % 7 == 0:
+                y[K - 1] = 0.0
+            x = np.zeros(K)
+            assert hostsim.hs_pinv(K, P(np.ascontiguousarray(A)), (1 << K) - 1, C.c_double(1e-4), P(y), P(x), 0) == 1
+            S = A @ A.T
+            lam = np.linalg.eigvalsh(S)
+            if np.min(np.abs(lam / lam.max() - 1e-4)) < 1e-7:
+                continue  # an eigenvalue on the cut-off itself: either side is right
+            ref = np.linalg.pinv(S, rcond=1e-4, hermitian=True) @ y
+            worst = max(worst, np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-30))
+    assert worst < 1e-9, worst
+
+
+def test_ki_integrator_sequence_vs_oracle(hostsim):
+    """ki != 0: every state carries its own integrated task-space error (osc.py:81-82, :262-264); 12 consecutive calls
+    on 8 independent state streams against 8 oracle controllers stepped the same way."""
+    cs = dict(arm="ur5", osc=dict(kp=30, ki=0.7, ctrlr_dof=[True] * 6, use_C=True), null=[("Damping", dict(kv=10))])
+    Bq, T = 8, 12
+    rng = np.random.default_rng(9)
+    ierr = np.zeros((Bq, 6))
+    ctrl = []
+    for b in range(Bq):
+        rc = oo.RobotOracle("ur5", "fp64")
+        ctrl.append(oo.OSC(rc, null_controllers=[oo.Damping(rc, kv=10)], **cs["osc"]))
+    for t in range(T):
+        q, dq, target = rng.uniform(0, 2 * np.pi, (Bq, 6)), rng.uniform(0, 2, (Bq, 6)), rng.uniform(-1, 1, (Bq, 6))
+        u, _, _ = hs_osc(hostsim, cs, q, dq, target, None, ierr=ierr)
+        ref = np.array([ctrl[b].generate(q[b], dq[b], target[b]) for b in range(Bq)])
+        assert np.max(np.abs(u - ref) / np.abs(ref).max(axis=1, keepdims=True)) < 1e-9, t
+        assert np.abs(ierr - np.array([c.err_sum for c in ctrl])).max() < 1e-12
 
 
 def test_non_finite_states_terminate_and_stay_local(hostsim):
