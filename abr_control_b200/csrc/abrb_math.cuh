@@ -145,7 +145,11 @@ struct StridedStore {
 template <int N, bool ORTHO>
 struct KinSlots {
   static constexpr int kT = 0, kZ = 3 * N, kPl = 6 * N, kR0 = 9 * N, kR1 = 12 * N, kS0 = 15 * N, kS1 = 18 * N;
-  static constexpr int kCount = ORTHO ? 9 * N : 21 * N;
+  // kPark: N (N + 1) / 2 slots where osc_eval parks the Cholesky factor of M while the task-space system is solved
+  // (it also re-uses the 3 N link-COM slots at kPl for 1/diag(L), g and C dq).  The non-orthonormal layout has 12 N
+  // slots (R_k columns / R_k^-1 rows) that are dead by then; the orthonormal one gets the extra slots.
+  static constexpr int kPark = 9 * N;
+  static constexpr int kCount = ORTHO ? 9 * N + N * (N + 1) / 2 : (21 * N > 9 * N + N * (N + 1) / 2 ? 21 * N : 9 * N + N * (N + 1) / 2);
 };
 
 template <typename T, int N, bool ORTHO_, template <typename, int> class Store = RegStore>

@@ -352,8 +352,38 @@ ABRB_HD void osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
   for (int r = 0; r < KD; ++r) y[r] = ((O.dof_mask >> r) & 1u) ? err[r] : T(0);
 
   K.sync();
-  // ---- M = L L^T ;  A <- rows of (L^-1 J^T)^T ;  S = J M^-1 J^T = A A^T   (osc.py:136-137)
+  // ---- M = L L^T   (osc.py:136)
   chol<T, N>(M, Mi);
+  // ---- secondary controllers that go through the null-space filter  I - J^T Mx J M^-1  (osc.py:310-318): their
+  //      task-space image z = J M^-1 u_null = A (L^-1 u_null) is formed so that Mx is applied to y and z in ONE place
+  //      (the truncating route decomposes once for both right-hand sides).  w = L^-1 u_null is taken here, while L is
+  //      at hand; z itself falls out of the S loop below.
+  T w[N];
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) w[k] = T(0);
+  if (any_null) {
+    if (any_avoid) {
+      T Lf[N * N];
+      ABRB_UNROLL
+      for (int a = 0; a < N; ++a)
+        ABRB_UNROLL
+      for (int b = 0; b < N; ++b) Lf[a * N + b] = M[a][b];
+      for (int i = 0; i < O.n_null; ++i) {
+        if (O.nul[i].kind == kNullAvoid) {
+          T ua[N], qa[N];  // private copies: only these (not the caller's register arrays) have their address taken
+          ABRB_UNROLL
+          for (int k = 0; k < N; ++k) qa[k] = q[k];
+          avoid_generate<T, N, ORTHO>(P, O.nul[i], qa, Lf, ua);
+          ABRB_UNROLL
+          for (int k = 0; k < N; ++k) un[k] += ua[k];
+        }
+      }
+    }
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) w[k] = un[k];
+    fwd_solve<T, N>(M, Mi, w);  // L^-1 u_null
+  }
+  // ---- A <- rows of (L^-1 J^T)^T   (in place over J)
   ABRB_UNROLL
   for (int r = 0; r < KD; ++r) {
     T row[N];
@@ -363,13 +393,34 @@ ABRB_HD void osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) K.s.st(Aslot(r, k), row[k]);
   }
-  // S is built straight into the array that is then factorised in place
+  // ---- nothing below needs L, 1/diag(L), g, C dq, u, u_null until the task-space solve is done: with the scratch in
+  //      shared memory they are parked there (slots that are free by now) instead of being carried in registers across
+  //      the 6x6 factorisation, where the register allocator would otherwise spill them to local memory
+  constexpr bool PARK = K_::kSharedScratch;
+  typedef typename K_::S SL;
+  if (PARK) {
+    int li = 0;
+    ABRB_UNROLL
+    for (int a = 0; a < N; ++a) {
+      ABRB_UNROLL
+      for (int b = 0; b < N; ++b)
+        if (b <= a) K.s.st(SL::kPark + li++, M[a][b]);
+      K.s.st(SL::kPl + a, Mi[a]);
+      K.s.st(SL::kPl + N + a, g[a]);
+      K.s.st(SL::kPl + 2 * N + a, (PLANT || O.use_C) ? cdq[a] : T(0));
+    }
+  }
+  // ---- S = J M^-1 J^T = A A^T (osc.py:137), built straight into the array that is then factorised in place; z = A w
   T Sc[KD][KD], Si[KD];
   ABRB_UNROLL
   for (int a = 0; a < KD; ++a) {
     T ra[N];
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) ra[k] = K.s.ld(Aslot(a, k));
+    T za = T(0);
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) za += ra[k] * w[k];
+    z[a] = ((O.dof_mask >> a) & 1u) ? za : T(0);
     ABRB_UNROLL
     for (int b = 0; b < KD; ++b) {
       if (b <= a) {
@@ -422,41 +473,6 @@ ABRB_HD void osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
       fast = rcond * tr * sqrt_t(fro) < T(1);
     }
   }
-  // ---- secondary controllers that go through the null-space filter  I - J^T Mx J M^-1  (osc.py:310-318): their
-  //      task-space image z = J M^-1 u_null is formed here so that Mx is applied to y and z in ONE place (the
-  //      truncating route decomposes once for both right-hand sides)
-  ABRB_UNROLL
-  for (int r = 0; r < KD; ++r) z[r] = T(0);
-  if (any_null) {
-    if (any_avoid) {
-      T Lf[N * N];
-      ABRB_UNROLL
-      for (int a = 0; a < N; ++a)
-        ABRB_UNROLL
-      for (int b = 0; b < N; ++b) Lf[a * N + b] = M[a][b];
-      for (int i = 0; i < O.n_null; ++i) {
-        if (O.nul[i].kind == kNullAvoid) {
-          T ua[N], qa[N];  // private copies: only these (not the caller's register arrays) have their address taken
-          ABRB_UNROLL
-          for (int k = 0; k < N; ++k) qa[k] = q[k];
-          avoid_generate<T, N, ORTHO>(P, O.nul[i], qa, Lf, ua);
-          ABRB_UNROLL
-          for (int k = 0; k < N; ++k) un[k] += ua[k];
-        }
-      }
-    }
-    T w[N];
-    ABRB_UNROLL
-    for (int k = 0; k < N; ++k) w[k] = un[k];
-    fwd_solve<T, N>(M, Mi, w);  // L^-1 u_null
-    ABRB_UNROLL
-    for (int r = 0; r < KD; ++r) {
-      T s = T(0);
-      ABRB_UNROLL
-      for (int k = 0; k < N; ++k) s += K.s.ld(Aslot(r, k)) * w[k];
-      z[r] = ((O.dof_mask >> r) & 1u) ? s : T(0);
-    }
-  }
   // y <- Mx y,  z <- Mx z: two triangular solves in the regular case ...
   if (fast) {
     fwd_solve<T, KD>(Sc, Si, y);
@@ -469,6 +485,18 @@ ABRB_HD void osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
   // ... and the truncating pseudo-inverse otherwise (always in double: the matrices that end up here have eigenvalue
   // ratios down to 1e-16).  When nothing is below the cut-off it returns S^-1 y itself, as numpy's pinv does.
   coop.template pinv<T, N, KD>(!fast, K, y, z, any_null, double(rcond));
+  if (PARK) {
+    int li = 0;
+    ABRB_UNROLL
+    for (int a = 0; a < N; ++a) {
+      ABRB_UNROLL
+      for (int b = 0; b < N; ++b)
+        if (b <= a) M[a][b] = K.s.ld(SL::kPark + li++);
+      Mi[a] = K.s.ld(SL::kPl + a);
+      g[a] = K.s.ld(SL::kPl + N + a);
+      cdq[a] = K.s.ld(SL::kPl + 2 * N + a);
+    }
+  }
 
   // J^T x = L (A^T x)   (osc.py:285-288)
   auto JT_apply = [&](const T *x, T *out) {
