@@ -27,81 +27,212 @@ struct CoopLayout {
   static constexpr int kSlots = 2 * KD + (COPY_A ? KD * N : 0);
 };
 
-// Decompose the states of the lanes in `mask` (warp-uniform, non-zero).  `arow`: where row r, column k of A of lane o
-// is found: abase[aslot(r, k) * 32 + o].  Not inlined: the hot path only pays a call, and the routine's registers are
-// its own.
-template <typename T, int N, int KD, class ASlot>
-__device__ __noinline__ void coop_pinv_warp(unsigned mask, const T *abase, T *xyz, int lane, double rcond, bool two) {
+// One-sided Jacobi SVD of NS independent KD x N matrices (NS = 1 or 2, interleaved: the rounds are dependent chains, so a
+// second state rides along almost for free) whose row `sub` this lane loaded into `me[s].b` (lanes sub >= KD of the
+// 8-lane group hold zero rows), followed by x = pinv(A A^T, rcond) y for the two right-hand sides: on return EVERY lane
+// of the group holds xy[s][] (and xz[s][] if `two`).  All 32 lanes of the warp must call it together.
+template <int N, int KD, int NS>
+__device__ __forceinline__ void coop_jacobi_group(JacobiRow<N, KD> (&me)[NS], int sub, int gbase, const bool (&owner)[NS],
+                                                  const double (&y)[NS][KD], const double (&z)[NS][KD], double rcond,
+                                                  bool two, double (&xy)[NS][KD], double (&xz)[NS][KD]) {
   constexpr unsigned kFull = 0xffffffffu;
   constexpr int NRR = KD + (KD & 1);
-  const int sub = lane & (kCoopGroup - 1), grp = lane / kCoopGroup, gbase = lane & ~(kCoopGroup - 1);
-  while (mask != 0u) {
-    const unsigned found = __fns(mask, 0u, grp + 1);  // the (grp+1)-th waiting lane, if any
-    const bool have = found != 0xffffffffu;
-    const int o = have ? (int)found : 0;
-    JacobiRow<N, KD> me, other;
-    const bool owner = have && sub < KD;
+  JacobiRow<N, KD> other[NS];
 #pragma unroll
-    for (int k = 0; k < N; ++k) me.b[k] = owner ? double(abase[ASlot::at(sub, k) * 32 + o]) : 0.0;
+  for (int s = 0; s < NS; ++s)
 #pragma unroll
-    for (int k = 0; k < KD; ++k) me.v[k] = k == sub ? 1.0 : 0.0;
+    for (int k = 0; k < KD; ++k) me[s].v[k] = k == sub ? 1.0 : 0.0;
 #pragma unroll 1
-    for (int sweep = 0; sweep < kJacobiMaxSweeps; ++sweep) {
-      bool big = false;
+  for (int sweep = 0; sweep < kJacobiMaxSweeps; ++sweep) {
+    bool big = false;
 #pragma unroll 1
-      for (int r = 0; r < NRR - 1; ++r) {
-        const int p = sub < NRR ? rr_partner(NRR, sub, r) : sub;
+    for (int r = 0; r < NRR - 1; ++r) {
+      const int p = sub < NRR ? rr_partner(NRR, sub, r) : sub;
 #pragma unroll
-        for (int k = 0; k < N; ++k) other.b[k] = __shfl_sync(kFull, me.b[k], gbase + p);
+      for (int s = 0; s < NS; ++s) {
 #pragma unroll
-        for (int k = 0; k < KD; ++k) other.v[k] = __shfl_sync(kFull, me.v[k], gbase + p);
-        if (sub < NRR) big = (jacobi_pair<N, KD>(sub < p, me, other) == 2) || big;
+        for (int k = 0; k < N; ++k) other[s].b[k] = __shfl_sync(kFull, me[s].b[k], gbase + p);
+#pragma unroll
+        for (int k = 0; k < KD; ++k) other[s].v[k] = __shfl_sync(kFull, me[s].v[k], gbase + p);
       }
-      if (!__any_sync(kFull, big)) break;
+      if (sub < NRR) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) big = (jacobi_pair<N, KD>(sub < p, me[s], other[s]) == 2) || big;
+      }
     }
+    if (!__any_sync(kFull, big)) break;
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
     // squared singular values, the cut-off (numpy.linalg.pinv: s <= rcond * max(s) is dropped) and the two products
     double s2 = 0.0;
 #pragma unroll
-    for (int k = 0; k < N; ++k) s2 += me.b[k] * me.b[k];
+    for (int k = 0; k < N; ++k) s2 += me[s].b[k] * me[s].b[k];
     double smax = s2;
 #pragma unroll
     for (int d = 1; d < kCoopGroup; d <<= 1) {
       const double t = __shfl_xor_sync(kFull, smax, d);
       smax = t > smax ? t : smax;
     }
-    const bool keep = owner && s2 > rcond * smax;
+    const bool keep = owner[s] && s2 > rcond * smax;
     double cy = 0.0, cz = 0.0;
     if (keep) {
 #pragma unroll
       for (int k = 0; k < KD; ++k) {
-        cy += me.v[k] * double(xyz[k * 32 + o]);
-        cz += me.v[k] * double(xyz[(KD + k) * 32 + o]);
+        cy += me[s].v[k] * y[s][k];
+        cz += me[s].v[k] * z[s][k];
       }
-#if ABRB_FAST_DIV
       const double is2 = inv_t(s2);
-#else
-      const double is2 = 1.0 / s2;
-#endif
       cy *= is2;
       cz *= is2;
     }
-    __syncwarp();  // every lane of the group has read y, z before they are overwritten
 #pragma unroll
     for (int k = 0; k < KD; ++k) {
-      double xy = cy * me.v[k], xz = cz * me.v[k];
+      double a = cy * me[s].v[k], c = cz * me[s].v[k];
 #pragma unroll
       for (int d = 1; d < kCoopGroup; d <<= 1) {
-        xy += __shfl_xor_sync(kFull, xy, d);
-        if (two) xz += __shfl_xor_sync(kFull, xz, d);
+        a += __shfl_xor_sync(kFull, a, d);
+        if (two) c += __shfl_xor_sync(kFull, c, d);
       }
-      if (have && sub == 0) {
-        xyz[k * 32 + o] = T(xy);
-        if (two) xyz[(KD + k) * 32 + o] = T(xz);
+      xy[s][k] = a;
+      xz[s][k] = c;
+    }
+  }
+}
+
+// Decompose the states of the lanes in `mask` (warp-uniform, non-zero) IN LINE: group g of the warp takes the g-th
+// waiting lane, four states per pass.  `ASlot`: where row r, column k of A of lane o is found:
+// abase[ASlot::at(r, k) * 32 + o].  y, z are read from, and Mx y, Mx z written to, xyz[(i) * 32 + o].  Not inlined: the
+// hot path only pays a call, and the routine's registers are its own.
+template <typename T, int N, int KD, class ASlot>
+__device__ __noinline__ void coop_pinv_warp(unsigned mask, const T *abase, T *xyz, int lane, double rcond, bool two) {
+  const int sub = lane & (kCoopGroup - 1), grp = lane / kCoopGroup, gbase = lane & ~(kCoopGroup - 1);
+  while (mask != 0u) {
+    const unsigned found = __fns(mask, 0u, grp + 1);  // the (grp+1)-th waiting lane, if any
+    const bool have = found != 0xffffffffu;
+    const int o = have ? (int)found : 0;
+    JacobiRow<N, KD> me[1];
+    const bool owner[1] = {have && sub < KD};
+#pragma unroll
+    for (int k = 0; k < N; ++k) me[0].b[k] = owner[0] ? double(abase[ASlot::at(sub, k) * 32 + o]) : 0.0;
+    double y[1][KD], z[1][KD], xy[1][KD], xz[1][KD];
+#pragma unroll
+    for (int k = 0; k < KD; ++k) {
+      y[0][k] = double(xyz[k * 32 + o]);
+      z[0][k] = double(xyz[(KD + k) * 32 + o]);
+    }
+    coop_jacobi_group<N, KD, 1>(me, sub, gbase, owner, y, z, rcond, two, xy, xz);
+    __syncwarp();  // every lane of the group has read y, z before they are overwritten
+    if (have && sub == 0) {
+#pragma unroll
+      for (int k = 0; k < KD; ++k) {
+        xyz[k * 32 + o] = T(xy[0][k]);
+        if (two) xyz[(KD + k) * 32 + o] = T(xz[0][k]);
       }
     }
     // drop the (up to) four states of this pass
 #pragma unroll
     for (int i = 0; i < 32 / kCoopGroup; ++i) mask &= mask - 1u;
+  }
+}
+
+// ---- deferred variant.  A pass costs the same ~9 us whether one or four of a warp's groups have a state to work on,
+// and a CTA cannot retire before its slowest warp: paying a pass per warp per tile (70 % of the warps of a UR5 batch)
+// doubles the kernel.  Instead a waiting lane finishes its evaluation WITHOUT the task-space term and leaves a record
+// (A, the Cholesky factor of M, y, z, its row) in a small queue of the CTA; the CTA empties the queue with all its
+// 16 groups at once — after its last tile, or earlier when 16 records have gathered — and adds the missing
+//   du = -J^T Mx y - J^T Mx J M^-1 u_null = -L A^T (Mx y + Mx z)
+// to the rows already written.  Records that do not fit are handled in line as above.
+template <int N, int KD>
+struct CoopRecord {
+  static constexpr int kA = 0, kL = KD * N, kY = kL + N * (N + 1) / 2, kZ = kY + KD, kLen = kZ + KD;
+};
+#ifndef ABRB_OSC_BLOCK
+#define ABRB_OSC_BLOCK 128
+#endif
+constexpr int kCoopQueue = 8 * (ABRB_OSC_BLOCK / 32);  // records per CTA (eight per warp)
+
+template <typename T>
+struct FlushOut {
+  T *u, *train;           // local (B, n) outputs (u may be null when only the gathered copy is wanted)
+  T *peer[kMaxPeers];     // gathered arrays (fused all-gather), row0 = first row of this rank's block
+  int n_peer, self;
+  int64_t row0;
+};
+
+// One round of the CTA's groups over the queue: group j of the CTA takes records j, j + G, ... (NS at a time).
+template <typename T, int N, int KD, int NS>
+__device__ __forceinline__ void coop_flush_round(const T *qrec, const long long *qrow, int n, int first, int stride,
+                                                 const FlushOut<T> &o, double rcond, bool two) {
+  typedef CoopRecord<N, KD> RC;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (kCoopGroup - 1), gbase = lane & ~(kCoopGroup - 1);
+  JacobiRow<N, KD> me[NS];
+  bool have[NS], owner[NS];
+  const T *rec[NS];
+  double y[NS][KD], z[NS][KD], xy[NS][KD], xz[NS][KD];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const int e = first + s * stride;
+    have[s] = e < n;
+    owner[s] = have[s] && sub < KD;
+    rec[s] = qrec + (size_t)(have[s] ? e : 0) * RC::kLen;
+#pragma unroll
+    for (int k = 0; k < N; ++k) me[s].b[k] = owner[s] ? double(rec[s][RC::kA + sub * N + k]) : 0.0;
+#pragma unroll
+    for (int k = 0; k < KD; ++k) {
+      y[s][k] = double(rec[s][RC::kY + k]);
+      z[s][k] = double(rec[s][RC::kZ + k]);
+    }
+  }
+  coop_jacobi_group<N, KD, NS>(me, sub, gbase, owner, y, z, rcond, two, xy, xz);
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    // du = -L (A^T x): lane k forms (A^T x)_k, lane i then row i of the triangular product
+    double wy = 0.0, wz = 0.0;
+    if (have[s] && sub < N) {
+#pragma unroll
+      for (int r = 0; r < KD; ++r) {
+        const double a = double(rec[s][RC::kA + r * N + sub]);
+        wy += a * xy[s][r];
+        wz += a * xz[s][r];
+      }
+    }
+    double dy = 0.0, dz = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const double ky = __shfl_sync(0xffffffffu, wy, gbase + k), kz = __shfl_sync(0xffffffffu, wz, gbase + k);
+      if (have[s] && sub < N && k <= sub) {
+        const double l = double(rec[s][RC::kL + sub * (sub + 1) / 2 + k]);
+        dy += l * ky;
+        dz += l * kz;
+      }
+    }
+    if (have[s] && sub < N) {
+      const int64_t row = qrow[first + s * stride];
+      const T *src = o.u != nullptr ? o.u + row * N + sub : o.peer[o.self] + (o.row0 + row) * N + sub;
+      const T v = T(double(*src) - dy - (two ? dz : 0.0));
+      if (o.u != nullptr) o.u[row * N + sub] = v;
+      if (o.train != nullptr) o.train[row * N + sub] = T(double(o.train[row * N + sub]) - dy);
+      for (int p = 0; p < o.n_peer; ++p) o.peer[p][(o.row0 + row) * N + sub] = v;
+    }
+  }
+}
+
+// Empties the CTA's queue (all threads of the CTA call it).  Up to one record per group it is one Jacobi pass; with
+// more, each group takes two records through the pass together (the rounds are latency-bound, two interleaved chains
+// cost ~1.2x one) — a CTA whose queue happens to hold more records than it has groups is otherwise the kernel's tail.
+template <typename T, int N, int KD>
+__device__ __noinline__ void coop_flush_cta(const T *qrec, const long long *qrow, int n, const FlushOut<T> &o, double rcond,
+                                            bool two) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  constexpr int kPerWarp = 32 / kCoopGroup;
+  const int groups = n_warps * kPerWarp, mine = warp * kPerWarp + lane / kCoopGroup;
+  if (n <= groups) {
+    if (warp * kPerWarp < n) coop_flush_round<T, N, KD, 1>(qrec, qrow, n, mine, groups, o, rcond, two);  // warp-uniform
+  } else {
+    for (int base = 0; base < n; base += 2 * groups)  // CTA-uniform trip count
+      if (base + warp * kPerWarp < n) coop_flush_round<T, N, KD, 2>(qrec, qrow, n, base + mine, groups, o, rcond, two);
   }
 }
 
@@ -120,11 +251,48 @@ struct WarpCoop {
   T *xch;            // the warp's exchange area
   const T *scratch;  // the warp's kinematic scratch (lane 0's column) when it is in shared memory
   int lane;
+  bool valid;        // this lane evaluates a state of its own (false: padding lane of a ragged last warp)
+  // deferral (osc_kernel only; null queue = always in line)
+  T *qrec = nullptr;
+  long long *qrow = nullptr;
+  int *qcount = nullptr;
+  long long row = 0;  // this lane's state index
 
-  template <typename T_, int N_, int KD_>
-  __device__ __forceinline__ void pinv(bool slow, K_ &K, T *y, T *z, bool two, double rcond) {
-    const unsigned mask = __ballot_sync(0xffffffffu, slow);
+  template <typename T_, int N_, int KD_, class LGet>
+  __device__ __forceinline__ void pinv(bool slow, K_ &K, LGet L, T *y, T *z, bool two, double rcond) {
+    slow = slow && valid;
+    unsigned mask = __ballot_sync(0xffffffffu, slow);
     if (mask == 0u) return;  // warp-uniform
+    if (qrec != nullptr) {
+      typedef CoopRecord<N, KD> RC;
+      bool queued = false;
+      if (slow) {
+        const int pos = atomicAdd(qcount, 1);
+        if (pos < kCoopQueue) {
+          queued = true;
+          T *rec = qrec + (size_t)pos * RC::kLen;
+          qrow[pos] = row;
+#pragma unroll
+          for (int r = 0; r < KD; ++r) {
+            rec[RC::kY + r] = y[r];
+            rec[RC::kZ + r] = z[r];
+            y[r] = T(0);  // the owner finishes without the task-space term; the flush adds it to the stored row
+            z[r] = T(0);
+#pragma unroll
+            for (int k = 0; k < N; ++k) rec[RC::kA + r * N + k] = K.s.ld(K_::aslot(r, k));
+          }
+          int li = 0;
+#pragma unroll
+          for (int a = 0; a < N; ++a)
+#pragma unroll
+            for (int b = 0; b < N; ++b)
+              if (b <= a) rec[RC::kL + li++] = L(a, b);
+        }
+      }
+      slow = slow && !queued;
+      mask = __ballot_sync(0xffffffffu, slow);
+      if (mask == 0u) return;
+    }
     if (slow) {
 #pragma unroll
       for (int r = 0; r < KD; ++r) {

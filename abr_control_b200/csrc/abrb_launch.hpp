@@ -19,11 +19,11 @@ struct RbdCall {
 // Fused all-gather of the control outputs over NVLink peer memory (BASELINE config 5): the OSC kernel's epilogue stores
 // every rank's rows straight into the gathered (B_total, n) array of EVERY rank (buffers mapped with CUDA IPC), so the
 // exchange overlaps the arithmetic tile by tile instead of following it as a separate collective.
-constexpr int kMaxPeers = 8;
 struct GatherArgs {
   void *peer_u[kMaxPeers];                  // base of the gathered array on each rank (own rank included)
   unsigned long long *peer_flag[kMaxPeers]; // &flags[my_rank] on each rank: receives `epoch` when all my rows are there
   int n_peer = 0;
+  int self = 0;                             // this rank's index in peer_u / peer_flag
   int64_t row0 = 0;                         // first row of this rank's block in the gathered array
   unsigned long long epoch = 0;
   unsigned *cta_counter = nullptr;          // local: CTAs of this launch that have finished

@@ -39,16 +39,58 @@ namespace abrb {
 constexpr int kMaxJoints = 7;
 constexpr int kMaxNull = 4;
 constexpr int kMaxObstacles = 16;
+constexpr int kMaxPeers = 8;  // GPUs of one box (fused all-gather of the control outputs)
 
+// sin and cos of a joint angle in double.  The CUDA library routine is ~115 executed instructions per call with a
+// Payne-Hanek slow path inlined at each of the nine call sites of an OSC evaluation (1.9 k static instructions, 12 % of
+// the executed ones, in kernels that stall on instruction fetch).  Joint angles are small numbers, so on the device:
+// three-term Cody-Waite reduction by pi/2 (exact products through FMA; |x| < 1024, beyond that — and for NaN — one
+// shared out-of-line call of the library routine) and the classic degree-13 / degree-14 kernel polynomials on
+// [-pi/4, pi/4]; measured against long-double references over [0, 2 pi) and [-50, 50]: <= 1.5 ulp.
+#ifdef __CUDA_ARCH__
+__device__ __noinline__ void sincos_cold(double x, double *s, double *c) { ::sincos(x, s, c); }
+__device__ __forceinline__ void sincos_t(double x, double *s, double *c) {
+  if (!(::fabs(x) < 1024.0)) {
+    sincos_cold(x, s, c);
+    return;
+  }
+  const double k = ::rint(x * 0.63661977236758138);  // 2 / pi
+  double r = ::fma(-k, 1.5707963267948966, x);        // pi/2 = hi + mid + lo
+  r = ::fma(-k, 6.123233995736766e-17, r);
+  r = ::fma(-k, -1.4973849048591698e-33, r);
+  const double z = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = ::fma(ps, z, -2.50507602534068634195e-08);
+  ps = ::fma(ps, z, 2.75573137070700676789e-06);
+  ps = ::fma(ps, z, -1.98412698298579493134e-04);
+  ps = ::fma(ps, z, 8.33333333332248946124e-03);
+  ps = ::fma(ps, z, -1.66666666666666324348e-01);
+  const double sn = ::fma(r * z, ps, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = ::fma(pc, z, 2.08757232129817482790e-09);
+  pc = ::fma(pc, z, -2.75573143513906633035e-07);
+  pc = ::fma(pc, z, 2.48015872894767294178e-05);
+  pc = ::fma(pc, z, -1.38888888888741095749e-03);
+  pc = ::fma(pc, z, 4.16666666666666019037e-02);
+  const double cs = ::fma(z * z, pc, ::fma(-0.5, z, 1.0));
+  const int n = (int)k;
+  const double a = (n & 1) ? cs : sn, b = (n & 1) ? sn : cs;
+  *s = (n & 2) ? -a : a;
+  *c = ((n + 1) & 2) ? -b : b;
+}
+#else
 ABRB_HD void sincos_t(double x, double *s, double *c) { ::sincos(x, s, c); }
+#endif
 ABRB_HD void sincos_t(float x, float *s, float *c) { ::sincosf(x, s, c); }
 ABRB_HD double sqrt_t(double x) { return ::sqrt(x); }
 ABRB_HD float sqrt_t(float x) { return ::sqrtf(x); }
-// Reciprocal and reciprocal square root.  Default: the IEEE division / square root (a ~30-instruction sequence each in
-// double on the GPU).  ABRB_FAST_DIV=1 (experimental, not the shipped default): hardware seed (rcp/rsqrt.approx.ftz.f64,
-// ~20 bits) refined by two Newton steps to ~1 ulp; operands here are pivots and norms far from the subnormal range.
+// Reciprocal and reciprocal square root of the pivots and norms of the small factorisations.  Default (ABRB_FAST_DIV=1):
+// the hardware seed (rcp / rsqrt.approx.ftz.f64, ~23 bits) refined by two Newton steps to ~1 ulp — the IEEE double
+// division / square root are ~30-instruction dependent sequences each, and these kernels are bound by exactly such
+// chains (measured on B200: UR5 6-DOF OSC fp64 41.2 -> 36.9 us without the pseudo-inverse states, one cooperative
+// Jacobi pass 22 k -> 17 k cycles).  Operands are far from the subnormal range.  ABRB_FAST_DIV=0 keeps the IEEE forms.
 #ifndef ABRB_FAST_DIV
-#define ABRB_FAST_DIV 0
+#define ABRB_FAST_DIV 1
 #endif
 ABRB_HD float inv_t(float x) { return 1.0f / x; }
 ABRB_HD float inv_sqrt_t(float x) { return 1.0f / ::sqrtf(x); }
@@ -81,6 +123,24 @@ ABRB_HD double inv_sqrt_t(double x) {
 ABRB_HD double inv_t(double x) { return 1.0 / x; }
 ABRB_HD double inv_sqrt_t(double x) { return 1.0 / ::sqrt(x); }
 #endif
+// 1 / sqrt(x) to ~2^-45: the hardware seed and ONE Newton step.  Only for the Jacobi rotations of the truncating
+// pseudo-inverse, whose rounds are a pure dependent chain: a rotation whose (c, s) are off by 1e-13 is still applied
+// identically to the row and to its row of V, and the iteration converges to the same decomposition (measured:
+// 5e-13 instead of 4e-14 on the pseudo-inverse, against a 1e-9 parity tolerance; two steps buy nothing there).
+ABRB_HD double inv_sqrt1_t(double x) {
+#if ABRB_FAST_DIV
+  double y;
+#ifdef __CUDA_ARCH__
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+  if (!(x > 1e-30 && x < 1e30)) return 1.0 / ::sqrt(x);
+  y = (double)(1.0f / ::sqrtf((float)x));
+#endif
+  return ::fma(y, ::fma(-0.5 * x * y, y, 0.5), y);
+#else
+  return 1.0 / ::sqrt(x);
+#endif
+}
 ABRB_HD double abs_t(double x) { return ::fabs(x); }
 ABRB_HD float abs_t(float x) { return ::fabsf(x); }
 ABRB_HD double fmod_t(double x, double y) { return ::fmod(x, y); }
@@ -145,11 +205,18 @@ struct StridedStore {
 template <int N, bool ORTHO>
 struct KinSlots {
   static constexpr int kT = 0, kZ = 3 * N, kPl = 6 * N, kR0 = 9 * N, kR1 = 12 * N, kS0 = 15 * N, kS1 = 18 * N;
-  // kPark: N (N + 1) / 2 slots where osc_eval parks the Cholesky factor of M while the task-space system is solved
-  // (it also re-uses the 3 N link-COM slots at kPl for 1/diag(L), g and C dq).  The non-orthonormal layout has 12 N
-  // slots (R_k columns / R_k^-1 rows) that are dead by then; the orthonormal one gets the extra slots.
+  // osc_eval parks 1/diag(L), g and C dq in the 3 N link-COM slots at kPl (free by then) while the task-space system is
+  // solved.  ABRB_PARK_L=1 would also park the Cholesky factor of M in N (N + 1) / 2 extra slots at kPark; measured on
+  // B200 it does not pay (UR5 6-DOF fp64: 60.8 us with, 59.1 us without; it costs 5.4 KB of shared memory per warp).
+#ifndef ABRB_PARK
+#define ABRB_PARK 1
+#endif
+#ifndef ABRB_PARK_L
+#define ABRB_PARK_L 0
+#endif
+  static constexpr bool kParkL = ABRB_PARK && ABRB_PARK_L && (!ORTHO || N <= 6);
   static constexpr int kPark = 9 * N;
-  static constexpr int kCount = ORTHO ? 9 * N + N * (N + 1) / 2 : (21 * N > 9 * N + N * (N + 1) / 2 ? 21 * N : 9 * N + N * (N + 1) / 2);
+  static constexpr int kCount = ORTHO ? 9 * N + (kParkL ? N * (N + 1) / 2 : 0) : 21 * N;
 };
 
 template <typename T, int N, bool ORTHO_, template <typename, int> class Store = RegStore>
@@ -1200,17 +1267,34 @@ ABRB_HD int rr_partner(int n, int i, int r) {
 }
 
 // One row's share of the rotation of a pair of rows.  `lo`: this row has the smaller index of the two.  Returns
-// 0 (already orthogonal to rounding: untouched), 1 (rotated, the cosine of the angle was below 1e-8: the quadratically
+// 0 (already orthogonal to rounding: untouched), 1 (rotated, the cosine of the angle was below 1e-6: the quadratically
 // convergent iteration is finished by this very rotation) or 2 (rotated, not yet converged).
 template <int N, int KD>
 ABRB_HD int jacobi_pair(bool lo, JacobiRow<N, KD> &me, const JacobiRow<N, KD> &other) {
-  double mine = 0.0, theirs = 0.0, ga = 0.0;
+  // (pairwise sums: the three inner products are the head of the round's dependent chain — depth 4 instead of 6 for
+  // six columns — and these rounds are pure latency)
+  double pm[(N + 1) / 2], pt[(N + 1) / 2], pg[(N + 1) / 2];
   ABRB_UNROLL
-  for (int k = 0; k < N; ++k) {
-    mine += me.b[k] * me.b[k];
-    theirs += other.b[k] * other.b[k];
-    ga += me.b[k] * other.b[k];
+  for (int k = 0; k + 1 < N; k += 2) {
+    pm[k / 2] = ::fma(me.b[k + 1], me.b[k + 1], me.b[k] * me.b[k]);
+    pt[k / 2] = ::fma(other.b[k + 1], other.b[k + 1], other.b[k] * other.b[k]);
+    pg[k / 2] = ::fma(me.b[k + 1], other.b[k + 1], me.b[k] * other.b[k]);
   }
+  if (N & 1) {
+    pm[N / 2] = me.b[N - 1] * me.b[N - 1];
+    pt[N / 2] = other.b[N - 1] * other.b[N - 1];
+    pg[N / 2] = me.b[N - 1] * other.b[N - 1];
+  }
+  ABRB_UNROLL
+  for (int w = 1; w < (N + 1) / 2; w *= 2) {
+    ABRB_UNROLL
+    for (int k = 0; k + w < (N + 1) / 2; k += 2 * w) {
+      pm[k] += pm[k + w];
+      pt[k] += pt[k + w];
+      pg[k] += pg[k + w];
+    }
+  }
+  const double mine = pm[0], theirs = pt[0], ga = pg[0];
   const double prod = mine * theirs, g2 = ga * ga;
   if (!(g2 > 1e-30 * prod)) return 0;
   // rows (lo, hi) with squared norms (al, be):  lo' = c lo - s hi,  hi' = s lo + c hi  with the rotation angle
@@ -1218,9 +1302,9 @@ ABRB_HD int jacobi_pair(bool lo, JacobiRow<N, KD> &me, const JacobiRow<N, KD> &o
   //   cos 2 theta = |d| / h,   c^2 = (1 + |d| / h) / 2  (in [1/2, 1]),   s = sgn(d) ga / (h c)
   // — two reciprocal square roots, no division, and no cancellation anywhere.
   const double d = lo ? theirs - mine : mine - theirs;
-  const double r1 = inv_sqrt_t(d * d + 4.0 * g2);  // 1 / h
+  const double r1 = inv_sqrt1_t(d * d + 4.0 * g2);  // 1 / h
   const double c2 = 0.5 + 0.5 * abs_t(d) * r1;
-  const double r2 = inv_sqrt_t(c2);                // 1 / c
+  const double r2 = inv_sqrt1_t(c2);                // 1 / c
   const double c = c2 * r2;
   const double sn = (d >= 0.0 ? ga : -ga) * r1 * r2;
   const double sp = lo ? -sn : sn;
@@ -1228,7 +1312,7 @@ ABRB_HD int jacobi_pair(bool lo, JacobiRow<N, KD> &me, const JacobiRow<N, KD> &o
   for (int k = 0; k < N; ++k) me.b[k] = c * me.b[k] + sp * other.b[k];
   ABRB_UNROLL
   for (int k = 0; k < KD; ++k) me.v[k] = c * me.v[k] + sp * other.v[k];
-  return g2 > 1e-16 * prod ? 2 : 1;
+  return g2 > 1e-12 * prod ? 2 : 1;
 }
 
 constexpr int kJacobiMaxSweeps = 24;

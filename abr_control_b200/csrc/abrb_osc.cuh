@@ -159,8 +159,8 @@ ABRB_HD T wrap_pm_pi(T d) {
 // Sequential stand-in for the warp-cooperative truncating pseudo-inverse (abrb_coop.cuh): used by the host
 // instantiation (tests/hostsim), where a "warp" is one state.
 struct SeqCoop {
-  template <typename T, int N, int KD, class K_>
-  ABRB_HD void pinv(bool slow, K_ &K, T *y, T *z, bool two, double rcond) const {
+  template <typename T, int N, int KD, class K_, class LGet>
+  ABRB_HD void pinv(bool slow, K_ &K, LGet, T *y, T *z, bool two, double rcond) const {
     if (!slow) return;
     double A[KD * N], yd[KD], zd[KD], xy[KD], xz[KD];
     for (int r = 0; r < KD; ++r) {
@@ -396,15 +396,15 @@ ABRB_HD void osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
   // ---- nothing below needs L, 1/diag(L), g, C dq, u, u_null until the task-space solve is done: with the scratch in
   //      shared memory they are parked there (slots that are free by now) instead of being carried in registers across
   //      the 6x6 factorisation, where the register allocator would otherwise spill them to local memory
-  constexpr bool PARK = K_::kSharedScratch;
   typedef typename K_::S SL;
+  constexpr bool PARK = K_::kSharedScratch && ABRB_PARK, PARK_L = PARK && SL::kParkL;
   if (PARK) {
     int li = 0;
     ABRB_UNROLL
     for (int a = 0; a < N; ++a) {
       ABRB_UNROLL
       for (int b = 0; b < N; ++b)
-        if (b <= a) K.s.st(SL::kPark + li++, M[a][b]);
+        if (PARK_L && b <= a) K.s.st(SL::kPark + li++, M[a][b]);
       K.s.st(SL::kPl + a, Mi[a]);
       K.s.st(SL::kPl + N + a, g[a]);
       K.s.st(SL::kPl + 2 * N + a, (PLANT || O.use_C) ? cdq[a] : T(0));
@@ -484,14 +484,15 @@ ABRB_HD void osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
   }
   // ... and the truncating pseudo-inverse otherwise (always in double: the matrices that end up here have eigenvalue
   // ratios down to 1e-16).  When nothing is below the cut-off it returns S^-1 y itself, as numpy's pinv does.
-  coop.template pinv<T, N, KD>(!fast, K, y, z, any_null, double(rcond));
+  auto Lget = [&](int a, int b) { return PARK_L ? K.s.ld(SL::kPark + a * (a + 1) / 2 + b) : M[a][b]; };
+  coop.template pinv<T, N, KD>(!fast, K, Lget, y, z, any_null, double(rcond));
   if (PARK) {
     int li = 0;
     ABRB_UNROLL
     for (int a = 0; a < N; ++a) {
       ABRB_UNROLL
       for (int b = 0; b < N; ++b)
-        if (b <= a) M[a][b] = K.s.ld(SL::kPark + li++);
+        if (PARK_L && b <= a) M[a][b] = K.s.ld(SL::kPark + li++);
       Mi[a] = K.s.ld(SL::kPl + a);
       g[a] = K.s.ld(SL::kPl + N + a);
       cdq[a] = K.s.ld(SL::kPl + 2 * N + a);

@@ -645,6 +645,7 @@ static int osc_generate_gather(const abrb_osc *c, int frame_id, const double *x_
     if (!g->peer[r]) return fail(ABRB_EINVAL, "abrb_osc_generate_gather: not every peer has been imported");
   GatherArgs ga;
   ga.n_peer = g->world;
+  ga.self = g->rank;
   ga.row0 = row0;
   ga.epoch = ++g->epoch;
   for (int r = 0; r < g->world; ++r) {

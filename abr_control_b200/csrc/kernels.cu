@@ -195,24 +195,68 @@ struct OscArgs {
   GatherArgs g;  // n_peer > 0: also store u into every rank's gathered array (peer memory over NVLink)
 };
 
-// One pass over the batch.  The states whose task-space inertia needs the truncating pseudo-inverse (3.8 % of
-// uniformly random UR5 6-DOF states: 70 % of the warps hold one) are finished by their warp cooperatively
-// (abrb_coop.cuh): every lane reaches WarpCoop::pinv together.
+// CTA-level shared memory of the OSC kernel behind the per-warp regions: the queue of deferred states (abrb_coop.cuh)
+template <typename T, int N, int KD>
+struct OscQueue {
+  static constexpr int kRecElems = kCoopQueue * CoopRecord<N, KD>::kLen;
+  static constexpr size_t kRowOff = ((size_t)kRecElems * sizeof(T) + 15) / 16 * 16;   // long long rows[kCoopQueue]
+  static constexpr size_t kCountOff = kRowOff + kCoopQueue * sizeof(long long);      // int count
+  static constexpr size_t kBytes = kCountOff + 16;
+};
+
+// One pass over the batch, persistent CTAs (grid = resident CTAs, tiles round-robin).  The states whose task-space
+// inertia needs the truncating pseudo-inverse (3.8 % of uniformly random UR5 6-DOF states: 70 % of the warps hold one)
+// leave a record in the CTA's queue and are finished by the whole CTA cooperatively (abrb_coop.cuh) once 16 of them
+// have gathered or the CTA has run out of tiles; what does not fit the queue is finished by its warp in line.
+// CTA size of the OSC kernel.  Measured on B200 (UR5 6-DOF fp64, B = 65 536): 128 threads 60.4 us, 64 threads 65.7 us —
+// what ends the kernel is the CTA whose queue happens to hold more records than it has groups (a second Jacobi pass),
+// and smaller CTAs have fewer groups per queue; 256 threads do not fit the non-orthonormal fp64 scratch.
+#ifndef ABRB_OSC_BLOCK
+#define ABRB_OSC_BLOCK 128
+#endif
+constexpr int kOscBlock = ABRB_OSC_BLOCK, kOscWarps = kOscBlock / 32;
+constexpr int kOscFlushAt = kOscWarps * (32 / kCoopGroup);  // one full round of the CTA's groups
+
 template <typename T, int N, bool ORTHO, int KD, bool KSMEM>
-__global__ void __launch_bounds__(kBlock, MinBlocks<T>::value)
+__global__ void __launch_bounds__(kOscBlock, (MinBlocks<T>::value * kBlock / kOscBlock > 0 ? MinBlocks<T>::value * kBlock / kOscBlock : 1))
 osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
            const __grid_constant__ OscArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef KinSel<T, N, ORTHO, KSMEM> KS;
   typedef OscSmem<T, N, ORTHO, KD, KSMEM> WS;
+  typedef OscQueue<T, N, KD> Q;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T *region = reinterpret_cast<T *>(smem_raw) + warp * WS::kElems;
   T *stage = region + WS::kKin;
+  unsigned char *qbase = smem_raw + ((size_t)kOscWarps * WS::kElems * sizeof(T) + 15) / 16 * 16;
+  T *qrec = reinterpret_cast<T *>(qbase);
+  long long *qrow = reinterpret_cast<long long *>(qbase + Q::kRowOff);
+  int *qcount = reinterpret_cast<int *>(qbase + Q::kCountOff);
+  if (threadIdx.x == 0) *qcount = 0;
+  __syncthreads();
+#ifdef ABRB_DBG_TIMING  // (timing experiments only) per-CTA cycle counts are written over the training-signal buffer
+  const long long dbg_t0 = clock64();
+  long long dbg_flush = 0, dbg_wait = 0;
+  int dbg_nflush = 0, dbg_rec = 0;
+#endif
   typename KS::type K;
   KS::bind(K, region, lane);
-  WarpCoop<T, N, KD, typename KS::type> coop{region + WS::kKin + WS::kTile, region, lane};
-  for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
-    // no early exit: every lane of a warp takes part in the cooperative step; idle lanes / warps redo a valid state
+  WarpCoop<T, N, KD, typename KS::type> coop{region + WS::kKin + WS::kTile, region, lane, true, qrec, qrow, qcount, 0};
+  FlushOut<T> fo;
+  fo.u = a.u;
+#ifdef ABRB_DBG_TIMING
+  fo.train = nullptr;
+#else
+  fo.train = a.train;
+#endif
+  fo.n_peer = a.g.n_peer;
+  fo.self = a.g.self;
+  fo.row0 = a.g.row0;
+#pragma unroll
+  for (int p = 0; p < kMaxPeers; ++p) fo.peer[p] = static_cast<T *>(a.g.peer_u[p]);
+  const double rcond = double(O.thr) * 0.1;
+  for (int64_t base = (int64_t)blockIdx.x * kOscBlock; base < a.B; base += (int64_t)gridDim.x * kOscBlock) {
+    // no early exit: every lane of a warp takes part in the cooperative steps; idle lanes / warps redo a valid state
     const int64_t warp_b0 = base + warp * 32;
     const int64_t rem = a.B - warp_b0;
     const int nvalid = rem < 32 ? (rem > 0 ? (int)rem : 0) : 32;
@@ -230,15 +274,54 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
       tv[c] = a.tv != nullptr ? a.tv[b * a.tv_stride + c] : T(0);
       ie[c] = a.ierr != nullptr ? a.ierr[b * 6 + c] : T(0);
     }
+    coop.valid = lane < nvalid;
+    coop.row = b;
     osc_eval<T, N, KD, false>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, a.ierr != nullptr ? ie : nullptr, u, tr,
                               (T *)nullptr, K, coop);
     if (a.u) store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);
+#ifndef ABRB_DBG_TIMING
     if (a.train) store_records<T, N>(a.train, warp_b0, nvalid, tr, stage, lane);
+#endif
     if (a.ierr) store_records<T, 6>(a.ierr, warp_b0, nvalid, ie, stage, lane);
     // fused all-gather: this tile's rows go to every rank's gathered array while the other warps still compute
     for (int p = 0; p < a.g.n_peer; ++p)
       store_records<T, N>(static_cast<T *>(a.g.peer_u[p]), a.g.row0 + warp_b0, nvalid, u, stage, lane);
+    // deferred states: emptied once a full round of the CTA's 16 groups has gathered, and after the last tile
+#ifdef ABRB_DBG_TIMING
+    const long long dbg_w0 = clock64();
+#endif
+    __syncthreads();  // this tile's rows and records are visible to the whole CTA
+#ifdef ABRB_DBG_TIMING
+    dbg_wait += clock64() - dbg_w0;
+    const long long dbg_f0 = clock64();
+#endif
+    const int queued = *qcount < kCoopQueue ? *qcount : kCoopQueue;
+    const bool last = base + (int64_t)gridDim.x * kOscBlock >= a.B;
+    if (queued >= kOscFlushAt || (last && queued > 0)) {
+#ifndef ABRB_DBG_NOFLUSH  // (timing experiments only: results of the deferred states are then wrong)
+      coop_flush_cta<T, N, KD>(qrec, qrow, queued, fo, rcond, O.n_null > 0);
+#endif
+      __syncthreads();
+      if (threadIdx.x == 0) *qcount = 0;
+#ifdef ABRB_DBG_TIMING
+      dbg_flush += clock64() - dbg_f0;
+      dbg_nflush += 1;
+      dbg_rec += queued;
+#endif
+    }
+    __syncthreads();
   }
+#ifdef ABRB_DBG_TIMING
+  if (lane == 0 && a.train != nullptr) {
+    T *d = a.train + ((size_t)blockIdx.x * kOscWarps + warp) * 6;
+    d[0] = T(clock64() - dbg_t0);
+    d[1] = T(dbg_flush);
+    d[2] = T(dbg_wait);
+    d[3] = T(dbg_nflush);
+    d[4] = T(dbg_rec);
+    d[5] = T(gridDim.x);
+  }
+#endif
   if (a.g.n_peer > 0) {
     // completion: once every CTA's peer stores are visible system-wide, the last CTA publishes this launch's epoch
     // in every rank's flag array; abrb_gather_wait() on the consumer side spins on those flags
@@ -280,7 +363,7 @@ rollout_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ O
   T *stage = region + WS::kKin;
   typename KS::type K;
   KS::bind(K, region, lane);
-  WarpCoop<T, N, KD, typename KS::type> coop{region + WS::kKin + WS::kTile, region, lane};
+  WarpCoop<T, N, KD, typename KS::type> coop{region + WS::kKin + WS::kTile, region, lane, true};
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
     // no early exit (cooperative step inside osc_eval): idle lanes / warps redo a valid state and store nothing
     const int64_t warp_b0 = base + warp * 32;
@@ -299,6 +382,7 @@ rollout_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ O
       tg[c] = a.target[b * a.target_stride + c];
       ie[c] = a.ierr != nullptr ? a.ierr[b * 6 + c] : T(0);
     }
+    coop.valid = lane < nvalid;
     for (int t = 0; t < a.steps; ++t) {
       osc_eval<T, N, KD, true>(P, O, q, dq, tg, (const T *)nullptr, a.ierr != nullptr ? ie : nullptr, u, (T *)nullptr,
                                acc, K, coop);
@@ -576,11 +660,25 @@ int osc_go(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
   a.tv_stride = c.tv_stride;
   if (c.gather != nullptr) a.g = *c.gather;
   constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32 || ABRB_ROLLED;  // rolled loops index the scratch at run time
-  const size_t smem = (size_t)kWarps * OscSmem<T, N, ORTHO, KD, KSMEM>::kElems * sizeof(T);
+  const size_t smem = ((size_t)kOscWarps * OscSmem<T, N, ORTHO, KD, KSMEM>::kElems * sizeof(T) + 15) / 16 * 16 +
+                      OscQueue<T, N, KD>::kBytes;
   auto kern = osc_kernel<T, N, ORTHO, KD, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
   if (e != cudaSuccess) return (int)e;
-  kern<<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, O, a);
+  // persistent CTAs: as many as are resident at once, so that each sees several tiles and its deferred states gather
+  static thread_local int resident = 0;
+  static thread_local int resident_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (resident_dev != dev) {
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kOscBlock, smem);
+    if (e != cudaSuccess) return (int)e;
+    resident = per_sm > 0 ? per_sm : 1;
+    resident_dev = dev;
+  }
+  const int64_t tiles = (c.B + kOscBlock - 1) / kOscBlock, cap = (int64_t)num_sms() * resident;
+  kern<<<(unsigned)(tiles < cap ? tiles : cap), kOscBlock, smem, c.stream>>>(P, O, a);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -225,6 +225,71 @@ def cpu_reference_run(n_evals, repeats=3):
                 sample=f"{n_small} UR5 OSC evals, NumPy oracle (oracle/_ref absent)"), u, (q[:n_small], dq[:n_small], target[:n_small])
 
 
+AS_SHIPPED = os.path.join(ROOT, "baseline", "_ref")
+
+
+def as_shipped_worker(n):
+    """Runs INSIDE the reference's environment (PYTHONPATH=baseline/_ref, HOME=baseline/_ref/home): the stock loop of
+    /root/reference/examples/timing_plots.py:14-28 — `for i: ctrlr.generate(q[i], dq[i], target[i])` — on the reference's
+    own UR5 config and OSC, Cython cache warm.  The only harness addition is the float64 cast NumPy >= 2 needs in
+    utils/transformations.py:1225."""
+    from abr_control.utils import transformations
+
+    _orig = transformations.quaternion_from_matrix
+    transformations.quaternion_from_matrix = lambda matrix, isprecise=False: _orig(np.asarray(matrix, dtype=np.float64), isprecise)
+    from abr_control.arms import ur5
+    from abr_control.controllers import OSC
+
+    rc = ur5.Config()
+    ctrlr = OSC(rc, kp=OSC_KW["kp"], ctrlr_dof=[True] * 6, use_C=True)
+    q, dq, tg = synth(n, 6, 123)
+    for i in range(min(n, 20)):
+        ctrlr.generate(q[i], dq[i], tg[i])
+    cython = type(rc._M).__name__ == "cython_function_or_method"
+    t0 = time.perf_counter()
+    for i in range(n):
+        ctrlr.generate(q[i], dq[i], tg[i])
+    print(json.dumps({"evals_per_s": n / (time.perf_counter() - t0), "cython": cython}))
+
+
+def as_shipped_run(n_per_worker=2000):
+    """evals/s of the reference exactly as shipped: one interpreter on one core, and one interpreter per core"""
+    if not os.path.isdir(os.path.join(AS_SHIPPED, "abr_control")) or not os.path.isdir(os.path.join(AS_SHIPPED, "home", ".cache")):
+        return {"unavailable": "baseline/_ref (reference + warm UR5 cache, oracle/ref_harness/install_baseline.sh) is absent"}
+    env = dict(os.environ, HOME=os.path.join(AS_SHIPPED, "home"), PYTHONPATH=AS_SHIPPED, OMP_NUM_THREADS="1",
+               OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    cmd = [sys.executable, "-W", "ignore", os.path.abspath(__file__), "--as-shipped-worker", str(n_per_worker)]
+
+    def launch(count):
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, cwd=tempfile.gettempdir())
+                 for _ in range(count)]
+        outs = [p.communicate(timeout=600)[0] for p in procs]
+        wall = time.perf_counter() - t0
+        rates = []
+        for o in outs:
+            try:
+                rates.append(json.loads(o.decode().strip().splitlines()[-1]))
+            except Exception:
+                pass
+        return rates, wall
+
+    one, _ = launch(1)
+    if not one:
+        return {"unavailable": "the reference did not run from baseline/_ref on this box"}
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    many, _ = launch(workers)
+    return {"evals_per_s_1_core": one[0]["evals_per_s"], "cython_path": bool(one[0]["cython"]),
+            "evals_per_s_all_cores": float(sum(r["evals_per_s"] for r in many)), "workers": len(many),
+            "sample": f"{n_per_worker} consecutive OSC.generate calls per interpreter (examples/timing_plots.py:14-28), "
+                      "one interpreter per worker, sum of the workers' own rates",
+            "harness_shim": "float64 cast in transformations.quaternion_from_matrix (NumPy >= 2, SURVEY.md S0.3)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -258,6 +323,8 @@ def run_reference(args):
         "config": bench_config(args.gpus),
         "sample_per_step": n_step,
         "cpu_baseline": base,
+        "generated_c": {"evals_per_s": value, "cores": base.get("cores"), "what": base.get("sample")},
+        "as_shipped_python": as_shipped_run(),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -659,8 +726,11 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--as-shipped-worker", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.as_shipped_worker:
+        as_shipped_worker(args.as_shipped_worker)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

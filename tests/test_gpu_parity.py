@@ -367,8 +367,11 @@ def test_large_batch_deferred_pinv_states():
         assert err[clear].max() < tol, (dtype, err[clear].max())
         assert np.median(err) < (1e-12 if dtype == np.float64 else 1e-5)
         # and identical to evaluating the same rows in a small batch
+        # (64 such states in one CTA overflow its queue of 32: half of them take the in-line cooperative route, the other
+        # half the deferred one — same arithmetic, different rounding order)
         small = ctrlr.generate(q[slow[:64]].astype(dtype), dq[slow[:64]].astype(dtype), target[slow[:64]].astype(dtype))
-        assert np.allclose(small, u[slow[:64]], rtol=1e-9 if dtype == np.float64 else 1e-4, atol=0)
+        dev = np.abs(small - u[slow[:64]]).max(axis=1) / np.abs(u[slow[:64]]).max(axis=1)
+        assert dev.max() < (1e-9 if dtype == np.float64 else 2e-5), (dtype, dev.max())
 
 
 def test_cooperative_pinv_every_lane_and_ragged_batches():
@@ -681,3 +684,44 @@ def test_random_chains_osc_rollout_and_controllers_on_the_device(n, dof, ortho):
         us = Sliding(rc, kd=40.0, lamb=12.0).generate(q, dq, tg3)
         refs, _ = oo.run_sliding_case(dict(arm=desc, ctrl=dict(kd=40.0, lamb=12.0)), q, dq, tg3, None, None)
         assert np.max(np.abs(us - refs) / np.abs(refs).max(axis=1, keepdims=True)) < 1e-8
+
+
+def test_ki_integrator_vs_reference_golden():
+    """ki != 0 against the REFERENCE's own call sequences (tests/golden/ur5_osc_ki.npz from
+    oracle/ref_harness/run_reference_ki.py): 6 streams x 12 consecutive calls, u and integrated_error after every call,
+    fp64 (vs the fp64 reference mode) and fp32 (vs the same, fp32 tolerance)."""
+    import torch
+
+    g = np.load(f"{GOLD}/ur5_osc_ki.npz")
+    q, dq, target = g["q"], g["dq"], g["target"]
+    T, S = q.shape[:2]
+    case = dict(arm="ur5", osc=dict(kp=float(g["kp"]), ki=float(g["ki"]), ctrlr_dof=[True] * 6, use_C=True),
+                null=[("Damping", dict(kv=10))])
+    for dtype, tol, itol in ((np.float64, 1e-9, 1e-11), (np.float32, 2e-3, 1e-4)):
+        ctrlr = _build_ctrl(_cfg("ur5", dtype=dtype), case)
+        for t in range(T):
+            u = ctrlr.generate(*[torch.as_tensor(a[t].astype(dtype), device="cuda") for a in (q, dq, target)]).cpu().numpy()
+            ref = g["u64"][t]
+            err = np.abs(u - ref).max(axis=1) / np.abs(ref).max(axis=1)
+            assert np.median(err) < tol and err.max() < tol * 100, (dtype, t, err)
+            (buf,) = ctrlr.integrated_error_batch.values()
+            assert np.abs(buf.cpu().numpy() - g["integrated_error64"][t]).max() < itol, (dtype, t)
+
+
+def test_mjcf_imported_chain_on_the_device(tmp_path):
+    """An arm read from an MJCF file (abr_control_b200/arms/mjcf.py; the reference's MujocoConfig reads the same format,
+    arms/mujoco_config.py:64-117) evaluated by the kernels against the oracle built from the imported descriptor."""
+    from abr_control_b200.arms.mjcf import MjcfConfig, chain_desc_from_mjcf
+    from oracle import rbd_oracle as ro
+    from test_mjcf import _random_model, _write
+
+    bodies, ee = _random_model(6, 77)
+    path = str(tmp_path / "arm.xml")
+    _write(path, bodies, ee)
+    rc = MjcfConfig(path)
+    c = ro.ChainOracle(chain_desc_from_mjcf(path))
+    rng = np.random.default_rng(3)
+    q, dq = rng.uniform(-np.pi, np.pi, (40, 6)), rng.uniform(-2, 2, (40, 6))
+    out = rc.eval(q, dq, want=("Tx", "J", "M", "g", "C"))
+    for k, ref in (("Tx", c.Tx("EE", q)), ("J", c.J("EE", q)), ("M", c.M(q)), ("g", c.g(q)), ("C", c.C(q, dq))):
+        assert np.abs(out[k] - ref).max() < 1e-10 * max(1.0, np.abs(ref).max()), k

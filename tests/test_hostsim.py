@@ -304,3 +304,18 @@ def test_frame_names(hostsim):
     assert hostsim.hs_frame_id(6, b"EE") == 13
     for bad in (b"link7", b"joint6", b"ee", b"link", b"hand", b"link-1", b"joint1x"):
         assert hostsim.hs_frame_id(6, bad) == _abi.EFRAME
+
+
+def test_ki_integrator_vs_reference_golden(hostsim):
+    """the kernels' per-state code (integrated_error carried from call to call) against the reference's own sequences"""
+    g = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "ur5_osc_ki.npz"))
+    q, dq, target = g["q"], g["dq"], g["target"]
+    T, S = q.shape[:2]
+    cs = dict(arm="ur5", osc=dict(kp=float(g["kp"]), ki=float(g["ki"]), ctrlr_dof=[True] * 6, use_C=True),
+              null=[("Damping", dict(kv=10))])
+    ierr = np.zeros((S, 6))
+    for t in range(T):
+        u, _, _ = hs_osc(hostsim, cs, q[t], dq[t], target[t], None, ierr=ierr)
+        ref = g["u64"][t]
+        assert np.max(np.abs(u - ref) / np.abs(ref).max(axis=1, keepdims=True)) < 1e-9, t
+        assert np.abs(ierr - g["integrated_error64"][t]).max() < 1e-11, t

@@ -44,11 +44,18 @@ def _mb(v):
 
 
 def record_traffic(traffic, name, tag, json_path):
+    """profiles/ncu_traffic.json: per captured kernel the DRAM bytes per launch, the FP-pipe fraction (what binds the
+    arithmetic-heavy kernels) and the capture's own duration; bench.py reads it for `roofline`."""
     for d in json.load(open(json_path)):
         if "dram__bytes_read.sum" in d:
             key = re.sub(r"void |unnamed>::|\(.*", "", d["kernel"]).strip()
+            is64 = "<double" in key
+            pipe = d.get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active" if is64 else
+                         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active")
             traffic[f"{name}:{key}"] = {
                 "dram_mb_per_launch": round(_mb(d["dram__bytes_read.sum"]) + _mb(d["dram__bytes_write.sum"]), 3),
+                "fp_pipe_frac": round(float(pipe[0].replace(",", "")) / 100.0, 4) if pipe else None,
+                "fp_pipe": "fp64" if is64 else "fma (fp32)",
                 "ncu_us": float(d["gpu__time_duration.sum"][0]), "tag": tag}
 
 
