@@ -18,30 +18,26 @@ namespace abrb {
 constexpr int kCoopGroup = 8;  // lanes per state (6 or 3 row owners + idle lanes: shuffles stay inside an 8-lane group)
 
 // Exchange area of one warp (shared memory, slot-major like the kinematic scratch: value i of lane l at [i * 32 + l]):
-//   [0, KD)        y  ->  Mx y
-//   [KD, 2 KD)     z  ->  Mx z
-//   [2 KD, ...)    A(r, k) at 2 KD + r * N + k     (only when the scratch lives in registers: COPY_A)
+//   [0, W)         in: y (KD values)   out: A^T Mx y (N values)        W = max(KD, N)
+//   [W, 2 W)       in: z               out: A^T Mx z
+//   [2 W, ...)     A(r, k) at 2 W + r * N + k     (only when the scratch lives in registers: COPY_A)
 template <int N, int KD, bool COPY_A>
 struct CoopLayout {
-  static constexpr int kY = 0, kZ = KD, kA = 2 * KD;
-  static constexpr int kSlots = 2 * KD + (COPY_A ? KD * N : 0);
+  static constexpr int kW = KD > N ? KD : N;
+  static constexpr int kY = 0, kZ = kW, kA = 2 * kW;
+  static constexpr int kSlots = 2 * kW + (COPY_A ? KD * N : 0);
 };
 
-// One-sided Jacobi SVD of NS independent KD x N matrices (NS = 1 or 2, interleaved: the rounds are dependent chains, so a
-// second state rides along almost for free) whose row `sub` this lane loaded into `me[s].b` (lanes sub >= KD of the
-// 8-lane group hold zero rows), followed by x = pinv(A A^T, rcond) y for the two right-hand sides: on return EVERY lane
-// of the group holds xy[s][] (and xz[s][] if `two`).  All 32 lanes of the warp must call it together.
+// One-sided Jacobi SVD of NS independent KD x N matrices (NS = 1 or 2, interleaved) whose row `sub` and right-hand-side
+// entries y[sub], z[sub] this lane loaded into `me[s]` (lanes sub >= KD of the 8-lane group hold zeros), followed by
+// w = A^T pinv(A A^T, rcond) y for the two right-hand sides: on return EVERY lane of the group holds wy[s][] (and
+// wz[s][] if `two`).  All 32 lanes of the warp must call it together.
 template <int N, int KD, int NS>
 __device__ __forceinline__ void coop_jacobi_group(JacobiRow<N, KD> (&me)[NS], int sub, int gbase, const bool (&owner)[NS],
-                                                  const double (&y)[NS][KD], const double (&z)[NS][KD], double rcond,
-                                                  bool two, double (&xy)[NS][KD], double (&xz)[NS][KD]) {
+                                                  double rcond, bool two, double (&wy)[NS][N], double (&wz)[NS][N]) {
   constexpr unsigned kFull = 0xffffffffu;
   constexpr int NRR = KD + (KD & 1);
   JacobiRow<N, KD> other[NS];
-#pragma unroll
-  for (int s = 0; s < NS; ++s)
-#pragma unroll
-    for (int k = 0; k < KD; ++k) me[s].v[k] = k == sub ? 1.0 : 0.0;
 #pragma unroll 1
   for (int sweep = 0; sweep < kJacobiMaxSweeps; ++sweep) {
     bool big = false;
@@ -52,8 +48,8 @@ __device__ __forceinline__ void coop_jacobi_group(JacobiRow<N, KD> (&me)[NS], in
       for (int s = 0; s < NS; ++s) {
 #pragma unroll
         for (int k = 0; k < N; ++k) other[s].b[k] = __shfl_sync(kFull, me[s].b[k], gbase + p);
-#pragma unroll
-        for (int k = 0; k < KD; ++k) other[s].v[k] = __shfl_sync(kFull, me[s].v[k], gbase + p);
+        other[s].t[0] = __shfl_sync(kFull, me[s].t[0], gbase + p);
+        other[s].t[1] = __shfl_sync(kFull, me[s].t[1], gbase + p);
       }
       if (sub < NRR) {
 #pragma unroll
@@ -75,36 +71,27 @@ __device__ __forceinline__ void coop_jacobi_group(JacobiRow<N, KD> (&me)[NS], in
       smax = t > smax ? t : smax;
     }
     const bool keep = owner[s] && s2 > rcond * smax;
-    double cy = 0.0, cz = 0.0;
-    if (keep) {
+    const double is2 = keep ? inv_t(s2) : 0.0;
+    const double cy = me[s].t[0] * is2, cz = me[s].t[1] * is2;
 #pragma unroll
-      for (int k = 0; k < KD; ++k) {
-        cy += me[s].v[k] * y[s][k];
-        cz += me[s].v[k] * z[s][k];
-      }
-      const double is2 = inv_t(s2);
-      cy *= is2;
-      cz *= is2;
-    }
-#pragma unroll
-    for (int k = 0; k < KD; ++k) {
-      double a = cy * me[s].v[k], c = cz * me[s].v[k];
+    for (int k = 0; k < N; ++k) {
+      double a = cy * me[s].b[k], c = cz * me[s].b[k];
 #pragma unroll
       for (int d = 1; d < kCoopGroup; d <<= 1) {
         a += __shfl_xor_sync(kFull, a, d);
         if (two) c += __shfl_xor_sync(kFull, c, d);
       }
-      xy[s][k] = a;
-      xz[s][k] = c;
+      wy[s][k] = a;
+      wz[s][k] = c;
     }
   }
 }
 
 // Decompose the states of the lanes in `mask` (warp-uniform, non-zero) IN LINE: group g of the warp takes the g-th
 // waiting lane, four states per pass.  `ASlot`: where row r, column k of A of lane o is found:
-// abase[ASlot::at(r, k) * 32 + o].  y, z are read from, and Mx y, Mx z written to, xyz[(i) * 32 + o].  Not inlined: the
-// hot path only pays a call, and the routine's registers are its own.
-template <typename T, int N, int KD, class ASlot>
+// abase[ASlot::at(r, k) * 32 + o].  y, z are read from xyz[(LY::kY / kZ + r) * 32 + o], and A^T Mx y, A^T Mx z written
+// over them.  Not inlined: the hot path only pays a call, and the routine's registers are its own.
+template <typename T, int N, int KD, class ASlot, class LY>
 __device__ __noinline__ void coop_pinv_warp(unsigned mask, const T *abase, T *xyz, int lane, double rcond, bool two) {
   const int sub = lane & (kCoopGroup - 1), grp = lane / kCoopGroup, gbase = lane & ~(kCoopGroup - 1);
   while (mask != 0u) {
@@ -113,21 +100,19 @@ __device__ __noinline__ void coop_pinv_warp(unsigned mask, const T *abase, T *xy
     const int o = have ? (int)found : 0;
     JacobiRow<N, KD> me[1];
     const bool owner[1] = {have && sub < KD};
+    const int row = sub < KD ? sub : 0;
 #pragma unroll
-    for (int k = 0; k < N; ++k) me[0].b[k] = owner[0] ? double(abase[ASlot::at(sub, k) * 32 + o]) : 0.0;
-    double y[1][KD], z[1][KD], xy[1][KD], xz[1][KD];
-#pragma unroll
-    for (int k = 0; k < KD; ++k) {
-      y[0][k] = double(xyz[k * 32 + o]);
-      z[0][k] = double(xyz[(KD + k) * 32 + o]);
-    }
-    coop_jacobi_group<N, KD, 1>(me, sub, gbase, owner, y, z, rcond, two, xy, xz);
+    for (int k = 0; k < N; ++k) me[0].b[k] = owner[0] ? double(abase[ASlot::at(row, k) * 32 + o]) : 0.0;
+    me[0].t[0] = owner[0] ? double(xyz[(LY::kY + row) * 32 + o]) : 0.0;
+    me[0].t[1] = (owner[0] && two) ? double(xyz[(LY::kZ + row) * 32 + o]) : 0.0;
+    double wy[1][N], wz[1][N];
     __syncwarp();  // every lane of the group has read y, z before they are overwritten
+    coop_jacobi_group<N, KD, 1>(me, sub, gbase, owner, rcond, two, wy, wz);
     if (have && sub == 0) {
 #pragma unroll
-      for (int k = 0; k < KD; ++k) {
-        xyz[k * 32 + o] = T(xy[0][k]);
-        if (two) xyz[(KD + k) * 32 + o] = T(xz[0][k]);
+      for (int k = 0; k < N; ++k) {
+        xyz[(LY::kY + k) * 32 + o] = T(wy[0][k]);
+        if (two) xyz[(LY::kZ + k) * 32 + o] = T(wz[0][k]);
       }
     }
     // drop the (up to) four states of this pass
@@ -147,10 +132,7 @@ template <int N, int KD>
 struct CoopRecord {
   static constexpr int kA = 0, kL = KD * N, kY = kL + N * (N + 1) / 2, kZ = kY + KD, kLen = kZ + KD;
 };
-#ifndef ABRB_OSC_BLOCK
-#define ABRB_OSC_BLOCK 128
-#endif
-constexpr int kCoopQueue = 8 * (ABRB_OSC_BLOCK / 32);  // records per CTA (eight per warp)
+constexpr int kCoopQueuePerWarp = 8;  // queue capacity of a CTA: eight records per warp
 
 template <typename T>
 struct FlushOut {
@@ -170,7 +152,8 @@ __device__ __forceinline__ void coop_flush_round(const T *qrec, const long long 
   JacobiRow<N, KD> me[NS];
   bool have[NS], owner[NS];
   const T *rec[NS];
-  double y[NS][KD], z[NS][KD], xy[NS][KD], xz[NS][KD];
+  double wy[NS][N], wz[NS][N];
+  const int row_ = sub < KD ? sub : 0;
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     const int e = first + s * stride;
@@ -178,37 +161,24 @@ __device__ __forceinline__ void coop_flush_round(const T *qrec, const long long 
     owner[s] = have[s] && sub < KD;
     rec[s] = qrec + (size_t)(have[s] ? e : 0) * RC::kLen;
 #pragma unroll
-    for (int k = 0; k < N; ++k) me[s].b[k] = owner[s] ? double(rec[s][RC::kA + sub * N + k]) : 0.0;
-#pragma unroll
-    for (int k = 0; k < KD; ++k) {
-      y[s][k] = double(rec[s][RC::kY + k]);
-      z[s][k] = double(rec[s][RC::kZ + k]);
-    }
+    for (int k = 0; k < N; ++k) me[s].b[k] = owner[s] ? double(rec[s][RC::kA + row_ * N + k]) : 0.0;
+    me[s].t[0] = owner[s] ? double(rec[s][RC::kY + row_]) : 0.0;
+    me[s].t[1] = (owner[s] && two) ? double(rec[s][RC::kZ + row_]) : 0.0;
   }
-  coop_jacobi_group<N, KD, NS>(me, sub, gbase, owner, y, z, rcond, two, xy, xz);
+  coop_jacobi_group<N, KD, NS>(me, sub, gbase, owner, rcond, two, wy, wz);
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
-    // du = -L (A^T x): lane k forms (A^T x)_k, lane i then row i of the triangular product
-    double wy = 0.0, wz = 0.0;
+    // du = -L (A^T Mx y + A^T Mx z): every lane holds the two vectors, lane i forms row i of the triangular product
     if (have[s] && sub < N) {
+      double dy = 0.0, dz = 0.0;
 #pragma unroll
-      for (int r = 0; r < KD; ++r) {
-        const double a = double(rec[s][RC::kA + r * N + sub]);
-        wy += a * xy[s][r];
-        wz += a * xz[s][r];
+      for (int k = 0; k < N; ++k) {
+        if (k <= sub) {
+          const double l = double(rec[s][RC::kL + sub * (sub + 1) / 2 + k]);
+          dy += l * wy[s][k];
+          dz += l * wz[s][k];
+        }
       }
-    }
-    double dy = 0.0, dz = 0.0;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      const double ky = __shfl_sync(0xffffffffu, wy, gbase + k), kz = __shfl_sync(0xffffffffu, wz, gbase + k);
-      if (have[s] && sub < N && k <= sub) {
-        const double l = double(rec[s][RC::kL + sub * (sub + 1) / 2 + k]);
-        dy += l * ky;
-        dz += l * kz;
-      }
-    }
-    if (have[s] && sub < N) {
       const int64_t row = qrow[first + s * stride];
       const T *src = o.u != nullptr ? o.u + row * N + sub : o.peer[o.self] + (o.row0 + row) * N + sub;
       const T v = T(double(*src) - dy - (two ? dz : 0.0));
@@ -257,9 +227,11 @@ struct WarpCoop {
   long long *qrow = nullptr;
   int *qcount = nullptr;
   long long row = 0;  // this lane's state index
+  int qcap = 0;       // queue capacity (records)
 
   template <typename T_, int N_, int KD_, class LGet>
-  __device__ __forceinline__ void pinv(bool slow, K_ &K, LGet L, T *y, T *z, bool two, double rcond) {
+  __device__ __forceinline__ void pinv(bool slow, K_ &K, LGet L, const T *y, const T *z, T *wy, T *wz, bool two,
+                                       double rcond) {
     slow = slow && valid;
     unsigned mask = __ballot_sync(0xffffffffu, slow);
     if (mask == 0u) return;  // warp-uniform
@@ -268,7 +240,7 @@ struct WarpCoop {
       bool queued = false;
       if (slow) {
         const int pos = atomicAdd(qcount, 1);
-        if (pos < kCoopQueue) {
+        if (pos < qcap) {
           queued = true;
           T *rec = qrec + (size_t)pos * RC::kLen;
           qrow[pos] = row;
@@ -276,8 +248,6 @@ struct WarpCoop {
           for (int r = 0; r < KD; ++r) {
             rec[RC::kY + r] = y[r];
             rec[RC::kZ + r] = z[r];
-            y[r] = T(0);  // the owner finishes without the task-space term; the flush adds it to the stored row
-            z[r] = T(0);
 #pragma unroll
             for (int k = 0; k < N; ++k) rec[RC::kA + r * N + k] = K.s.ld(K_::aslot(r, k));
           }
@@ -287,6 +257,11 @@ struct WarpCoop {
 #pragma unroll
             for (int b = 0; b < N; ++b)
               if (b <= a) rec[RC::kL + li++] = L(a, b);
+#pragma unroll
+          for (int k = 0; k < N; ++k) {  // the owner finishes without the task-space term; the flush adds it to the stored row
+            wy[k] = T(0);
+            wz[k] = T(0);
+          }
         }
       }
       slow = slow && !queued;
@@ -308,15 +283,15 @@ struct WarpCoop {
     }
     __syncwarp();
     if (kCopyA)
-      coop_pinv_warp<T, N, KD, InExchange>(mask, xch, xch, lane, rcond, two);
+      coop_pinv_warp<T, N, KD, InExchange, LY>(mask, xch, xch, lane, rcond, two);
     else
-      coop_pinv_warp<T, N, KD, InScratch>(mask, scratch, xch, lane, rcond, two);
+      coop_pinv_warp<T, N, KD, InScratch, LY>(mask, scratch, xch, lane, rcond, two);
     __syncwarp();
     if (slow) {
 #pragma unroll
-      for (int r = 0; r < KD; ++r) {
-        y[r] = xch[(LY::kY + r) * 32 + lane];
-        if (two) z[r] = xch[(LY::kZ + r) * 32 + lane];
+      for (int k = 0; k < N; ++k) {
+        wy[k] = xch[(LY::kY + k) * 32 + lane];
+        wz[k] = two ? xch[(LY::kZ + k) * 32 + lane] : T(0);
       }
     }
   }

@@ -618,26 +618,58 @@ ABRB_HD void dynamics_Mg_rotational(const ChainK<T, N> &P, const K_ &K, const T 
       W.apply(Z[a], zd[a]);
       W.add(K, a, dq[a]);
     }
-    ABRB_UNROLL
-    for (int k = 0; k < N; ++k) {
-      T hz[3] = {T(0), T(0), T(0)}, hd[3] = {T(0), T(0), T(0)};
+    // hz_k = Wos[k] o (sum_{j<=k} dq_j z_j) + sum_{j>k} dq_j Wos[j] o z_j: a running prefix and a stored suffix instead of
+    // the O(N^2) double loop (likewise hd with zd)
+    T Qz[N][3], Qd[N][3];
+    {
+      T rz[3] = {T(0), T(0), T(0)}, rd[3] = {T(0), T(0), T(0)};
       ABRB_UNROLL
-      for (int j = 0; j < N; ++j) {
-        const int m = k > j ? k : j;
+      for (int k = N - 1; k >= 0; --k) {
         ABRB_UNROLL
         for (int c = 0; c < 3; ++c) {
-          hz[c] += dq[j] * P.Wos[m][c] * Z[j][c];
-          hd[c] += dq[j] * P.Wos[m][c] * zd[j][c];
+          Qz[k][c] = rz[c];
+          Qd[k][c] = rd[c];
+          rz[c] += dq[k] * P.Wos[k][c] * Z[k][c];
+          rd[c] += dq[k] * P.Wos[k][c] * zd[k][c];
         }
       }
-      cdq[k] += dot3(zd[k], hz) + dot3(Z[k], hd);
-      // -(1/2) d/dq_i terms: state k receives from every i < k:  - dq_k (Omega_i z_k) . hz_k
+    }
+    T Pz[3] = {T(0), T(0), T(0)}, Pd[3] = {T(0), T(0), T(0)};
+    T hzs[N][3];
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) {
+      T hd[3];
       ABRB_UNROLL
-      for (int i = 0; i < N; ++i) {
-        if (i < k) {
-          T oz[3];
-          omega_apply(K, i, Z[k], oz);
-          cdq[i] -= dq[k] * dot3(oz, hz);
+      for (int c = 0; c < 3; ++c) {
+        Pz[c] += dq[k] * Z[k][c];
+        Pd[c] += dq[k] * zd[k][c];
+        hzs[k][c] = P.Wos[k][c] * Pz[c] + Qz[k][c];
+        hd[c] = P.Wos[k][c] * Pd[c] + Qd[k][c];
+      }
+      cdq[k] += dot3(zd[k], hzs[k]) + dot3(Z[k], hd);
+    }
+    // -(1/2) d/dq_i terms: state i receives from every k > i:  - dq_k (Omega_i z_k) . hz_k
+    if (ORTHO) {
+      // (z_i x z_k) . hz_k = z_i . (z_k x hz_k): one cross product per k and a running suffix sum
+      T acc[3] = {T(0), T(0), T(0)};
+      ABRB_UNROLL
+      for (int i = N - 2; i >= 0; --i) {
+        T v[3];
+        cross3(Z[i + 1], hzs[i + 1], v);
+        ABRB_UNROLL
+        for (int c = 0; c < 3; ++c) acc[c] += dq[i + 1] * v[c];
+        cdq[i] -= dot3(Z[i], acc);
+      }
+    } else {
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) {
+        ABRB_UNROLL
+        for (int i = 0; i < N; ++i) {
+          if (i < k) {
+            T oz[3];
+            omega_apply(K, i, Z[k], oz);
+            cdq[i] -= dq[k] * dot3(oz, hzs[k]);
+          }
         }
       }
     }
@@ -1244,17 +1276,19 @@ ABRB_HD_NOINLINE void pinv_apply_sym(const T *Sin, unsigned active, T rcond, con
 // numpy.linalg.pinv drops the singular values <= rcond * largest; for the symmetric positive semi-definite A A^T
 // they are its eigenvalues, i.e. the SQUARED singular values of A.  A one-sided (Hestenes) Jacobi SVD of the rows
 // of A finds them without ever forming A A^T (whose eigenvalue ratios reach 1e-16 here): pairs of rows are rotated
-// until all rows are mutually orthogonal, B = V A, B B^T = diag(s2), and then
-//   pinv(A A^T) y = sum_{i: s2_i > rcond * max s2} V_i^T (V_i . y) / s2_i .
+// until all rows are mutually orthogonal, B = G A, B B^T = diag(s2), and then
+//   pinv(A A^T) y = sum_{i: s2_i > rcond * max s2} G_i^T (G y)_i / s2_i .
 // The pairs of one round (round-robin tournament schedule) are disjoint, so a round is ONE parallel step: on the GPU
 // each row lives in its own lane of an 8-lane group of the warp and the partners exchange rows with shuffles
 // (abrb_coop.cuh); the host instantiation (tests/hostsim) walks the same schedule sequentially.  Both use the
 // per-row step below, so the arithmetic is the same.
 template <int N, int KD>
 struct JacobiRow {
-  double b[N];   // the (rotated) row of A
-  double v[KD];  // its row of the accumulated rotations V
+  double b[N];  // the (rotated) row of A
+  double t[2];  // its entries of the rotated right-hand sides G y and G z (G: the accumulated rotations)
 };
+// (The accumulated rotations themselves are never needed: with B = G A, B B^T = diag(s2), the product the controller
+// wants is  A^T pinv(A A^T) y = B^T diag(keep / s2) G y = sum_i b_i (G y)_i / s2_i  — J^T Mx y is L times that.)
 
 // Partner of player i in round r of a round-robin tournament of n (even) players, r = 0 .. n-2: player n-1 stays,
 // the others move around a circle (i + j = 2 r mod n-1).
@@ -1310,22 +1344,24 @@ ABRB_HD int jacobi_pair(bool lo, JacobiRow<N, KD> &me, const JacobiRow<N, KD> &o
   const double sp = lo ? -sn : sn;
   ABRB_UNROLL
   for (int k = 0; k < N; ++k) me.b[k] = c * me.b[k] + sp * other.b[k];
-  ABRB_UNROLL
-  for (int k = 0; k < KD; ++k) me.v[k] = c * me.v[k] + sp * other.v[k];
+  me.t[0] = c * me.t[0] + sp * other.t[0];
+  me.t[1] = c * me.t[1] + sp * other.t[1];
   return g2 > 1e-12 * prod ? 2 : 1;
 }
 
 constexpr int kJacobiMaxSweeps = 24;
 
-// Sequential walk over the same schedule (host instantiation and single-state fall-backs).  A: KD x N row-major.
+// Sequential walk over the same schedule (host instantiation).  A: KD x N row-major.  Returns
+// wy = A^T pinv(A A^T, rcond) y and wz likewise (N values each).
 template <int N, int KD>
-ABRB_HD void pinv_rows_jacobi_seq(const double *A, double rcond, const double *y, const double *z, bool two, double *xy,
-                                  double *xz) {
+ABRB_HD void pinv_rows_jacobi_seq(const double *A, double rcond, const double *y, const double *z, bool two, double *wy,
+                                  double *wz) {
   constexpr int NRR = KD + (KD & 1);
   JacobiRow<N, KD> row[NRR], old[NRR];
   for (int i = 0; i < NRR; ++i) {
     for (int k = 0; k < N; ++k) row[i].b[k] = i < KD ? A[i * N + k] : 0.0;
-    for (int k = 0; k < KD; ++k) row[i].v[k] = i == k ? 1.0 : 0.0;
+    row[i].t[0] = i < KD ? y[i] : 0.0;
+    row[i].t[1] = (i < KD && two) ? z[i] : 0.0;
   }
   for (int sweep = 0; sweep < kJacobiMaxSweeps; ++sweep) {
     bool big = false;
@@ -1345,19 +1381,13 @@ ABRB_HD void pinv_rows_jacobi_seq(const double *A, double rcond, const double *y
     s2[i] = acc;
     smax = acc > smax ? acc : smax;
   }
-  for (int k = 0; k < KD; ++k) xy[k] = xz[k] = 0.0;
+  for (int k = 0; k < N; ++k) wy[k] = wz[k] = 0.0;
   for (int i = 0; i < KD; ++i) {
     if (!(s2[i] > rcond * smax)) continue;
-    double cy = 0.0, cz = 0.0;
-    for (int k = 0; k < KD; ++k) {
-      cy += row[i].v[k] * y[k];
-      if (two) cz += row[i].v[k] * z[k];
-    }
-    cy /= s2[i];
-    cz /= s2[i];
-    for (int k = 0; k < KD; ++k) {
-      xy[k] += row[i].v[k] * cy;
-      if (two) xz[k] += row[i].v[k] * cz;
+    const double cy = row[i].t[0] / s2[i], cz = row[i].t[1] / s2[i];
+    for (int k = 0; k < N; ++k) {
+      wy[k] += row[i].b[k] * cy;
+      wz[k] += row[i].b[k] * cz;
     }
   }
 }

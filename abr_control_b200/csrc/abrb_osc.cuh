@@ -160,18 +160,18 @@ ABRB_HD T wrap_pm_pi(T d) {
 // instantiation (tests/hostsim), where a "warp" is one state.
 struct SeqCoop {
   template <typename T, int N, int KD, class K_, class LGet>
-  ABRB_HD void pinv(bool slow, K_ &K, LGet, T *y, T *z, bool two, double rcond) const {
+  ABRB_HD void pinv(bool slow, K_ &K, LGet, const T *y, const T *z, T *wy, T *wz, bool two, double rcond) const {
     if (!slow) return;
-    double A[KD * N], yd[KD], zd[KD], xy[KD], xz[KD];
+    double A[KD * N], yd[KD], zd[KD], oy[N], oz[N];
     for (int r = 0; r < KD; ++r) {
       yd[r] = double(y[r]);
       zd[r] = double(z[r]);
       for (int k = 0; k < N; ++k) A[r * N + k] = double(K.s.ld(K_::aslot(r, k)));
     }
-    pinv_rows_jacobi_seq<N, KD>(A, rcond, yd, zd, two, xy, xz);
-    for (int r = 0; r < KD; ++r) {
-      y[r] = T(xy[r]);
-      if (two) z[r] = T(xz[r]);
+    pinv_rows_jacobi_seq<N, KD>(A, rcond, yd, zd, two, oy, oz);
+    for (int k = 0; k < N; ++k) {
+      wy[k] = T(oy[k]);
+      wz[k] = T(oz[k]);
     }
   }
 };
@@ -484,8 +484,24 @@ ABRB_HD void osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
   }
   // ... and the truncating pseudo-inverse otherwise (always in double: the matrices that end up here have eigenvalue
   // ratios down to 1e-16).  When nothing is below the cut-off it returns S^-1 y itself, as numpy's pinv does.
+  // wy = A^T Mx y, wz = A^T Mx z  (J^T x = L (A^T x), osc.py:285-288): from the solved y, z in the regular case; for the
+  // states on the truncating route the cooperative step provides them directly (zero if the state was deferred: the
+  // CTA's flush then adds the task-space term to the stored row)
+  T wy[N], wz[N];
+  ABRB_UNROLL
+  for (int k = 0; k < N; ++k) {
+    T sy = T(0), sz = T(0);
+    ABRB_UNROLL
+    for (int r = 0; r < KD; ++r) {
+      const T ark = K.s.ld(Aslot(r, k));
+      sy += ark * y[r];
+      sz += ark * z[r];
+    }
+    wy[k] = sy;
+    wz[k] = sz;
+  }
   auto Lget = [&](int a, int b) { return PARK_L ? K.s.ld(SL::kPark + a * (a + 1) / 2 + b) : M[a][b]; };
-  coop.template pinv<T, N, KD>(!fast, K, Lget, y, z, any_null, double(rcond));
+  coop.template pinv<T, N, KD>(!fast, K, Lget, y, z, wy, wz, any_null, double(rcond));
   if (PARK) {
     int li = 0;
     ABRB_UNROLL
@@ -499,16 +515,7 @@ ABRB_HD void osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
     }
   }
 
-  // J^T x = L (A^T x)   (osc.py:285-288)
-  auto JT_apply = [&](const T *x, T *out) {
-    T w[N];
-    ABRB_UNROLL
-    for (int k = 0; k < N; ++k) {
-      T s = T(0);
-      ABRB_UNROLL
-      for (int r = 0; r < KD; ++r) s += K.s.ld(Aslot(r, k)) * x[r];
-      w[k] = s;
-    }
+  auto L_apply = [&](const T *w, T *out) {
     ABRB_UNROLL
     for (int i = 0; i < N; ++i) {
       T s = T(0);
@@ -520,7 +527,7 @@ ABRB_HD void osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
   };
   {
     T jt[N];
-    JT_apply(y, jt);
+    L_apply(wy, jt);
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) u[k] -= jt[k];
   }
@@ -539,7 +546,7 @@ ABRB_HD void osc_eval(const ChainK<T, N> &P, const OscK<T, N> &O, const T *q, co
   // ---- secondary controllers, filtered:  u += u_null - J^T Mx J M^-1 u_null   (osc.py:310-318)
   if (any_null) {
     T jt[N];
-    JT_apply(z, jt);
+    L_apply(wz, jt);
     ABRB_UNROLL
     for (int k = 0; k < N; ++k) u[k] += un[k] - jt[k];
   }

@@ -196,11 +196,11 @@ struct OscArgs {
 };
 
 // CTA-level shared memory of the OSC kernel behind the per-warp regions: the queue of deferred states (abrb_coop.cuh)
-template <typename T, int N, int KD>
+template <typename T, int N, int KD, int CAP>
 struct OscQueue {
-  static constexpr int kRecElems = kCoopQueue * CoopRecord<N, KD>::kLen;
-  static constexpr size_t kRowOff = ((size_t)kRecElems * sizeof(T) + 15) / 16 * 16;   // long long rows[kCoopQueue]
-  static constexpr size_t kCountOff = kRowOff + kCoopQueue * sizeof(long long);      // int count
+  static constexpr int kRecElems = CAP * CoopRecord<N, KD>::kLen;
+  static constexpr size_t kRowOff = ((size_t)kRecElems * sizeof(T) + 15) / 16 * 16;   // long long rows[CAP]
+  static constexpr size_t kCountOff = kRowOff + CAP * sizeof(long long);             // int count
   static constexpr size_t kBytes = kCountOff + 16;
 };
 
@@ -214,17 +214,32 @@ struct OscQueue {
 #ifndef ABRB_OSC_BLOCK
 #define ABRB_OSC_BLOCK 128
 #endif
-constexpr int kOscBlock = ABRB_OSC_BLOCK, kOscWarps = kOscBlock / 32;
-constexpr int kOscFlushAt = kOscWarps * (32 / kCoopGroup);  // one full round of the CTA's groups
+// The orthonormal-chain fp64 kernels (UR5 ...: 54 scratch slots per lane) could afford one 256-thread CTA per SM instead
+// of two 128-thread ones (eight warps sharing the instruction fetches of the same straight-line code, a queue that
+// practically never overflows the CTA's groups).  Measured on B200, UR5 6-DOF fp64 B = 65 536: 60.7 us against 60.4 us —
+// the flush gets cheaper and the evaluation itself slower (40.1 against 37.0 us without pseudo-inverse states) — so both
+// stay at 128; the non-orthonormal scratch (126 slots) does not fit eight warps anyway.
+#ifndef ABRB_OSC_BLOCK_ORTHO64
+#define ABRB_OSC_BLOCK_ORTHO64 128
+#endif
+template <typename T, bool ORTHO>
+struct OscBlock {
+  static constexpr int value = (ORTHO && sizeof(T) == 8) ? ABRB_OSC_BLOCK_ORTHO64 : ABRB_OSC_BLOCK;
+};
 
 template <typename T, int N, bool ORTHO, int KD, bool KSMEM>
-__global__ void __launch_bounds__(kOscBlock, (MinBlocks<T>::value * kBlock / kOscBlock > 0 ? MinBlocks<T>::value * kBlock / kOscBlock : 1))
+__global__ void __launch_bounds__(OscBlock<T, ORTHO>::value,
+                                  (MinBlocks<T>::value * kBlock / OscBlock<T, ORTHO>::value > 0
+                                       ? MinBlocks<T>::value * kBlock / OscBlock<T, ORTHO>::value : 1))
 osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
            const __grid_constant__ OscArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef KinSel<T, N, ORTHO, KSMEM> KS;
   typedef OscSmem<T, N, ORTHO, KD, KSMEM> WS;
-  typedef OscQueue<T, N, KD> Q;
+  constexpr int kOscBlock = OscBlock<T, ORTHO>::value, kOscWarps = kOscBlock / 32;
+  constexpr int kOscFlushAt = kOscWarps * (32 / kCoopGroup);  // one full round of the CTA's groups
+  constexpr int kCoopQueue = kCoopQueuePerWarp * kOscWarps;
+  typedef OscQueue<T, N, KD, kCoopQueue> Q;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T *region = reinterpret_cast<T *>(smem_raw) + warp * WS::kElems;
   T *stage = region + WS::kKin;
@@ -241,7 +256,8 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
 #endif
   typename KS::type K;
   KS::bind(K, region, lane);
-  WarpCoop<T, N, KD, typename KS::type> coop{region + WS::kKin + WS::kTile, region, lane, true, qrec, qrow, qcount, 0};
+  WarpCoop<T, N, KD, typename KS::type> coop{region + WS::kKin + WS::kTile, region, lane, true, qrec, qrow, qcount, 0,
+                                             kCoopQueue};
   FlushOut<T> fo;
   fo.u = a.u;
 #ifdef ABRB_DBG_TIMING
@@ -660,8 +676,9 @@ int osc_go(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
   a.tv_stride = c.tv_stride;
   if (c.gather != nullptr) a.g = *c.gather;
   constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32 || ABRB_ROLLED;  // rolled loops index the scratch at run time
+  constexpr int kOscBlock = OscBlock<T, ORTHO>::value, kOscWarps = kOscBlock / 32;
   const size_t smem = ((size_t)kOscWarps * OscSmem<T, N, ORTHO, KD, KSMEM>::kElems * sizeof(T) + 15) / 16 * 16 +
-                      OscQueue<T, N, KD>::kBytes;
+                      OscQueue<T, N, KD, kCoopQueuePerWarp * kOscWarps>::kBytes;
   auto kern = osc_kernel<T, N, ORTHO, KD, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
   if (e != cudaSuccess) return (int)e;

@@ -264,15 +264,15 @@ int hs_ik(const abrb_chain_desc *d, int f32, int force_general, double max_dx, d
 
 int hs_frame_id(int n, const char *name) { return parse_frame(n, name); }
 
-// x = pinv(A A^T, rcond) y for a K x 6 matrix A (K = 6 or 3) through the one-sided Jacobi route of the OSC kernels
-// (which = 0, pinv_rows_jacobi_seq: the sequential walk over the schedule the warp-cooperative device code runs in
-// parallel), or x = pinv(S, rcond) y for a symmetric K x K matrix S through the cyclic Jacobi routine (which = 1).
+// which = 0: w = A^T pinv(A A^T, rcond) y (6 values) for a K x 6 matrix A (K = 6 or 3) through the one-sided Jacobi route
+// of the OSC kernels (pinv_rows_jacobi_seq: the sequential walk over the schedule the warp-cooperative device code runs
+// in parallel); which = 1: x = pinv(S, rcond) y (K values) for a symmetric K x K matrix S through the cyclic Jacobi routine.
 int hs_pinv(int K, const double *A_or_S, unsigned active, double rcond, const double *y, double *x, int which) {
   if (K != 6 && K != 3) return -1;
   if (which == 0) {
-    double zero[6] = {0, 0, 0, 0, 0, 0}, xz[6];
-    if (K == 6) pinv_rows_jacobi_seq<6, 6>(A_or_S, rcond, y, zero, false, x, xz);
-    else pinv_rows_jacobi_seq<6, 3>(A_or_S, rcond, y, zero, false, x, xz);
+    double zero[6] = {0, 0, 0, 0, 0, 0}, wz[6];
+    if (K == 6) pinv_rows_jacobi_seq<6, 6>(A_or_S, rcond, y, zero, false, x, wz);
+    else pinv_rows_jacobi_seq<6, 3>(A_or_S, rcond, y, zero, false, x, wz);
     return 1;
   }
   double Sf[36], yi[6];

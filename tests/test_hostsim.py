@@ -227,14 +227,14 @@ def test_jacobi_pinv_route_vs_numpy(hostsim):
             y = rng.normal(size=K)
             if trial % 7 == 0:
                 y[K - 1] = 0.0
-            x = np.zeros(K)
-            assert hostsim.hs_pinv(K, P(np.ascontiguousarray(A)), (1 << K) - 1, C.c_double(1e-4), P(y), P(x), 0) == 1
+            w = np.zeros(6)  # A^T pinv(A A^T) y: what the controller needs (J^T Mx y = L w)
+            assert hostsim.hs_pinv(K, P(np.ascontiguousarray(A)), (1 << K) - 1, C.c_double(1e-4), P(y), P(w), 0) == 1
             S = A @ A.T
             lam = np.linalg.eigvalsh(S)
             if np.min(np.abs(lam / lam.max() - 1e-4)) < 1e-7:
                 continue  # an eigenvalue on the cut-off itself: either side is right
-            ref = np.linalg.pinv(S, rcond=1e-4, hermitian=True) @ y
-            worst = max(worst, np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-30))
+            ref = A.T @ (np.linalg.pinv(S, rcond=1e-4, hermitian=True) @ y)
+            worst = max(worst, np.abs(w - ref).max() / max(np.abs(ref).max(), 1e-30))
     assert worst < 1e-9, worst
 
 

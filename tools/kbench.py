@@ -53,6 +53,19 @@ for name, dt in (("f64", np.float64), ("f32", np.float32)):
     S3 = sets(dt, 8, 262144)
     u3 = torch.empty((262144, 6), dtype=tdt, device=dev)
     res[f"jaco2_cfg3_B262144_{name}"] = bench.time_kernel(lambda s: c3.generate_into(s[0], s[1], s[2], u3), 50, torch, S3) * 1e6
+# BASELINE config 4: UR5 OSC(kp=10) rollout, 4096 trajectories x 128 steps (us per STEP)
+c4 = OSC(ur5.Config(), kp=10.0)
+q4, dq4, tg4 = (torch.as_tensor(a, device=dev) for a in bench.synth(4096, 6, 4242))
+for _ in range(2):
+    c4.rollout(q4, dq4 * 0.1, tg4, steps=128, dt=1e-3, record=())
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(3):
+    c4.rollout(q4, dq4 * 0.1, tg4, steps=128, dt=1e-3, record=())
+e1.record()
+torch.cuda.synchronize()
+res["rollout4096_us_per_step"] = e0.elapsed_time(e1) * 1e3 / 3 / 128
 print(os.environ.get("ABRB_LIBRARY", "default"), json.dumps({k: round(v, 1) for k, v in res.items()}))
 if os.environ.get("KB_CLOCKS"):
     # SM clock / throttle reasons over a sustained run of the heaviest kernel (is a long FP64 burst power capped?)
