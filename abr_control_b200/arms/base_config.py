@@ -174,18 +174,26 @@ class BaseConfig:
         """Allocation-free batched evaluation for hot loops: ``q``/``dq`` contiguous CUDA tensors (B, n) of one dtype,
         ``out`` a dict key -> preallocated contiguous CUDA tensor of the right shape (keys as in ``eval``)."""
         B = q.shape[0]
+        if not q.is_cuda or q.dim() != 2 or q.shape[1] != self.N_JOINTS or not q.is_contiguous():
+            raise ValueError("eval_into: q must be a contiguous CUDA tensor of shape (B, n_joints)")
+        if dq is not None and (dq.shape != q.shape or dq.dtype != q.dtype or dq.device != q.device or not dq.is_contiguous()):
+            raise ValueError("eval_into: dq must match q")
         o = _abi.RbdOut()
+        shapes = self._shapes()
         for k, t in out.items():
-            if k not in _RBD_KEYS or t.dtype != q.dtype or not t.is_contiguous():
+            if k not in _RBD_KEYS or t.dtype != q.dtype or not t.is_contiguous() or t.device != q.device:
                 raise ValueError(f"eval_into: bad output {k}")
+            if tuple(t.shape) != (B,) + shapes[k]:
+                raise ValueError(f"eval_into: output {k} must have shape {(B,) + shapes[k]}")
             setattr(o, k, t.data_ptr())
         xo = None
         if x is not None:
             xo = (C.c_double * 3)(*[float(v) for v in x])
         L = _lib.lib()
         fn = L.abrb_rbd_eval_f32 if q.dtype == torch.float32 else L.abrb_rbd_eval_f64
-        _lib.check(fn(self._handle, self.frame_id(name), xo, q.data_ptr(), None if dq is None else dq.data_ptr(), B,
-                      C.byref(o), torch.cuda.current_stream(q.device).cuda_stream))
+        with torch.cuda.device(q.device):  # the launch goes to the tensors' device, whatever the current one is
+            _lib.check(fn(self._handle, self.frame_id(name), xo, q.data_ptr(), None if dq is None else dq.data_ptr(), B,
+                          C.byref(o), torch.cuda.current_stream(q.device).cuda_stream))
         return out
 
     def _one(self, key, q, dq=None, name="EE", x=None, ref32=False):

@@ -40,6 +40,7 @@ struct OscCall {
   cudaStream_t stream;
   void *ierr = nullptr;  // (B, 6) integrated task-space error, in/out (device), only with ki != 0
   const GatherArgs *gather = nullptr;
+  int *sched = nullptr;  // device: {next tile, CTAs done}, zero between launches (api.cu, sched_slot), or nullptr
 };
 
 struct RolloutCall {

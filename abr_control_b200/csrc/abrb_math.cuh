@@ -177,27 +177,35 @@ ABRB_HD int frame_dep(int frame) {  // number of joints the frame moves with == 
 // columns 0,1 of R_k and rows 0,1 of R_k^-1.  The values live in a "slot store": registers (RegStore) or a strided
 // shared-memory column per thread (StridedStore, slot-major so consecutive lanes hit consecutive words), which is
 // what the fp64 kernels use to stay under the register limit without spilling to local memory.
+// Phase barrier of the CTA (`sync()`), called by the per-state code at points every thread of the CTA reaches.  The
+// evaluations are ~10^4 straight-line instructions per state, far beyond the instruction caches, and instruction fetch
+// is their top stall reason; a barrier at the phase boundaries keeps the warps of a CTA inside the same code window so
+// that they share the fetched lines.  Measured on B200: it pays for the OSC and rollout kernels (UR5 6-DOF fp64
+// 57.6 -> 54.3 us, rollout step 9.2 -> 8.2 us) and costs the shorter rbd kernels 8-11 %, so the kernel decides (`psync`).
 template <typename T, int COUNT>
 struct RegStore {
   static constexpr bool kShared = false;
   T v[COUNT];
+  bool psync = false;
   ABRB_HD T ld(int i) const { return v[i]; }
   ABRB_HD void st(int i, T x) { v[i] = x; }
-  ABRB_HD void sync() const {}
+  ABRB_HD void sync() const {
+#ifdef __CUDA_ARCH__
+    if (psync) __syncthreads();
+#endif
+  }
 };
 template <typename T, int COUNT>
 struct StridedStore {
   static constexpr bool kShared = true;
   T *base;
   int stride;
+  bool psync = false;
   ABRB_HD T ld(int i) const { return base[i * stride]; }
   ABRB_HD void st(int i, T x) { base[i * stride] = x; }
-  // Phase barrier of the CTA.  The kernels are ~10^4 straight-line instructions per state, far beyond the
-  // instruction caches, and profile as instruction-fetch bound; keeping the warps of a CTA inside the same code
-  // window makes them share the fetched lines.  Only called at points every thread of the CTA reaches.
   ABRB_HD void sync() const {
-#if defined(__CUDA_ARCH__) && defined(ABRB_PHASE_SYNC)  // measured neutral on B200 (tools/kbench.py): off by default
-    __syncthreads();
+#ifdef __CUDA_ARCH__
+    if (psync) __syncthreads();
 #endif
   }
 };

@@ -67,6 +67,95 @@ struct OscK {
   NullK<T, N> nul[kMaxNull];
 };
 
+// pinv of a 3 x N matrix (the position or the orientation rows of a Jacobian) as numpy.linalg.pinv computes it
+// (rcond = 1e-15), applied to right-hand sides: a one-sided (Hestenes) Jacobi SVD of the rows — rotations of row pairs
+// until they are mutually orthogonal give J = V^T diag(sigma) U^T with sigma_i u_i = rotated row i, so
+// pinv(J) y = sum_i row_i (v_i . y) / sigma_i^2 over the sigma_i > 1e-15 sigma_max.  (Going through J J^T would square
+// the condition number.)  The sweep loop is rolled around three rotations with static indices.
+template <typename T, int N>
+struct RowPinv3 {
+  T b0[N], b1[N], b2[N], v0[3], v1[3], v2[3], i0, i1, i2;
+
+  ABRB_HD static void rotate(T *bi, T *bj, T *vi, T *vj) {
+    T al = T(0), be = T(0), ga = T(0);
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) {
+      al += bi[k] * bi[k];
+      be += bj[k] * bj[k];
+      ga += bi[k] * bj[k];
+    }
+    if (ga * ga > (sizeof(T) == 8 ? T(1e-32) : T(1e-14)) * al * be && ga != T(0)) {
+      const T zeta = (be - al) / (T(2) * ga);
+      const T t = (zeta >= T(0) ? T(1) : T(-1)) / (abs_t(zeta) + sqrt_t(T(1) + zeta * zeta));
+      const T c = T(1) / sqrt_t(T(1) + t * t), sn = c * t;
+      ABRB_UNROLL
+      for (int k = 0; k < N; ++k) {
+        const T x = bi[k], y = bj[k];
+        bi[k] = c * x - sn * y;
+        bj[k] = sn * x + c * y;
+      }
+      ABRB_UNROLL
+      for (int k = 0; k < 3; ++k) {
+        const T x = vi[k], y = vj[k];
+        vi[k] = c * x - sn * y;
+        vj[k] = sn * x + c * y;
+      }
+    }
+  }
+
+  // cut_rel: squared singular values <= cut_rel * largest are dropped (numpy.linalg.pinv of the 3 x N matrix with
+  // rcond = 1e-15: 1e-30; pinv(J J^T, rcond) of the symmetric product: rcond itself)
+  ABRB_HD void build(const T *r0, const T *r1, const T *r2, T cut_rel = T(1e-30)) {
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) {
+      b0[k] = r0[k];
+      b1[k] = r1[k];
+      b2[k] = r2[k];
+    }
+    ABRB_UNROLL
+    for (int k = 0; k < 3; ++k) {
+      v0[k] = k == 0 ? T(1) : T(0);
+      v1[k] = k == 1 ? T(1) : T(0);
+      v2[k] = k == 2 ? T(1) : T(0);
+    }
+    ABRB_NOUNROLL
+    for (int sweep = 0; sweep < 8; ++sweep) {
+      rotate(b0, b1, v0, v1);
+      rotate(b0, b2, v0, v2);
+      rotate(b1, b2, v1, v2);
+    }
+    T s0 = T(0), s1 = T(0), s2 = T(0);
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) {
+      s0 += b0[k] * b0[k];
+      s1 += b1[k] * b1[k];
+      s2 += b2[k] * b2[k];
+    }
+    const T smax = s0 > s1 ? (s0 > s2 ? s0 : s2) : (s1 > s2 ? s1 : s2);
+    const T cut = cut_rel * smax;
+    i0 = s0 > cut ? T(1) / s0 : T(0);
+    i1 = s1 > cut ? T(1) / s1 : T(0);
+    i2 = s2 > cut ? T(1) / s2 : T(0);
+  }
+
+  // out = pinv(J J^T, cut_rel) y: the eigenvalues of J J^T are the squared singular values, its eigenvectors the rows of V
+  ABRB_HD void apply_sym(const T *y, T *out) const {
+    const T c0 = (v0[0] * y[0] + v0[1] * y[1] + v0[2] * y[2]) * i0;
+    const T c1 = (v1[0] * y[0] + v1[1] * y[1] + v1[2] * y[2]) * i1;
+    const T c2 = (v2[0] * y[0] + v2[1] * y[1] + v2[2] * y[2]) * i2;
+    ABRB_UNROLL
+    for (int k = 0; k < 3; ++k) out[k] = v0[k] * c0 + v1[k] * c1 + v2[k] * c2;
+  }
+
+  ABRB_HD void apply(const T *y, T *out) const {  // out = pinv(J) y
+    const T c0 = (v0[0] * y[0] + v0[1] * y[1] + v0[2] * y[2]) * i0;
+    const T c1 = (v1[0] * y[0] + v1[1] * y[1] + v1[2] * y[2]) * i1;
+    const T c2 = (v2[0] * y[0] + v2[1] * y[1] + v2[2] * y[2]) * i2;
+    ABRB_UNROLL
+    for (int k = 0; k < N; ++k) out[k] = b0[k] * c0 + b1[k] * c1 + b2[k] * c2;
+  }
+};
+
 // AvoidObstacles.generate — the rare, data-dependent secondary controller; not inlined and self-contained
 // (re-walks the chain) so that the main path's register allocation is unaffected.
 // Lm: Cholesky factor of M (row-major N x N, lower).
@@ -126,15 +215,12 @@ ABRB_HD_NOINLINE void avoid_generate(const ChainK<T, N> &P, const NullK<T, N> &A
           Wc[r][i] = sacc / Lm[i * N + i];
         }
       }
-      T S3[9];
-      for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b) {
-          T sacc = T(0);
-          for (int k = 0; k < N; ++k) sacc += Wc[a][k] * Wc[b][k];
-          S3[a * 3 + b] = sacc;
-        }
+      // Mx_pt F = pinv(Jp M^-1 Jp^T, rcond = 0.01) F  (avoid_obstacles.py:113-116): Jp M^-1 Jp^T = Wc Wc^T, so its
+      // eigen-decomposition is the one-sided Jacobi SVD of the three rows of Wc (registers, no 3 x 3 matrix formed)
       T x3[3];
-      pinv_apply_sym<T, 3>(S3, 7u, T(0.01), F, x3);
+      RowPinv3<T, N> rp;
+      rp.build(Wc[0], Wc[1], Wc[2], T(0.01));
+      rp.apply_sym(F, x3);
       for (int k = 0; k < N; ++k) up[k] -= Jp[0][k] * x3[0] + Jp[1][k] * x3[1] + Jp[2][k] * x3[2];
     }
   }
@@ -735,84 +821,6 @@ ABRB_HD void floating_state(const ChainK<T, N> &P, bool task_space, bool dynamic
   }
   (void)ORTHO;
 }
-
-// pinv of a 3 x N matrix (the position or the orientation rows of a Jacobian) as numpy.linalg.pinv computes it
-// (rcond = 1e-15), applied to right-hand sides: a one-sided (Hestenes) Jacobi SVD of the rows — rotations of row pairs
-// until they are mutually orthogonal give J = V^T diag(sigma) U^T with sigma_i u_i = rotated row i, so
-// pinv(J) y = sum_i row_i (v_i . y) / sigma_i^2 over the sigma_i > 1e-15 sigma_max.  (Going through J J^T would square
-// the condition number.)  The sweep loop is rolled around three rotations with static indices.
-template <typename T, int N>
-struct RowPinv3 {
-  T b0[N], b1[N], b2[N], v0[3], v1[3], v2[3], i0, i1, i2;
-
-  ABRB_HD static void rotate(T *bi, T *bj, T *vi, T *vj) {
-    T al = T(0), be = T(0), ga = T(0);
-    ABRB_UNROLL
-    for (int k = 0; k < N; ++k) {
-      al += bi[k] * bi[k];
-      be += bj[k] * bj[k];
-      ga += bi[k] * bj[k];
-    }
-    if (ga * ga > (sizeof(T) == 8 ? T(1e-32) : T(1e-14)) * al * be && ga != T(0)) {
-      const T zeta = (be - al) / (T(2) * ga);
-      const T t = (zeta >= T(0) ? T(1) : T(-1)) / (abs_t(zeta) + sqrt_t(T(1) + zeta * zeta));
-      const T c = T(1) / sqrt_t(T(1) + t * t), sn = c * t;
-      ABRB_UNROLL
-      for (int k = 0; k < N; ++k) {
-        const T x = bi[k], y = bj[k];
-        bi[k] = c * x - sn * y;
-        bj[k] = sn * x + c * y;
-      }
-      ABRB_UNROLL
-      for (int k = 0; k < 3; ++k) {
-        const T x = vi[k], y = vj[k];
-        vi[k] = c * x - sn * y;
-        vj[k] = sn * x + c * y;
-      }
-    }
-  }
-
-  ABRB_HD void build(const T *r0, const T *r1, const T *r2) {
-    ABRB_UNROLL
-    for (int k = 0; k < N; ++k) {
-      b0[k] = r0[k];
-      b1[k] = r1[k];
-      b2[k] = r2[k];
-    }
-    ABRB_UNROLL
-    for (int k = 0; k < 3; ++k) {
-      v0[k] = k == 0 ? T(1) : T(0);
-      v1[k] = k == 1 ? T(1) : T(0);
-      v2[k] = k == 2 ? T(1) : T(0);
-    }
-    ABRB_NOUNROLL
-    for (int sweep = 0; sweep < 8; ++sweep) {
-      rotate(b0, b1, v0, v1);
-      rotate(b0, b2, v0, v2);
-      rotate(b1, b2, v1, v2);
-    }
-    T s0 = T(0), s1 = T(0), s2 = T(0);
-    ABRB_UNROLL
-    for (int k = 0; k < N; ++k) {
-      s0 += b0[k] * b0[k];
-      s1 += b1[k] * b1[k];
-      s2 += b2[k] * b2[k];
-    }
-    const T smax = s0 > s1 ? (s0 > s2 ? s0 : s2) : (s1 > s2 ? s1 : s2);
-    const T cut = T(1e-30) * smax;  // (rcond = 1e-15)^2 on the squared singular values
-    i0 = s0 > cut ? T(1) / s0 : T(0);
-    i1 = s1 > cut ? T(1) / s1 : T(0);
-    i2 = s2 > cut ? T(1) / s2 : T(0);
-  }
-
-  ABRB_HD void apply(const T *y, T *out) const {  // out = pinv(J) y
-    const T c0 = (v0[0] * y[0] + v0[1] * y[1] + v0[2] * y[2]) * i0;
-    const T c1 = (v1[0] * y[0] + v1[1] * y[1] + v1[2] * y[2]) * i1;
-    const T c2 = (v2[0] * y[0] + v2[1] * y[1] + v2[2] * y[2]) * i2;
-    ABRB_UNROLL
-    for (int k = 0; k < N; ++k) out[k] = b0[k] * c0 + b1[k] * c1 + b2[k] * c2;
-  }
-};
 
 // Sliding.generate (controllers/sliding.py:34-99); pinv(J[:3]) through RowPinv3.
 template <typename T, int N, class K_>

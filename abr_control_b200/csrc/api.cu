@@ -91,6 +91,8 @@ struct Workspace {
     void *ptr = nullptr;
     size_t cap = 0;
     cudaStream_t lanes[kLanes] = {nullptr, nullptr};  // chunk pipeline inside one call
+    cudaStream_t side[kLanes] = {nullptr, nullptr};   // second copy stream of each lane (dq goes up beside q)
+    cudaEvent_t side_done[kLanes] = {nullptr, nullptr};
     int used = 0;                                      // lanes with work in flight
   } slots[kSlots];
   void release() {
@@ -102,8 +104,11 @@ struct Workspace {
     if (stream) cudaStreamDestroy(stream);
     for (auto &sl : slots) {
       cudaFree(sl.ptr);
-      for (auto &l : sl.lanes)
-        if (l) cudaStreamDestroy(l);
+      for (int l = 0; l < kLanes; ++l) {
+        if (sl.lanes[l]) cudaStreamDestroy(sl.lanes[l]);
+        if (sl.side[l]) cudaStreamDestroy(sl.side[l]);
+        if (sl.side_done[l]) cudaEventDestroy(sl.side_done[l]);
+      }
       sl = Slot();
     }
     cudaSetDevice(cur);
@@ -125,8 +130,10 @@ struct Workspace {
       e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
       if (e != cudaSuccess) return (int)e;
       for (auto &sl : slots)
-        for (auto &l : sl.lanes) {
-          e = cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking);
+        for (int l = 0; l < kLanes; ++l) {
+          e = cudaStreamCreateWithFlags(&sl.lanes[l], cudaStreamNonBlocking);
+          if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sl.side[l], cudaStreamNonBlocking);
+          if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.side_done[l], cudaEventDisableTiming);
           if (e != cudaSuccess) return (int)e;
         }
     }
@@ -161,7 +168,9 @@ struct Workspace {
     Slot &sl = slots[i];
     cudaError_t first = cudaSuccess;
     for (int l = 0; l < sl.used; ++l) {
-      cudaError_t e = cudaStreamSynchronize(sl.lanes[l]);
+      cudaError_t e = cudaStreamSynchronize(sl.side[l]);
+      if (e != cudaSuccess && first == cudaSuccess) first = e;
+      e = cudaStreamSynchronize(sl.lanes[l]);
       if (e != cudaSuccess && first == cudaSuccess) first = e;
     }
     sl.used = 0;
@@ -171,6 +180,40 @@ struct Workspace {
 thread_local Workspace g_ws;
 
 size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+// Tile counters of the OSC kernel's dynamic tile scheduling: every launch takes the next of kSchedSlots {next tile, CTAs
+// done} pairs of its device (zeroed once; the launch's last CTA re-arms its pair).  Launches on one stream are ordered,
+// so a pair can only be shared by two launches in flight if 4096 launches were enqueued between them on other streams.
+// Allocated at the first launch per device (not inside a CUDA-graph capture) and kept for the life of the process.
+constexpr int kSchedSlots = 4096, kMaxDevices = 64;
+struct SchedPool {
+  int *base = nullptr;
+  bool failed = false;
+  std::atomic<unsigned> seq{0};
+};
+SchedPool g_sched[kMaxDevices];
+std::mutex g_sched_mu;
+
+int *sched_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  SchedPool &p = g_sched[dev];
+  if (p.base == nullptr) {
+    std::lock_guard<std::mutex> lock(g_sched_mu);
+    if (p.base == nullptr && !p.failed) {
+      int *b = nullptr;
+      if (cudaMalloc(&b, kSchedSlots * 2 * sizeof(int)) == cudaSuccess &&
+          cudaMemset(b, 0, kSchedSlots * 2 * sizeof(int)) == cudaSuccess) {
+        p.base = b;
+      } else {
+        cudaGetLastError();
+        p.failed = true;  // static tile assignment from now on
+      }
+    }
+  }
+  if (p.base == nullptr) return nullptr;
+  return p.base + 2 * (p.seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
+}
 
 // a cudaMemcpyAsync that is rejected (bad pointer, wrong direction) fails at the call, NOT at the later synchronise
 #define ABRB_CU(call, where)                                \
@@ -380,6 +423,7 @@ static int osc_generate(const abrb_osc *c, int frame_id, const double *x_off, co
   OscCall k{frame_id, x_off, q, dq, target, tv, target_stride, tv_stride, u, train, B, f32, (cudaStream_t)stream};
   k.ierr = ierr;
   k.gather = gather;
+  k.sched = sched_slot();
   int e = cudaErrorInvalidValue;
   switch (n) {
 #define X(j) case j: e = launch_osc<j>(c->model->host, c->params, k); break;
@@ -473,14 +517,18 @@ static int osc_generate_host_async(const abrb_osc *c, int frame_id, const double
     const size_t off_s = (size_t)b0 * row, off_t = (size_t)b0 * 6 * es;
     auto at = [](const void *p, size_t o) { return (const void *)((const char *)p + o); };
     auto atw = [](void *p, size_t o) { return (void *)((char *)p + o); };
+    // q and dq go up on two streams at once (one host->device stream alone reaches about half of what the link gives:
+    // 23 vs 40 GB/s measured on the B200 box); the lane's stream waits for the side copy before the kernel
+    ABRB_CUH(cudaMemcpyAsync(atw(d_dq, off_s), at(dq, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, sl.side[lane]), where);
+    ABRB_CUH(cudaEventRecord(sl.side_done[lane], sl.side[lane]), where);
     ABRB_CUH(cudaMemcpyAsync(atw(d_q, off_s), at(q, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, s), where);
-    ABRB_CUH(cudaMemcpyAsync(atw(d_dq, off_s), at(dq, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, s), where);
     if (target_stride)
       ABRB_CUH(cudaMemcpyAsync(atw(d_t, off_t), at(target, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s), where);
     if (tv && tv_stride)
       ABRB_CUH(cudaMemcpyAsync(atw(d_tv, off_t), at(tv, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s), where);
     if (ierr)
       ABRB_CUH(cudaMemcpyAsync(atw(d_ie, off_t), at(ierr, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s), where);
+    ABRB_CUH(cudaStreamWaitEvent(s, sl.side_done[lane], 0), where);
     rc = osc_generate(c, frame_id, x_off, at(d_q, off_s), at(d_dq, off_s), target_stride ? at(d_t, off_t) : d_t,
                       target_stride, tv ? (tv_stride ? at(d_tv, off_t) : d_tv) : nullptr, tv_stride, atw(d_u, off_s),
                       train ? atw(d_tr, off_s) : nullptr, ierr ? atw(d_ie, off_t) : nullptr, nb, s, f32);

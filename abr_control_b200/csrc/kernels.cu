@@ -193,6 +193,7 @@ struct OscArgs {
   int64_t B;
   int target_stride, tv_stride;
   GatherArgs g;  // n_peer > 0: also store u into every rank's gathered array (peer memory over NVLink)
+  int *sched;    // {next tile, CTAs done} of this launch (zero on entry, re-armed by the last CTA), or nullptr: static tiles
 };
 
 // CTA-level shared memory of the OSC kernel behind the per-warp regions: the queue of deferred states (abrb_coop.cuh)
@@ -201,7 +202,7 @@ struct OscQueue {
   static constexpr int kRecElems = CAP * CoopRecord<N, KD>::kLen;
   static constexpr size_t kRowOff = ((size_t)kRecElems * sizeof(T) + 15) / 16 * 16;   // long long rows[CAP]
   static constexpr size_t kCountOff = kRowOff + CAP * sizeof(long long);             // int count
-  static constexpr size_t kBytes = kCountOff + 16;
+  static constexpr size_t kBytes = kCountOff + 32;  // count (int), next tile (long long)
 };
 
 // One pass over the batch, persistent CTAs (grid = resident CTAs, tiles round-robin).  The states whose task-space
@@ -222,6 +223,18 @@ struct OscQueue {
 #ifndef ABRB_OSC_BLOCK_ORTHO64
 #define ABRB_OSC_BLOCK_ORTHO64 128
 #endif
+// CTA phase barriers inside the evaluation (abrb_math.cuh, RegStore / StridedStore::sync)
+#ifndef ABRB_OSC_PSYNC_F64
+#define ABRB_OSC_PSYNC_F64 1
+#endif
+#ifndef ABRB_OSC_PSYNC_F32
+#define ABRB_OSC_PSYNC_F32 0
+#endif
+template <typename T>
+struct OscPhaseSync {
+  static constexpr bool value = sizeof(T) == 8 ? (ABRB_OSC_PSYNC_F64 != 0) : (ABRB_OSC_PSYNC_F32 != 0);
+};
+
 template <typename T, bool ORTHO>
 struct OscBlock {
   static constexpr int value = (ORTHO && sizeof(T) == 8) ? ABRB_OSC_BLOCK_ORTHO64 : ABRB_OSC_BLOCK;
@@ -256,6 +269,7 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
 #endif
   typename KS::type K;
   KS::bind(K, region, lane);
+  K.s.psync = OscPhaseSync<T>::value;
   WarpCoop<T, N, KD, typename KS::type> coop{region + WS::kKin + WS::kTile, region, lane, true, qrec, qrow, qcount, 0,
                                              kCoopQueue};
   FlushOut<T> fo;
@@ -271,7 +285,16 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
 #pragma unroll
   for (int p = 0; p < kMaxPeers; ++p) fo.peer[p] = static_cast<T *>(a.g.peer_u[p]);
   const double rcond = double(O.thr) * 0.1;
-  for (int64_t base = (int64_t)blockIdx.x * kOscBlock; base < a.B; base += (int64_t)gridDim.x * kOscBlock) {
+  // Tiles: the first one is the CTA's own index; the following ones come from the launch's tile counter, so that a CTA
+  // whose tiles happen to be expensive (obstacle-active states, many pseudo-inverse states) simply takes fewer of them.
+  const long long n_tiles = (a.B + kOscBlock - 1) / kOscBlock;
+  long long *next_tile = reinterpret_cast<long long *>(qbase + Q::kCountOff + 8);
+  for (long long tile = blockIdx.x; tile < n_tiles;) {
+    const int64_t base = tile * kOscBlock;
+    // (the next tile's index is asked for now and published at the end of this tile: the atomic's round trip hides
+    // under the evaluation)
+    long long upcoming = 0;
+    if (threadIdx.x == 0) upcoming = a.sched != nullptr ? (long long)gridDim.x + atomicAdd(a.sched, 1) : tile + gridDim.x;
     // no early exit: every lane of a warp takes part in the cooperative steps; idle lanes / warps redo a valid state
     const int64_t warp_b0 = base + warp * 32;
     const int64_t rem = a.B - warp_b0;
@@ -306,13 +329,15 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
 #ifdef ABRB_DBG_TIMING
     const long long dbg_w0 = clock64();
 #endif
-    __syncthreads();  // this tile's rows and records are visible to the whole CTA
+    if (threadIdx.x == 0) *next_tile = upcoming;
+    __syncthreads();  // this tile's rows and records, and the next tile's index, are visible to the whole CTA
 #ifdef ABRB_DBG_TIMING
     dbg_wait += clock64() - dbg_w0;
     const long long dbg_f0 = clock64();
 #endif
     const int queued = *qcount < kCoopQueue ? *qcount : kCoopQueue;
-    const bool last = base + (int64_t)gridDim.x * kOscBlock >= a.B;
+    tile = *next_tile;
+    const bool last = tile >= n_tiles;
     if (queued >= kOscFlushAt || (last && queued > 0)) {
 #ifndef ABRB_DBG_NOFLUSH  // (timing experiments only: results of the deferred states are then wrong)
       coop_flush_cta<T, N, KD>(qrec, qrow, queued, fo, rcond, O.n_null > 0);
@@ -326,6 +351,14 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
 #endif
     }
     __syncthreads();
+  }
+  if (a.sched != nullptr && threadIdx.x == 0) {  // every CTA has taken its last tile index: the last one re-arms the counter
+    const int done = atomicAdd(a.sched + 1, 1);
+    if (done == (int)gridDim.x - 1) {
+      a.sched[0] = 0;
+      a.sched[1] = 0;
+      __threadfence();
+    }
   }
 #ifdef ABRB_DBG_TIMING
   if (lane == 0 && a.train != nullptr) {
@@ -379,6 +412,7 @@ rollout_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ O
   T *stage = region + WS::kKin;
   typename KS::type K;
   KS::bind(K, region, lane);
+  K.s.psync = OscPhaseSync<T>::value;
   WarpCoop<T, N, KD, typename KS::type> coop{region + WS::kKin + WS::kTile, region, lane, true};
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
     // no early exit (cooperative step inside osc_eval): idle lanes / warps redo a valid state and store nothing
@@ -675,6 +709,7 @@ int osc_go(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
   a.target_stride = c.target_stride;
   a.tv_stride = c.tv_stride;
   if (c.gather != nullptr) a.g = *c.gather;
+  a.sched = c.sched;
   constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32 || ABRB_ROLLED;  // rolled loops index the scratch at run time
   constexpr int kOscBlock = OscBlock<T, ORTHO>::value, kOscWarps = kOscBlock / 32;
   const size_t smem = ((size_t)kOscWarps * OscSmem<T, N, ORTHO, KD, KSMEM>::kElems * sizeof(T) + 15) / 16 * 16 +

@@ -53,6 +53,13 @@ for name, dt in (("f64", np.float64), ("f32", np.float32)):
     S3 = sets(dt, 8, 262144)
     u3 = torch.empty((262144, 6), dtype=tdt, device=dev)
     res[f"jaco2_cfg3_B262144_{name}"] = bench.time_kernel(lambda s: c3.generate_into(s[0], s[1], s[2], u3), 50, torch, S3) * 1e6
+# BASELINE config 5 (per-GPU share): Jaco2 OSC x,y,z + vmax + AvoidObstacles + Damping, fp32, B = 131072
+from abr_control_b200.controllers import AvoidObstacles
+c5 = OSC(rc3, kp=200, vmax=[0.5, 0], ctrlr_dof=[True, True, True, False, False, False],
+         null_controllers=[AvoidObstacles(rc3, obstacles=[[0.09596, -0.2661, 0.64204, 0.05]], threshold=0.2), Damping(rc3, kv=10)])
+S5 = [tuple(t_[:131072].contiguous() for t_ in s) for s in S3]
+u5 = torch.empty((131072, 6), dtype=torch.float32, device=dev)
+res["jaco2_cfg5_B131072_f32"] = bench.time_kernel(lambda s: c5.generate_into(s[0], s[1], s[2], u5), 40, torch, S5) * 1e6
 # BASELINE config 4: UR5 OSC(kp=10) rollout, 4096 trajectories x 128 steps (us per STEP)
 c4 = OSC(ur5.Config(), kp=10.0)
 q4, dq4, tg4 = (torch.as_tensor(a, device=dev) for a in bench.synth(4096, 6, 4242))
