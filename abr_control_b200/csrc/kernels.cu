@@ -6,6 +6,7 @@
 // contiguous per warp; every output array is staged per warp in shared memory and written back with
 // fully coalesced 16-byte stores, so HBM sees whole 128-byte lines only.
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 #include <atomic>
 
@@ -285,6 +286,12 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
 #pragma unroll
   for (int p = 0; p < kMaxPeers; ++p) fo.peer[p] = static_cast<T *>(a.g.peer_u[p]);
   const double rcond = double(O.thr) * 0.1;
+  // Programmatic dependent launch: everything above touched only kernel parameters and shared memory.  A launch that
+  // follows another kernel in its stream is allowed onto the SMs while that kernel's last CTAs are still running (its
+  // launch latency, parameter upload and CTA ramp-up overlap their tail) and waits HERE, before its first global access,
+  // until that kernel has completed and its memory is visible.  Without the launch attribute both are no-ops.
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // Tiles: the first one is the CTA's own index; the following ones come from the launch's tile counter, so that a CTA
   // whose tiles happen to be expensive (obstacle-active states, many pseudo-inverse states) simply takes fewer of them.
   const long long n_tiles = (a.B + kOscBlock - 1) / kOscBlock;
@@ -610,6 +617,16 @@ ik_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ IkArgs
 }
 
 // ------------------------------------------------------------------------------------------------ launch
+// programmatic dependent launch of the OSC kernel (on unless ABRB_PDL=0 in the environment: an A/B switch for timing)
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *v = std::getenv("ABRB_PDL");
+    on = (v != nullptr && v[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 inline int num_sms() {
   static int sm_count = 0;
   if (sm_count == 0) {
@@ -730,9 +747,19 @@ int osc_go(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
     resident_dev = dev;
   }
   const int64_t tiles = (c.B + kOscBlock - 1) / kOscBlock, cap = (int64_t)num_sms() * resident;
-  kern<<<(unsigned)(tiles < cap ? tiles : cap), kOscBlock, smem, c.stream>>>(P, O, a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(tiles < cap ? tiles : cap));
+  cfg.blockDim = dim3(kOscBlock);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  e = cudaLaunchKernelEx(&cfg, kern, P, O, a);
   count_launch();
-  return (int)cudaGetLastError();
+  return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }
 
 template <typename T, int N, bool ORTHO, int KD>

@@ -626,7 +626,9 @@ def run_ours(args):
                                              ("rbd_ur5_JMg_f64_B262144", ("J", "M", "g"), 672, torch.float64, 262144)):
             ring, ring_b = rbd_ring(Bx, want, dtype)
             dt = time_kernel(lambda s: rc.eval_into(s[0], s[1], s[2]), 200 if Bx == B else 60, torch, ring)
-            f = ncu_facts("rbd:" + key)
+            f = ncu_facts({"rbd_ur5_JMgC_f64": "rbd_JMgC:", "rbd_ur5_JMg_f64": "rbd_JMg:",
+                           "rbd_ur5_JMgC_f64_B262144": "rbd_JMgC_B262144:", "rbd_ur5_JMg_f64_B262144": "rbd_JMg_B262144:"}
+                          .get(key, "(no capture)"))
             extra[key] = {"states_per_s": Bx / dt, "us_per_launch": dt * 1e6, "bytes_per_state": nbytes,
                           "achieved_gbs": Bx * nbytes / dt / 1e9, "frac_hbm": Bx * nbytes / dt / 1e9 / hbm_peak, "B": Bx,
                           "ring_mb_in_and_out": ring_b / 1e6, "dram_mb_per_launch_ncu": f.get("dram_mb_per_launch"),
@@ -642,7 +644,7 @@ def run_ours(args):
             s3.append(tuple(torch.as_tensor(a, device=dev) for a in (q, dq, tg)))
         u3 = torch.empty((B3, 6), dtype=torch.float32, device=dev)
         dt = time_kernel(lambda s: c3.generate_into(s[0], s[1], s[2], u3), 100, torch, s3)
-        f = ncu_facts("osc:osc_kernel<float, 6, 0, 6")
+        f = ncu_facts("osc_cfg3:")
         extra["osc_jaco2_cfg3_f32_B262144"] = {"evals_per_s": B3 / dt, "us_per_launch": dt * 1e6, "bytes_per_state": 96,
                                                "achieved_gbs": B3 * 96 / dt / 1e9, "frac_hbm": B3 * 96 / dt / 1e9 / hbm_peak,
                                                "fp_pipe_frac_ncu": f.get("fp_pipe_frac")}
@@ -654,13 +656,19 @@ def run_ours(args):
         s5 = [tuple(t_[:B5].contiguous() for t_ in s) for s in s3[:8]]
         u5 = torch.empty((B5, 6), dtype=torch.float32, device=dev)
         dt = time_kernel(lambda s: c5.generate_into(s[0], s[1], s[2], u5), 50, torch, s5)
-        extra["osc_jaco2_cfg5_avoid_f32_B131072"] = {"evals_per_s": B5 / dt, "us_per_launch": dt * 1e6, "bytes_per_state": 96}
+        f = ncu_facts("osc_cfg5:")
+        extra["osc_jaco2_cfg5_avoid_f32_B131072"] = {"evals_per_s": B5 / dt, "us_per_launch": dt * 1e6, "bytes_per_state": 96,
+                                                     "dram_mb_per_launch_ncu": f.get("dram_mb_per_launch"),
+                                                     "fp_pipe_frac_ncu": f.get("fp_pipe_frac")}
         extra["rollout_ur5_cfg4_f64_4096x128"] = multi["config4_ur5_rollout_f64"]
         ctrl32 = OSC(ur5.Config(), **OSC_KW)
         s32 = [tuple(t_.float() for t_ in s) for s in sets[:24]]
         u32b = torch.empty((B, 6), dtype=torch.float32, device=dev)
         dt = time_kernel(lambda s: ctrl32.generate_into(s[0], s[1], s[2], u32b), 200, torch, s32)
-        extra["osc_ur5_6dof_f32_B65536"] = {"evals_per_s": B / dt, "us_per_launch": dt * 1e6, "bytes_per_state": 96}
+        f = ncu_facts("osc_ur5_f32:")
+        extra["osc_ur5_6dof_f32_B65536"] = {"evals_per_s": B / dt, "us_per_launch": dt * 1e6, "bytes_per_state": 96,
+                                            "dram_mb_per_launch_ncu": f.get("dram_mb_per_launch"),
+                                            "fp_pipe_frac_ncu": f.get("fp_pipe_frac")}
 
     cpu = None
     if world == 1 and not quick:

@@ -56,7 +56,8 @@ def record_traffic(traffic, name, tag, json_path):
                 "dram_mb_per_launch": round(_mb(d["dram__bytes_read.sum"]) + _mb(d["dram__bytes_write.sum"]), 3),
                 "fp_pipe_frac": round(float(pipe[0].replace(",", "")) / 100.0, 4) if pipe else None,
                 "fp_pipe": "fp64" if is64 else "fma (fp32)",
-                "ncu_us": float(d["gpu__time_duration.sum"][0]), "tag": tag}
+                "ncu_us": round(float(d["gpu__time_duration.sum"][0].replace(",", "")) *
+                                {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}[d["gpu__time_duration.sum"][1]], 3), "tag": tag}
 
 
 def main():
