@@ -5,9 +5,10 @@
 // (/root/reference/abr_control/controllers/osc.py:138-145).  With one state per thread those lanes used to walk a
 // ~20 us serial eigen-route while the other 30 lanes of their warp idled (47 % of the headline kernel's time).
 // Here the whole warp takes that route TOGETHER: the lanes that need it are found with a ballot, and each group of
-// 8 lanes works on one such state — lane r of the group owns row r of A = (L^-1 J^T)^T and of the accumulated
-// rotations, the disjoint row pairs of one round of a one-sided Jacobi SVD (abrb_math.cuh, jacobi_pair) exchange
-// their rows with shuffles, so a round is one parallel step and four states are decomposed per pass.  The loops are
+// six (eight for 7-joint arms) lanes works on one such state — lane r of the group owns row r of A = (L^-1 J^T)^T and
+// the r-th entries of the rotated right-hand sides, the disjoint row pairs of one round of a one-sided Jacobi SVD
+// (abrb_math.cuh, jacobi_pair) exchange their rows with shuffles, so a round is one parallel step and five (four)
+// states are decomposed per pass.  The loops are
 // rolled (a few hundred instructions in all), every lane is active, and the owner lanes get Mx y and Mx z back
 // through the warp's exchange area in shared memory.
 #pragma once
@@ -15,7 +16,22 @@
 
 namespace abrb {
 
-constexpr int kCoopGroup = 8;  // lanes per state (6 or 3 row owners + idle lanes: shuffles stay inside an 8-lane group)
+// Lanes per state: one lane per row of A (KD <= 6 of them) and, in the deferred variant, per row of du = -L w (N of them).
+// Six-lane groups put FIVE states on a warp (lanes 30, 31 spare), eight-lane groups four: a CTA of four warps then
+// empties up to 20 queued records in one pass instead of 16, which is what keeps a two-tile CTA of the 65 536-state UR5
+// batch (9.6 records on average) out of the two-records-per-group pass that used to be the kernel's tail.
+template <int N, int KD>
+struct CoopGroup {
+  static constexpr int kW = KD > N ? KD : N;
+  static constexpr int kLanes = kW <= 6 ? 6 : 8;
+  static constexpr int kPerWarp = 32 / kLanes;
+  // lane -> (group, row in the group, first lane of the group); the spare lanes act as extra non-owners of the last group
+  static __device__ __forceinline__ int group(int lane) { return lane / kLanes < kPerWarp ? lane / kLanes : kPerWarp; }
+  static __device__ __forceinline__ int sub(int lane) { return lane / kLanes < kPerWarp ? lane % kLanes : kLanes; }
+  static __device__ __forceinline__ int base(int lane) {
+    return (lane / kLanes < kPerWarp ? lane / kLanes : kPerWarp - 1) * kLanes;
+  }
+};
 
 // Exchange area of one warp (shared memory, slot-major like the kinematic scratch: value i of lane l at [i * 32 + l]):
 //   [0, W)         in: y (KD values)   out: A^T Mx y (N values)        W = max(KD, N)
@@ -29,7 +45,7 @@ struct CoopLayout {
 };
 
 // One-sided Jacobi SVD of NS independent KD x N matrices (NS = 1 or 2, interleaved) whose row `sub` and right-hand-side
-// entries y[sub], z[sub] this lane loaded into `me[s]` (lanes sub >= KD of the 8-lane group hold zeros), followed by
+// entries y[sub], z[sub] this lane loaded into `me[s]` (lanes sub >= KD of the group, and the spare lanes, hold zeros), followed by
 // w = A^T pinv(A A^T, rcond) y for the two right-hand sides: on return EVERY lane of the group holds wy[s][] (and
 // wz[s][] if `two`).  All 32 lanes of the warp must call it together.
 template <int N, int KD, int NS>
@@ -43,13 +59,14 @@ __device__ __forceinline__ void coop_jacobi_group(JacobiRow<N, KD> (&me)[NS], in
     bool big = false;
 #pragma unroll 1
     for (int r = 0; r < NRR - 1; ++r) {
-      const int p = sub < NRR ? rr_partner(NRR, sub, r) : sub;
+      const int p = sub < NRR ? rr_partner(NRR, sub, r) : 0;
+      const int src = gbase + p;  // (lanes that own no row read some lane of their group; the value is not used)
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
 #pragma unroll
-        for (int k = 0; k < N; ++k) other[s].b[k] = __shfl_sync(kFull, me[s].b[k], gbase + p);
-        other[s].t[0] = __shfl_sync(kFull, me[s].t[0], gbase + p);
-        other[s].t[1] = __shfl_sync(kFull, me[s].t[1], gbase + p);
+        for (int k = 0; k < N; ++k) other[s].b[k] = __shfl_sync(kFull, me[s].b[k], src);
+        other[s].t[0] = __shfl_sync(kFull, me[s].t[0], src);
+        other[s].t[1] = __shfl_sync(kFull, me[s].t[1], src);
       }
       if (sub < NRR) {
 #pragma unroll
@@ -64,10 +81,10 @@ __device__ __forceinline__ void coop_jacobi_group(JacobiRow<N, KD> (&me)[NS], in
     double s2 = 0.0;
 #pragma unroll
     for (int k = 0; k < N; ++k) s2 += me[s].b[k] * me[s].b[k];
-    double smax = s2;
+    double smax = 0.0;  // (the row lanes of the group are gbase .. gbase + KD - 1, whatever the group width)
 #pragma unroll
-    for (int d = 1; d < kCoopGroup; d <<= 1) {
-      const double t = __shfl_xor_sync(kFull, smax, d);
+    for (int r = 0; r < KD; ++r) {
+      const double t = __shfl_sync(kFull, s2, gbase + r);
       smax = t > smax ? t : smax;
     }
     const bool keep = owner[s] && s2 > rcond * smax;
@@ -75,27 +92,29 @@ __device__ __forceinline__ void coop_jacobi_group(JacobiRow<N, KD> (&me)[NS], in
     const double cy = me[s].t[0] * is2, cz = me[s].t[1] * is2;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      double a = cy * me[s].b[k], c = cz * me[s].b[k];
+      const double a = cy * me[s].b[k], c = cz * me[s].b[k];
+      double sa = 0.0, sc = 0.0;
 #pragma unroll
-      for (int d = 1; d < kCoopGroup; d <<= 1) {
-        a += __shfl_xor_sync(kFull, a, d);
-        if (two) c += __shfl_xor_sync(kFull, c, d);
+      for (int r = 0; r < KD; ++r) {
+        sa += __shfl_sync(kFull, a, gbase + r);
+        if (two) sc += __shfl_sync(kFull, c, gbase + r);
       }
-      wy[s][k] = a;
-      wz[s][k] = c;
+      wy[s][k] = sa;
+      wz[s][k] = sc;
     }
   }
 }
 
 // Decompose the states of the lanes in `mask` (warp-uniform, non-zero) IN LINE: group g of the warp takes the g-th
-// waiting lane, four states per pass.  `ASlot`: where row r, column k of A of lane o is found:
+// waiting lane, four or five states per pass.  `ASlot`: where row r, column k of A of lane o is found:
 // abase[ASlot::at(r, k) * 32 + o].  y, z are read from xyz[(LY::kY / kZ + r) * 32 + o], and A^T Mx y, A^T Mx z written
 // over them.  Not inlined: the hot path only pays a call, and the routine's registers are its own.
 template <typename T, int N, int KD, class ASlot, class LY>
 __device__ __noinline__ void coop_pinv_warp(unsigned mask, const T *abase, T *xyz, int lane, double rcond, bool two) {
-  const int sub = lane & (kCoopGroup - 1), grp = lane / kCoopGroup, gbase = lane & ~(kCoopGroup - 1);
+  typedef CoopGroup<N, KD> G;
+  const int sub = G::sub(lane), grp = G::group(lane), gbase = G::base(lane);
   while (mask != 0u) {
-    const unsigned found = __fns(mask, 0u, grp + 1);  // the (grp+1)-th waiting lane, if any
+    const unsigned found = grp < G::kPerWarp ? __fns(mask, 0u, grp + 1) : 0xffffffffu;  // the (grp+1)-th waiting lane, if any
     const bool have = found != 0xffffffffu;
     const int o = have ? (int)found : 0;
     JacobiRow<N, KD> me[1];
@@ -115,9 +134,9 @@ __device__ __noinline__ void coop_pinv_warp(unsigned mask, const T *abase, T *xy
         if (two) xyz[(LY::kZ + k) * 32 + o] = T(wz[0][k]);
       }
     }
-    // drop the (up to) four states of this pass
+    // drop the (up to) four or five states of this pass
 #pragma unroll
-    for (int i = 0; i < 32 / kCoopGroup; ++i) mask &= mask - 1u;
+    for (int i = 0; i < G::kPerWarp; ++i) mask &= mask - 1u;
   }
 }
 
@@ -125,7 +144,7 @@ __device__ __noinline__ void coop_pinv_warp(unsigned mask, const T *abase, T *xy
 // and a CTA cannot retire before its slowest warp: paying a pass per warp per tile (70 % of the warps of a UR5 batch)
 // doubles the kernel.  Instead a waiting lane finishes its evaluation WITHOUT the task-space term and leaves a record
 // (A, the Cholesky factor of M, y, z, its row) in a small queue of the CTA; the CTA empties the queue with all its
-// 16 groups at once — after its last tile, or earlier when 16 records have gathered — and adds the missing
+// groups (20 or 16) at once — after its last tile, or earlier when as many records have gathered — and adds the missing
 //   du = -J^T Mx y - J^T Mx J M^-1 u_null = -L A^T (Mx y + Mx z)
 // to the rows already written.  Records that do not fit are handled in line as above.
 template <int N, int KD>
@@ -148,7 +167,9 @@ __device__ __forceinline__ void coop_flush_round(const T *qrec, const long long 
                                                  const FlushOut<T> &o, double rcond, bool two) {
   typedef CoopRecord<N, KD> RC;
   const int lane = threadIdx.x & 31;
-  const int sub = lane & (kCoopGroup - 1), gbase = lane & ~(kCoopGroup - 1);
+  typedef CoopGroup<N, KD> G;
+  const int sub = G::sub(lane), gbase = G::base(lane);
+  const bool spare = G::group(lane) >= G::kPerWarp;
   JacobiRow<N, KD> me[NS];
   bool have[NS], owner[NS];
   const T *rec[NS];
@@ -157,7 +178,7 @@ __device__ __forceinline__ void coop_flush_round(const T *qrec, const long long 
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     const int e = first + s * stride;
-    have[s] = e < n;
+    have[s] = e < n && !spare;
     owner[s] = have[s] && sub < KD;
     rec[s] = qrec + (size_t)(have[s] ? e : 0) * RC::kLen;
 #pragma unroll
@@ -196,8 +217,8 @@ template <typename T, int N, int KD>
 __device__ __noinline__ void coop_flush_cta(const T *qrec, const long long *qrow, int n, const FlushOut<T> &o, double rcond,
                                             bool two) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  constexpr int kPerWarp = 32 / kCoopGroup;
-  const int groups = n_warps * kPerWarp, mine = warp * kPerWarp + lane / kCoopGroup;
+  constexpr int kPerWarp = CoopGroup<N, KD>::kPerWarp;
+  const int groups = n_warps * kPerWarp, mine = warp * kPerWarp + CoopGroup<N, KD>::group(lane);
   if (n <= groups) {
     if (warp * kPerWarp < n) coop_flush_round<T, N, KD, 1>(qrec, qrow, n, mine, groups, o, rcond, two);  // warp-uniform
   } else {

@@ -93,6 +93,8 @@ struct Workspace {
     cudaStream_t lanes[kLanes] = {nullptr, nullptr};  // chunk pipeline inside one call
     cudaStream_t side[kLanes] = {nullptr, nullptr};   // second copy stream of each lane (dq goes up beside q)
     cudaEvent_t side_done[kLanes] = {nullptr, nullptr};
+    cudaStream_t side2[kLanes] = {nullptr, nullptr};  // third copy stream of each lane (per-state targets)
+    cudaEvent_t side2_done[kLanes] = {nullptr, nullptr};
     int used = 0;                                      // lanes with work in flight
   } slots[kSlots];
   void release() {
@@ -108,6 +110,8 @@ struct Workspace {
         if (sl.lanes[l]) cudaStreamDestroy(sl.lanes[l]);
         if (sl.side[l]) cudaStreamDestroy(sl.side[l]);
         if (sl.side_done[l]) cudaEventDestroy(sl.side_done[l]);
+        if (sl.side2[l]) cudaStreamDestroy(sl.side2[l]);
+        if (sl.side2_done[l]) cudaEventDestroy(sl.side2_done[l]);
       }
       sl = Slot();
     }
@@ -134,6 +138,8 @@ struct Workspace {
           e = cudaStreamCreateWithFlags(&sl.lanes[l], cudaStreamNonBlocking);
           if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sl.side[l], cudaStreamNonBlocking);
           if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.side_done[l], cudaEventDisableTiming);
+          if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sl.side2[l], cudaStreamNonBlocking);
+          if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.side2_done[l], cudaEventDisableTiming);
           if (e != cudaSuccess) return (int)e;
         }
     }
@@ -169,6 +175,8 @@ struct Workspace {
     cudaError_t first = cudaSuccess;
     for (int l = 0; l < sl.used; ++l) {
       cudaError_t e = cudaStreamSynchronize(sl.side[l]);
+      if (e != cudaSuccess && first == cudaSuccess) first = e;
+      e = cudaStreamSynchronize(sl.side2[l]);
       if (e != cudaSuccess && first == cudaSuccess) first = e;
       e = cudaStreamSynchronize(sl.lanes[l]);
       if (e != cudaSuccess && first == cudaSuccess) first = e;
@@ -517,18 +525,23 @@ static int osc_generate_host_async(const abrb_osc *c, int frame_id, const double
     const size_t off_s = (size_t)b0 * row, off_t = (size_t)b0 * 6 * es;
     auto at = [](const void *p, size_t o) { return (const void *)((const char *)p + o); };
     auto atw = [](void *p, size_t o) { return (void *)((char *)p + o); };
-    // q and dq go up on two streams at once (one host->device stream alone reaches about half of what the link gives:
-    // 23 vs 40 GB/s measured on the B200 box); the lane's stream waits for the side copy before the kernel
+    // q, dq and the per-state targets go up on three streams at once (one host->device stream alone reaches less than
+    // half of what the link gives: 18-23 vs 40+ GB/s measured on the B200 boxes); the lane's stream waits for the side
+    // copies before the kernel
     ABRB_CUH(cudaMemcpyAsync(atw(d_dq, off_s), at(dq, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, sl.side[lane]), where);
     ABRB_CUH(cudaEventRecord(sl.side_done[lane], sl.side[lane]), where);
+    if (target_stride) {
+      ABRB_CUH(cudaMemcpyAsync(atw(d_t, off_t), at(target, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice,
+                               sl.side2[lane]), where);
+      ABRB_CUH(cudaEventRecord(sl.side2_done[lane], sl.side2[lane]), where);
+    }
     ABRB_CUH(cudaMemcpyAsync(atw(d_q, off_s), at(q, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, s), where);
-    if (target_stride)
-      ABRB_CUH(cudaMemcpyAsync(atw(d_t, off_t), at(target, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s), where);
     if (tv && tv_stride)
       ABRB_CUH(cudaMemcpyAsync(atw(d_tv, off_t), at(tv, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s), where);
     if (ierr)
       ABRB_CUH(cudaMemcpyAsync(atw(d_ie, off_t), at(ierr, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s), where);
     ABRB_CUH(cudaStreamWaitEvent(s, sl.side_done[lane], 0), where);
+    if (target_stride) ABRB_CUH(cudaStreamWaitEvent(s, sl.side2_done[lane], 0), where);
     rc = osc_generate(c, frame_id, x_off, at(d_q, off_s), at(d_dq, off_s), target_stride ? at(d_t, off_t) : d_t,
                       target_stride, tv ? (tv_stride ? at(d_tv, off_t) : d_tv) : nullptr, tv_stride, atw(d_u, off_s),
                       train ? atw(d_tr, off_s) : nullptr, ierr ? atw(d_ie, off_t) : nullptr, nb, s, f32);

@@ -7,6 +7,7 @@
 // fully coalesced 16-byte stores, so HBM sees whole 128-byte lines only.
 #include <cuda_runtime.h>
 #include <cstdlib>
+#include <utility>
 
 #include <atomic>
 
@@ -144,6 +145,14 @@ struct WarpSmem {
 template <typename T, int N, bool ORTHO, int KD, bool KSMEM>
 struct OscSmem : WarpSmem<T, N, ORTHO, KSMEM, (N > 6 ? N : 6), CoopLayout<N, KD, !KSMEM>::kSlots> {};
 
+// Programmatic dependent launch (see launch_pdl): let the stream's next kernel be scheduled as CTAs of this one retire,
+// and wait until the previous kernel of the stream has completed and its memory is visible.  Both are no-ops for a
+// launch without the attribute.
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 template <typename T, int N, bool ORTHO, bool DYN, bool CMAT, bool XTRA, bool KSMEM>
 __global__ void __launch_bounds__(kBlock, MinBlocks<T>::value)
 rbd_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ RbdArgs<T> a) {
@@ -167,6 +176,7 @@ rbd_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ RbdAr
   sink.ptr[kOutC] = a.C;
   sink.tile = region + WS::kKin;
   sink.lane = lane;
+  pdl_entry();
   for (int64_t base = (int64_t)blockIdx.x * kBlock; base < a.B; base += (int64_t)gridDim.x * kBlock) {
     // no early exit: every thread of the CTA takes part in the phase barriers; idle lanes / warps redo a valid state
     const int64_t warp_b0 = base + warp * 32;
@@ -241,17 +251,29 @@ struct OscBlock {
   static constexpr int value = (ORTHO && sizeof(T) == 8) ? ABRB_OSC_BLOCK_ORTHO64 : ABRB_OSC_BLOCK;
 };
 
+// Resident CTAs per SM the OSC kernel is compiled for.  fp64: 2 (255 registers).  fp32 with orthonormal frames (UR5: the
+// signed-permutation constants fold away): 4 (128 registers) measured best; fp32 with general frames (Jaco2) spills
+// ~3 KB per thread at 128 registers — 2 CTAs at 255 registers run config 3 in 71.7 instead of 83.2 us and config 5 in
+// 173 instead of 189 us (profiles/r02_experiments.md).
+#ifndef ABRB_MINBLOCKS_OSC_F32_GENERAL
+#define ABRB_MINBLOCKS_OSC_F32_GENERAL 2
+#endif
+template <typename T, bool ORTHO>
+struct MinBlocksOsc {
+  static constexpr int value = sizeof(T) == 8 ? MinBlocks<T>::value : (ORTHO ? MinBlocks<T>::value : ABRB_MINBLOCKS_OSC_F32_GENERAL);
+};
+
 template <typename T, int N, bool ORTHO, int KD, bool KSMEM>
 __global__ void __launch_bounds__(OscBlock<T, ORTHO>::value,
-                                  (MinBlocks<T>::value * kBlock / OscBlock<T, ORTHO>::value > 0
-                                       ? MinBlocks<T>::value * kBlock / OscBlock<T, ORTHO>::value : 1))
+                                  (MinBlocksOsc<T, ORTHO>::value * kBlock / OscBlock<T, ORTHO>::value > 0
+                                       ? MinBlocksOsc<T, ORTHO>::value * kBlock / OscBlock<T, ORTHO>::value : 1))
 osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<T, N> O,
            const __grid_constant__ OscArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef KinSel<T, N, ORTHO, KSMEM> KS;
   typedef OscSmem<T, N, ORTHO, KD, KSMEM> WS;
   constexpr int kOscBlock = OscBlock<T, ORTHO>::value, kOscWarps = kOscBlock / 32;
-  constexpr int kOscFlushAt = kOscWarps * (32 / kCoopGroup);  // one full round of the CTA's groups
+  constexpr int kOscFlushAt = kOscWarps * CoopGroup<N, KD>::kPerWarp;  // one full round of the CTA's groups
   constexpr int kCoopQueue = kCoopQueuePerWarp * kOscWarps;
   typedef OscQueue<T, N, KD, kCoopQueue> Q;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -290,8 +312,7 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
   // follows another kernel in its stream is allowed onto the SMs while that kernel's last CTAs are still running (its
   // launch latency, parameter upload and CTA ramp-up overlap their tail) and waits HERE, before its first global access,
   // until that kernel has completed and its memory is visible.  Without the launch attribute both are no-ops.
-  asm volatile("griddepcontrol.launch_dependents;");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  pdl_entry();
   // Tiles: the first one is the CTA's own index; the following ones come from the launch's tile counter, so that a CTA
   // whose tiles happen to be expensive (obstacle-active states, many pseudo-inverse states) simply takes fewer of them.
   const long long n_tiles = (a.B + kOscBlock - 1) / kOscBlock;
@@ -332,7 +353,7 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
     // fused all-gather: this tile's rows go to every rank's gathered array while the other warps still compute
     for (int p = 0; p < a.g.n_peer; ++p)
       store_records<T, N>(static_cast<T *>(a.g.peer_u[p]), a.g.row0 + warp_b0, nvalid, u, stage, lane);
-    // deferred states: emptied once a full round of the CTA's 16 groups has gathered, and after the last tile
+    // deferred states: emptied once a full round of the CTA's groups has gathered, and after the last tile
 #ifdef ABRB_DBG_TIMING
     const long long dbg_w0 = clock64();
 #endif
@@ -627,6 +648,26 @@ inline bool pdl_enabled() {
   return on == 1;
 }
 
+// kernel<<<grid, block, smem, stream>>>(args...) with programmatic stream serialization allowed: the launch may be
+// brought onto the SMs while the stream's previous kernel drains; the kernels launched through it (osc_kernel,
+// rbd_kernel) call pdl_entry() before their first global-memory access, which holds them until that kernel has
+// completed and flushed.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
+                              Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 inline int num_sms() {
   static int sm_count = 0;
   if (sm_count == 0) {
@@ -676,9 +717,9 @@ int rbd_go(const ChainHost &h, const RbdCall &c, unsigned want) {
   auto kern = rbd_kernel<T, N, ORTHO, DYN, CMAT, XTRA, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
   if (e != cudaSuccess) return (int)e;
-  kern<<<grid_for(c.B, 8), kBlock, smem, c.stream>>>(P, a);
+  e = launch_pdl(kern, grid_for(c.B, 8), kBlock, smem, c.stream, P, a);
   count_launch();
-  return (int)cudaGetLastError();
+  return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }
 
 template <typename T, int N>
@@ -747,17 +788,7 @@ int osc_go(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
     resident_dev = dev;
   }
   const int64_t tiles = (c.B + kOscBlock - 1) / kOscBlock, cap = (int64_t)num_sms() * resident;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(tiles < cap ? tiles : cap));
-  cfg.blockDim = dim3(kOscBlock);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = c.stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  e = cudaLaunchKernelEx(&cfg, kern, P, O, a);
+  e = launch_pdl(kern, (unsigned)(tiles < cap ? tiles : cap), kOscBlock, smem, c.stream, P, O, a);
   count_launch();
   return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }
