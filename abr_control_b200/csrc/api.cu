@@ -25,6 +25,8 @@ struct abrb_osc {
   const abrb_model *model;
   abrb_osc_params params;
   int64_t host_chunk = 0;  // option "host_chunk_states": states per pipeline chunk of the *_host entry points, 0 = auto
+  int host_streams = 2;    // option "host_upload_streams": copy streams per chunk (1: q, dq, target in turn; 2: dq beside
+                           // q; 3: per-state targets on a stream of their own as well)
 };
 
 // Symmetric gather buffers of one rank (include/abrb.h): one cudaMalloc'd region [ n_buffers x bytes | flags | counter ]
@@ -392,6 +394,10 @@ int abrb_osc_create(const abrb_model *m, const abrb_osc_params *p, abrb_osc **ou
   c->model = m;
   c->params = *p;
   if (const char *v = std::getenv("ABRB_HOST_CHUNK")) c->host_chunk = (int64_t)std::atoll(v);
+  if (const char *v = std::getenv("ABRB_HOST_STREAMS")) {
+    const int k = std::atoi(v);
+    if (k >= 1 && k <= 3) c->host_streams = k;
+  }
   *out = c;
   return ABRB_OK;
 }
@@ -400,6 +406,11 @@ int abrb_osc_set_option(abrb_osc *c, const char *name, double value) {
   if (!c || !name) return fail(ABRB_EINVAL, "abrb_osc_set_option: NULL argument");
   if (std::strcmp(name, "host_chunk_states") == 0) {
     c->host_chunk = value > 0 ? (int64_t)value : 0;
+    return ABRB_OK;
+  }
+  if (std::strcmp(name, "host_upload_streams") == 0) {
+    if (!(value >= 1 && value <= 3)) return fail(ABRB_EINVAL, "abrb_osc_set_option: host_upload_streams must be 1, 2 or 3");
+    c->host_streams = (int)value;
     return ABRB_OK;
   }
   return fail(ABRB_EINVAL, std::string("abrb_osc_set_option: unknown option ") + name);
@@ -462,7 +473,7 @@ int abrb_osc_generate_f32(const abrb_osc *c, int frame_id, const double *x_off, 
 // overheads, so two chunks up to ~200 k states and four above.
 static int osc_generate_host_async(const abrb_osc *c, int frame_id, const double *x_off, const void *q, const void *dq,
                                    const void *target, int target_stride, const void *tv, int tv_stride, void *u,
-                                   void *train, void *ierr, int64_t B, int slot, bool f32) {
+                                   void *train, void *ierr, int64_t B, int slot, bool f32, bool blocking) {
   if (!c) return fail(ABRB_EINVAL, "abrb_osc_generate_host: NULL controller");
   if (B < 0) return fail(ABRB_EINVAL, "abrb_osc_generate_host: B < 0");
   if (slot < 0 || slot >= kSlots) return fail(ABRB_EINVAL, "abrb_osc_generate_host: slot must be 0 or 1");
@@ -488,7 +499,12 @@ static int osc_generate_host_async(const abrb_osc *c, int frame_id, const double
   void *d_q = take(sz_state), *d_dq = take(sz_state), *d_u = take(sz_state), *d_tr = take(sz_state);
   void *d_t = take(sz_t), *d_tv = tv ? take(sz_tv) : nullptr, *d_ie = ierr ? take(sz_six) : nullptr;
   const size_t row = n * es;
-  int64_t chunk = B < 49152 ? B : ((B + (B <= 196608 ? 1 : 3)) / (B <= 196608 ? 2 : 4) + 127) / 128 * 128;
+  // Chunking inside one call pays when the caller then waits for the result (upload of chunk 1 under the kernel of chunk
+  // 0): +6 % measured at 65 536 states.  A caller of the asynchronous entry points overlaps whole CALLS on the two slots,
+  // and there the extra copies and launches of a chunked call only cost (287 vs 312 M evals/s, tools/dbg/e2e_ab.py): one
+  // chunk up to 196 608 states.
+  int64_t chunk = (B < 49152 || (!blocking && B <= 196608))
+                      ? B : ((B + (B <= 196608 ? 1 : 3)) / (B <= 196608 ? 2 : 4) + 127) / 128 * 128;
   if (c->host_chunk > 0) chunk = (c->host_chunk < B ? c->host_chunk : B + 127) / 128 * 128;
   if (chunk <= 0) chunk = B;
   const int n_chunks = (int)((B + chunk - 1) / chunk);
@@ -525,23 +541,24 @@ static int osc_generate_host_async(const abrb_osc *c, int frame_id, const double
     const size_t off_s = (size_t)b0 * row, off_t = (size_t)b0 * 6 * es;
     auto at = [](const void *p, size_t o) { return (const void *)((const char *)p + o); };
     auto atw = [](void *p, size_t o) { return (void *)((char *)p + o); };
-    // q, dq and the per-state targets go up on three streams at once (one host->device stream alone reaches less than
-    // half of what the link gives: 18-23 vs 40+ GB/s measured on the B200 boxes); the lane's stream waits for the side
-    // copies before the kernel
-    ABRB_CUH(cudaMemcpyAsync(atw(d_dq, off_s), at(dq, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, sl.side[lane]), where);
-    ABRB_CUH(cudaEventRecord(sl.side_done[lane], sl.side[lane]), where);
+    // q, dq and the per-state targets go up on up to three streams at once (on some B200 hosts one host->device stream
+    // alone reaches less than half of what the link gives: 18-23 vs 40+ GB/s; on others 54 GB/s); the lane's stream waits
+    // for the side copies before the kernel.  c->host_streams: 1, 2 (default) or 3.
+    cudaStream_t s_dq = c->host_streams >= 2 ? sl.side[lane] : s;
+    cudaStream_t s_t = c->host_streams >= 3 ? sl.side2[lane] : s;
+    ABRB_CUH(cudaMemcpyAsync(atw(d_dq, off_s), at(dq, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, s_dq), where);
+    if (s_dq != s) ABRB_CUH(cudaEventRecord(sl.side_done[lane], s_dq), where);
     if (target_stride) {
-      ABRB_CUH(cudaMemcpyAsync(atw(d_t, off_t), at(target, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice,
-                               sl.side2[lane]), where);
-      ABRB_CUH(cudaEventRecord(sl.side2_done[lane], sl.side2[lane]), where);
+      ABRB_CUH(cudaMemcpyAsync(atw(d_t, off_t), at(target, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s_t), where);
+      if (s_t != s) ABRB_CUH(cudaEventRecord(sl.side2_done[lane], s_t), where);
     }
     ABRB_CUH(cudaMemcpyAsync(atw(d_q, off_s), at(q, off_s), (size_t)nb * row, cudaMemcpyHostToDevice, s), where);
     if (tv && tv_stride)
       ABRB_CUH(cudaMemcpyAsync(atw(d_tv, off_t), at(tv, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s), where);
     if (ierr)
       ABRB_CUH(cudaMemcpyAsync(atw(d_ie, off_t), at(ierr, off_t), (size_t)nb * 6 * es, cudaMemcpyHostToDevice, s), where);
-    ABRB_CUH(cudaStreamWaitEvent(s, sl.side_done[lane], 0), where);
-    if (target_stride) ABRB_CUH(cudaStreamWaitEvent(s, sl.side2_done[lane], 0), where);
+    if (s_dq != s) ABRB_CUH(cudaStreamWaitEvent(s, sl.side_done[lane], 0), where);
+    if (target_stride && s_t != s) ABRB_CUH(cudaStreamWaitEvent(s, sl.side2_done[lane], 0), where);
     rc = osc_generate(c, frame_id, x_off, at(d_q, off_s), at(d_dq, off_s), target_stride ? at(d_t, off_t) : d_t,
                       target_stride, tv ? (tv_stride ? at(d_tv, off_t) : d_tv) : nullptr, tv_stride, atw(d_u, off_s),
                       train ? atw(d_tr, off_s) : nullptr, ierr ? atw(d_ie, off_t) : nullptr, nb, s, f32);
@@ -576,28 +593,28 @@ int abrb_osc_generate_host_async_f64(const abrb_osc *c, int frame_id, const doub
                                      const double *target_velocity, int tv_stride, double *u, double *training_signal,
                                      double *integrated_error, int64_t B, int slot) {
   return osc_generate_host_async(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride, u,
-                                 training_signal, integrated_error, B, slot, false);
+                                 training_signal, integrated_error, B, slot, false, false);
 }
 int abrb_osc_generate_host_async_f32(const abrb_osc *c, int frame_id, const double *x_off, const float *q,
                                      const float *dq, const float *target, int target_stride,
                                      const float *target_velocity, int tv_stride, float *u, float *training_signal,
                                      float *integrated_error, int64_t B, int slot) {
   return osc_generate_host_async(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride, u,
-                                 training_signal, integrated_error, B, slot, true);
+                                 training_signal, integrated_error, B, slot, true, false);
 }
 int abrb_osc_generate_host_f64(const abrb_osc *c, int frame_id, const double *x_off, const double *q, const double *dq,
                                const double *target, int target_stride, const double *target_velocity,
                                int tv_stride, double *u, double *training_signal, double *integrated_error,
                                int64_t B) {
   const int rc = osc_generate_host_async(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride,
-                                         u, training_signal, integrated_error, B, 0, false);
+                                         u, training_signal, integrated_error, B, 0, false, true);
   return rc ? rc : abrb_osc_host_wait(c, 0);
 }
 int abrb_osc_generate_host_f32(const abrb_osc *c, int frame_id, const double *x_off, const float *q, const float *dq,
                                const float *target, int target_stride, const float *target_velocity, int tv_stride,
                                float *u, float *training_signal, float *integrated_error, int64_t B) {
   const int rc = osc_generate_host_async(c, frame_id, x_off, q, dq, target, target_stride, target_velocity, tv_stride,
-                                         u, training_signal, integrated_error, B, 0, true);
+                                         u, training_signal, integrated_error, B, 0, true, true);
   return rc ? rc : abrb_osc_host_wait(c, 0);
 }
 

@@ -152,8 +152,14 @@ int abrb_osc_create(const abrb_model *m, const abrb_osc_params *p, abrb_osc **ou
 int abrb_osc_destroy(abrb_osc *c);
 
 /* Execution options of one controller (no effect on results).  Names:
- *   "host_chunk_states"  states per pipeline chunk of the *_host entry points; 0 = automatic (default; the
- *                        environment variable ABRB_HOST_CHUNK sets another default).
+ *   "host_chunk_states"  states per pipeline chunk of the *_host entry points; 0 = automatic (default: the blocking
+ *                        calls split batches of 49 152 states and more into two chunks, four above 196 608; the
+ *                        asynchronous calls, which overlap whole calls on the two slots, keep one chunk up to 196 608
+ *                        states; the environment variable ABRB_HOST_CHUNK sets another default).
+ *   "host_upload_streams" copy streams per chunk of the *_host entry points: 1 (q, dq, target one after the other), 2
+ *                        (default: dq beside q) or 3 (per-state targets on a stream of their own as well); default from
+ *                        ABRB_HOST_STREAMS.  Which is fastest depends on the host: one pinned host->device stream
+ *                        reaches 18 to 54 GB/s on different B200 boxes of the same pool.
  * Returns ABRB_EINVAL for an unknown name.  Not thread safe against concurrent generate calls on the same handle. */
 int abrb_osc_set_option(abrb_osc *c, const char *name, double value);
 
