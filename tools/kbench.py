@@ -73,6 +73,21 @@ for _ in range(3):
 e1.record()
 torch.cuda.synchronize()
 res["rollout4096_us_per_step"] = e0.elapsed_time(e1) * 1e3 / 3 / 128
+if os.environ.get("KB_MORE"):
+    # the same rollouts with the `_Mx` threshold at 0 (no step takes the pseudo-inverse route: the evaluation + plant alone)
+    _abi.osc_params = lambda *a, **k: _orig(*a, **dict(k, mx_threshold=0.0))
+    c4n = OSC(ur5.Config(), kp=10.0)
+    c4n._native()
+    _abi.osc_params = _orig
+    for _ in range(2):
+        c4n.rollout(q4, dq4 * 0.1, tg4, steps=128, dt=1e-3, record=())
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        c4n.rollout(q4, dq4 * 0.1, tg4, steps=128, dt=1e-3, record=())
+    e1.record()
+    torch.cuda.synchronize()
+    res["rollout4096_noslow_us_per_step"] = e0.elapsed_time(e1) * 1e3 / 3 / 128
 print(os.environ.get("ABRB_LIBRARY", "default"), json.dumps({k: round(v, 1) for k, v in res.items()}))
 if os.environ.get("KB_CLOCKS"):
     # SM clock / throttle reasons over a sustained run of the heaviest kernel (is a long FP64 burst power capped?)
