@@ -25,6 +25,7 @@ struct abrb_osc {
   const abrb_model *model;
   abrb_osc_params params;
   int64_t host_chunk = 0;  // option "host_chunk_states": states per pipeline chunk of the *_host entry points, 0 = auto
+  int gather_bulk = 1;     // option "gather_bulk_copies": the fused all-gather sends tiles as bulk copies (1) or stores (0)
   int host_streams = 2;    // option "host_upload_streams": copy streams per chunk (1: q, dq, target in turn; 2: dq beside
                            // q; 3: per-state targets on a stream of their own as well)
 };
@@ -236,6 +237,10 @@ int *sched_slot() {
 // published `epoch` in our flag array, i.e. all its rows of this launch have landed in our buffer.
 __global__ void gather_wait_kernel(const unsigned long long *flags, int world, unsigned long long epoch, int *status) {
   const int r = threadIdx.x;
+  // launched as a programmatic dependent of the stream's previous kernel (the OSC kernel that feeds the gather): the
+  // thread block is already resident when that kernel completes instead of paying a launch after it
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (r < world) {
     const long long t0 = clock64();
     for (;;) {
@@ -406,6 +411,10 @@ int abrb_osc_set_option(abrb_osc *c, const char *name, double value) {
   if (!c || !name) return fail(ABRB_EINVAL, "abrb_osc_set_option: NULL argument");
   if (std::strcmp(name, "host_chunk_states") == 0) {
     c->host_chunk = value > 0 ? (int64_t)value : 0;
+    return ABRB_OK;
+  }
+  if (std::strcmp(name, "gather_bulk_copies") == 0) {
+    c->gather_bulk = value != 0.0 ? 1 : 0;
     return ABRB_OK;
   }
   if (std::strcmp(name, "host_upload_streams") == 0) {
@@ -694,11 +703,21 @@ int abrb_gather_destroy(abrb_gather *g) {
 int abrb_gather_wait(abrb_gather *g, void *stream) {
   if (!g) return fail(ABRB_EINVAL, "abrb_gather_wait: NULL argument");
   char *mine = static_cast<char *>(g->peer[g->rank]);
-  gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long *>(mine + g->flag_off),
-                                                          g->world, g->epoch,
-                                                          reinterpret_cast<int *>(mine + g->counter_off + 64));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(32);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  const char *pdl = std::getenv("ABRB_PDL");
+  cfg.numAttrs = (pdl != nullptr && pdl[0] == '0') ? 0 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gather_wait_kernel,
+                                     (const unsigned long long *)reinterpret_cast<unsigned long long *>(mine + g->flag_off),
+                                     g->world, g->epoch, reinterpret_cast<int *>(mine + g->counter_off + 64));
   count_launch();
-  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaGetLastError();
   return e ? cuda_fail((int)e, "abrb_gather_wait") : ABRB_OK;
 }
 
@@ -726,6 +745,7 @@ static int osc_generate_gather(const abrb_osc *c, int frame_id, const double *x_
   ga.self = g->rank;
   ga.row0 = row0;
   ga.epoch = ++g->epoch;
+  ga.bulk = c->gather_bulk;
   for (int r = 0; r < g->world; ++r) {
     char *base = static_cast<char *>(g->peer[r]);
     ga.peer_u[r] = base + (size_t)buffer_index * g->bytes;

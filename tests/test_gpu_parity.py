@@ -427,6 +427,54 @@ def test_unaligned_row_slices_are_accepted():
     assert torch.equal(M, rc.M(q)[1:])
 
 
+def test_cuda_graph_capture_and_replay():
+    """A launch-bound inner loop captured once and replayed (torch.cuda.CUDAGraph): several OSC and rigid-body launches —
+    issued with programmatic stream serialization, tile counters and deferred-state queues included — must give, on every
+    replay, bit for bit what the same calls give eagerly; inputs are changed between replays through the captured buffers."""
+    import torch
+
+    rc = _cfg("ur5")
+    ctrlr = _build_ctrl(rc, dict(arm="ur5", osc=dict(kp=10, ctrlr_dof=[True] * 6, use_C=True)))
+    xyz = _build_ctrl(rc, dict(arm="ur5", osc=dict(kp=10)))
+    rng = np.random.default_rng(11)
+    Bq = 128 * 37 + 5  # ragged, several tiles per persistent CTA would need > 296 tiles: covered by the full-size tests
+    mk = lambda: tuple(torch.as_tensor(rng.uniform(0, 6, (Bq, 6)), device="cuda") for _ in range(3))  # noqa: E731
+    q, dq, tg = mk()
+    outs = [torch.empty((Bq, 6), dtype=torch.float64, device="cuda") for _ in range(3)]
+    M = torch.empty((Bq, 6, 6), dtype=torch.float64, device="cuda")
+    g = torch.empty((Bq, 6), dtype=torch.float64, device="cuda")
+
+    def work():
+        ctrlr.generate_into(q, dq, tg, outs[0])
+        rc.eval_into(q, dq, dict(M=M, g=g))
+        xyz.generate_into(q, dq, tg, outs[1])
+        ctrlr.generate_into(q, dq * 0.5, tg, outs[2])
+
+    work()  # warm-up outside the capture (workspace, tile-counter pool, function attributes)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(graph, stream=side):
+            work()
+    torch.cuda.synchronize()
+    for rep in range(3):
+        nq, ndq, ntg = mk()
+        q.copy_(nq), dq.copy_(ndq), tg.copy_(ntg)
+        for o in outs:
+            o.zero_()
+        M.zero_(), g.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        got = [o.clone() for o in outs] + [M.clone(), g.clone()]
+        work()
+        torch.cuda.synchronize()
+        for a, b in zip(got, outs + [M, g]):
+            assert torch.equal(a, b), f"replay {rep}"
+        assert float(outs[0].abs().max()) > 0
+
+
 def test_ki_integrator_sequences():
     """ki != 0 (osc.py:81-82, :262-264): per-state integrated task-space error over a 12-call sequence, fp64 and fp32,
     CUDA tensors and host arrays, against oracle controllers stepped the same way (one per state stream); the
