@@ -41,7 +41,8 @@ template <int N, int KD, bool COPY_A>
 struct CoopLayout {
   static constexpr int kW = KD > N ? KD : N;
   static constexpr int kY = 0, kZ = kW, kA = 2 * kW;
-  static constexpr int kSlots = 2 * kW + (COPY_A ? KD * N : 0);
+  static constexpr int kQ = 2 * kW + (COPY_A ? KD * N : 0);  // where this lane's record went (-1: not deferred), see WarpCoop
+  static constexpr int kSlots = kQ + 1;
 };
 
 // One-sided Jacobi SVD of NS independent KD x N matrices (NS = 1 or 2, interleaved) whose row `sub` and right-hand-side
@@ -153,7 +154,10 @@ struct CoopRecord {
   // term (stored by the kernel once the evaluation has returned): the flush writes u + du, it never reads global memory
   static constexpr int kA = 0, kL = KD * N, kY = kL + N * (N + 1) / 2, kZ = kY + KD, kU = kZ + KD, kLen = kU + N;
 };
-constexpr int kCoopQueuePerWarp = 8;  // queue capacity of a CTA: eight records per warp
+// Queue capacity of a CTA: six records per warp (24 for the 128-thread CTAs, against 20 groups).  Not more: with 8 the
+// fp64 kernels' shared memory (2 CTAs x 99.4 KB with the bulk-copy buffer) crosses the SM's 196 KB carve-out step, the L1
+// that serves the register spills shrinks from 60 to 28 KB and every fp64 OSC kernel loses 3 us (53.7 vs 50.4 us).
+constexpr int kCoopQueuePerWarp = 6;
 
 // Bulk asynchronous copy shared -> global (any rank's memory: TMA, cp.async.bulk), tracked by the issuing thread's bulk
 // async-group; the fused all-gather of the OSC kernel sends every finished tile of u to every rank with these.
@@ -279,7 +283,10 @@ struct WarpCoop {
   int *qcount = nullptr;
   long long row = 0;  // this lane's state index
   int qcap = 0;       // queue capacity (records)
-  int qpos = -1;      // where this lane's record went (the kernel adds the row of u to it after the evaluation)
+  // Where this lane's record went is parked in the exchange area, not in a register that would stay live through the
+  // rest of the evaluation: the kernel clears it before the evaluation and reads it back afterwards to add the row of u.
+  __device__ __forceinline__ void clear_qpos() { xch[LY::kQ * 32 + lane] = T(-1); }
+  __device__ __forceinline__ int take_qpos() const { return int(xch[LY::kQ * 32 + lane]); }
 
   template <typename T_, int N_, int KD_, class LGet>
   __device__ __forceinline__ void pinv(bool slow, K_ &K, LGet L, const T *y, const T *z, T *wy, T *wz, bool two,
@@ -294,7 +301,7 @@ struct WarpCoop {
         const int pos = atomicAdd(qcount, 1);
         if (pos < qcap) {
           queued = true;
-          qpos = pos;
+          xch[LY::kQ * 32 + lane] = T(pos);
           T *rec = qrec + (size_t)pos * RC::kLen;
           qrow[pos] = row;
 #pragma unroll

@@ -219,9 +219,12 @@ struct OscQueue {
 // Behind the queue: one row-major (32, N) tile of u per warp, the SOURCE of the bulk copies (TMA, cp.async.bulk) that
 // carry a finished tile into every rank's gathered array (fused all-gather).  Unlike the pitch-33 staging tile it must
 // stay untouched until the copy engine has read it, so it is a buffer of its own (<= 1792 bytes per warp).
+#ifndef ABRB_GATHER_BULK
+#define ABRB_GATHER_BULK 1  // 0: build without the bulk-copy epilogue (A/B builds)
+#endif
 template <typename T, int N>
 struct OscBulk {
-  static constexpr size_t kPerWarp = (size_t)32 * N * sizeof(T);  // a multiple of 16
+  static constexpr size_t kPerWarp = ABRB_GATHER_BULK ? (size_t)32 * N * sizeof(T) : 0;  // a multiple of 16
 };
 
 // One pass over the batch, persistent CTAs (grid = resident CTAs, tiles round-robin).  The states whose task-space
@@ -352,12 +355,13 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
     }
     coop.valid = lane < nvalid;
     coop.row = b;
+    coop.clear_qpos();
     osc_eval<T, N, KD, false>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, a.ierr != nullptr ? ie : nullptr, u, tr,
                               (T *)nullptr, K, coop);
-    if (coop.qpos >= 0) {  // a deferred state: its row of u (without the task-space term) completes the record
+    const int qpos = coop.take_qpos();
+    if (qpos >= 0) {  // a deferred state: its row of u (without the task-space term) completes the record
 #pragma unroll
-      for (int k = 0; k < N; ++k) qrec[(size_t)coop.qpos * CoopRecord<N, KD>::kLen + CoopRecord<N, KD>::kU + k] = u[k];
-      coop.qpos = -1;
+      for (int k = 0; k < N; ++k) qrec[(size_t)qpos * CoopRecord<N, KD>::kLen + CoopRecord<N, KD>::kU + k] = u[k];
     }
     if (a.u) store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);
 #ifndef ABRB_DBG_TIMING
@@ -372,7 +376,7 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
     if (a.g.n_peer > 0 && nvalid > 0) {
       const unsigned bytes = (unsigned)nvalid * N * (unsigned)sizeof(T);
       const size_t off = (size_t)(a.g.row0 + warp_b0) * N * sizeof(T);
-      if (a.g.bulk != 0 && ((bytes | (unsigned)off) & 15u) == 0u) {
+      if (ABRB_GATHER_BULK && a.g.bulk != 0 && ((bytes | (unsigned)off) & 15u) == 0u) {
         if (lane == 0) bulk_wait_read();  // the previous tile's copies have read the buffer
         __syncwarp();
 #pragma unroll
