@@ -41,8 +41,7 @@ template <int N, int KD, bool COPY_A>
 struct CoopLayout {
   static constexpr int kW = KD > N ? KD : N;
   static constexpr int kY = 0, kZ = kW, kA = 2 * kW;
-  static constexpr int kQ = 2 * kW + (COPY_A ? KD * N : 0);  // where this lane's record went (-1: not deferred), see WarpCoop
-  static constexpr int kSlots = kQ + 1;
+  static constexpr int kSlots = 2 * kW + (COPY_A ? KD * N : 0);
 };
 
 // One-sided Jacobi SVD of NS independent KD x N matrices (NS = 1 or 2, interleaved) whose row `sub` and right-hand-side
@@ -150,30 +149,9 @@ __device__ __noinline__ void coop_pinv_warp(unsigned mask, const T *abase, T *xy
 // to the rows already written.  Records that do not fit are handled in line as above.
 template <int N, int KD>
 struct CoopRecord {
-  // A (KD x N), the Cholesky factor of M (lower triangle), y, z, and the row of u the owner computed WITHOUT the task-space
-  // term (stored by the kernel once the evaluation has returned): the flush writes u + du, it never reads global memory
-  static constexpr int kA = 0, kL = KD * N, kY = kL + N * (N + 1) / 2, kZ = kY + KD, kU = kZ + KD, kLen = kU + N;
+  static constexpr int kA = 0, kL = KD * N, kY = kL + N * (N + 1) / 2, kZ = kY + KD, kLen = kZ + KD;
 };
-// Queue capacity of a CTA: six records per warp (24 for the 128-thread CTAs, against 20 groups).  Not more: with 8 the
-// fp64 kernels' shared memory (2 CTAs x 99.4 KB with the bulk-copy buffer) crosses the SM's 196 KB carve-out step, the L1
-// that serves the register spills shrinks from 60 to 28 KB and every fp64 OSC kernel loses 3 us (53.7 vs 50.4 us).
-constexpr int kCoopQueuePerWarp = 6;
-
-// Bulk asynchronous copy shared -> global (any rank's memory: TMA, cp.async.bulk), tracked by the issuing thread's bulk
-// async-group; the fused all-gather of the OSC kernel sends every finished tile of u to every rank with these.
-__device__ __forceinline__ void bulk_store(void *dst_global, const void *src_shared, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global),
-               "r"((unsigned)__cvta_generic_to_shared(src_shared)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// the copies issued by this thread have READ their source (the buffer may be rewritten)
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-// the copies issued by this thread are complete; the proxy fence orders them before later ordinary accesses
-__device__ __forceinline__ void bulk_wait_all() {
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  asm volatile("fence.proxy.async;" ::: "memory");
-}
+constexpr int kCoopQueuePerWarp = 8;  // queue capacity of a CTA: eight records per warp
 
 template <typename T>
 struct FlushOut {
@@ -185,7 +163,7 @@ struct FlushOut {
 
 // One round of the CTA's groups over the queue: group j of the CTA takes records j, j + G, ... (NS at a time).
 template <typename T, int N, int KD, int NS>
-__device__ __forceinline__ void coop_flush_round(T *qrec, const long long *qrow, int n, int first, int stride,
+__device__ __forceinline__ void coop_flush_round(const T *qrec, const long long *qrow, int n, int first, int stride,
                                                  const FlushOut<T> &o, double rcond, bool two) {
   typedef CoopRecord<N, KD> RC;
   const int lane = threadIdx.x & 31;
@@ -194,7 +172,7 @@ __device__ __forceinline__ void coop_flush_round(T *qrec, const long long *qrow,
   const bool spare = G::group(lane) >= G::kPerWarp;
   JacobiRow<N, KD> me[NS];
   bool have[NS], owner[NS];
-  T *rec[NS];
+  const T *rec[NS];
   double wy[NS][N], wz[NS][N];
   const int row_ = sub < KD ? sub : 0;
 #pragma unroll
@@ -223,10 +201,11 @@ __device__ __forceinline__ void coop_flush_round(T *qrec, const long long *qrow,
         }
       }
       const int64_t row = qrow[first + s * stride];
-      const T v = T(double(rec[s][RC::kU + sub]) - dy - (two ? dz : 0.0));
+      const T *src = o.u != nullptr ? o.u + row * N + sub : o.peer[o.self] + (o.row0 + row) * N + sub;
+      const T v = T(double(*src) - dy - (two ? dz : 0.0));
       if (o.u != nullptr) o.u[row * N + sub] = v;
       if (o.train != nullptr) o.train[row * N + sub] = T(double(o.train[row * N + sub]) - dy);
-      rec[s][RC::kU + sub] = v;  // the final row, for the gathered copies (coop_flush_cta)
+      for (int p = 0; p < o.n_peer; ++p) o.peer[p][(o.row0 + row) * N + sub] = v;
     }
   }
 }
@@ -235,7 +214,7 @@ __device__ __forceinline__ void coop_flush_round(T *qrec, const long long *qrow,
 // more, each group takes two records through the pass together (the rounds are latency-bound, two interleaved chains
 // cost ~1.2x one) — a CTA whose queue happens to hold more records than it has groups is otherwise the kernel's tail.
 template <typename T, int N, int KD>
-__device__ __noinline__ void coop_flush_cta(T *qrec, const long long *qrow, int n, const FlushOut<T> &o, double rcond,
+__device__ __noinline__ void coop_flush_cta(const T *qrec, const long long *qrow, int n, const FlushOut<T> &o, double rcond,
                                             bool two) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   constexpr int kPerWarp = CoopGroup<N, KD>::kPerWarp;
@@ -245,19 +224,6 @@ __device__ __noinline__ void coop_flush_cta(T *qrec, const long long *qrow, int 
   } else {
     for (int base = 0; base < n; base += 2 * groups)  // CTA-uniform trip count
       if (base + warp * kPerWarp < n) coop_flush_round<T, N, KD, 2>(qrec, qrow, n, base + mine, groups, o, rcond, two);
-  }
-  if (o.n_peer > 0) {
-    // Fused all-gather: the tiles' rows travel to the ranks as bulk copies that may still be in flight; they had the whole
-    // pass to land.  Once every warp's copies are complete the final rows of the deferred states go on top of them.
-    if (lane == 0) bulk_wait_all();
-    __syncthreads();
-    typedef CoopRecord<N, KD> RC;
-    for (int i = threadIdx.x; i < n * N; i += blockDim.x) {
-      const int e = i / N, k = i - e * N;
-      const T v = qrec[(size_t)e * RC::kLen + RC::kU + k];
-      const int64_t at = (o.row0 + qrow[e]) * N + k;
-      for (int p = 0; p < o.n_peer; ++p) o.peer[p][at] = v;
-    }
   }
 }
 
@@ -283,10 +249,6 @@ struct WarpCoop {
   int *qcount = nullptr;
   long long row = 0;  // this lane's state index
   int qcap = 0;       // queue capacity (records)
-  // Where this lane's record went is parked in the exchange area, not in a register that would stay live through the
-  // rest of the evaluation: the kernel clears it before the evaluation and reads it back afterwards to add the row of u.
-  __device__ __forceinline__ void clear_qpos() { xch[LY::kQ * 32 + lane] = T(-1); }
-  __device__ __forceinline__ int take_qpos() const { return int(xch[LY::kQ * 32 + lane]); }
 
   template <typename T_, int N_, int KD_, class LGet>
   __device__ __forceinline__ void pinv(bool slow, K_ &K, LGet L, const T *y, const T *z, T *wy, T *wz, bool two,
@@ -301,7 +263,6 @@ struct WarpCoop {
         const int pos = atomicAdd(qcount, 1);
         if (pos < qcap) {
           queued = true;
-          xch[LY::kQ * 32 + lane] = T(pos);
           T *rec = qrec + (size_t)pos * RC::kLen;
           qrow[pos] = row;
 #pragma unroll

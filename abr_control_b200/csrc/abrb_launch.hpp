@@ -27,7 +27,6 @@ struct GatherArgs {
   int64_t row0 = 0;                         // first row of this rank's block in the gathered array
   unsigned long long epoch = 0;
   unsigned *cta_counter = nullptr;          // local: CTAs of this launch that have finished
-  int bulk = 1;                             // 1: tiles travel as bulk copies (cp.async.bulk), 0: as the warps' own stores
 };
 
 struct OscCall {

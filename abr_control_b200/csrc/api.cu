@@ -25,7 +25,6 @@ struct abrb_osc {
   const abrb_model *model;
   abrb_osc_params params;
   int64_t host_chunk = 0;  // option "host_chunk_states": states per pipeline chunk of the *_host entry points, 0 = auto
-  int gather_bulk = 1;     // option "gather_bulk_copies": the fused all-gather sends tiles as bulk copies (1) or stores (0)
   int host_streams = 2;    // option "host_upload_streams": copy streams per chunk (1: q, dq, target in turn; 2: dq beside
                            // q; 3: per-state targets on a stream of their own as well)
 };
@@ -413,10 +412,6 @@ int abrb_osc_set_option(abrb_osc *c, const char *name, double value) {
     c->host_chunk = value > 0 ? (int64_t)value : 0;
     return ABRB_OK;
   }
-  if (std::strcmp(name, "gather_bulk_copies") == 0) {
-    c->gather_bulk = value != 0.0 ? 1 : 0;
-    return ABRB_OK;
-  }
   if (std::strcmp(name, "host_upload_streams") == 0) {
     if (!(value >= 1 && value <= 3)) return fail(ABRB_EINVAL, "abrb_osc_set_option: host_upload_streams must be 1, 2 or 3");
     c->host_streams = (int)value;
@@ -745,7 +740,6 @@ static int osc_generate_gather(const abrb_osc *c, int frame_id, const double *x_
   ga.self = g->rank;
   ga.row0 = row0;
   ga.epoch = ++g->epoch;
-  ga.bulk = c->gather_bulk;
   for (int r = 0; r < g->world; ++r) {
     char *base = static_cast<char *>(g->peer[r]);
     ga.peer_u[r] = base + (size_t)buffer_index * g->bytes;

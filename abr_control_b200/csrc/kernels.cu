@@ -216,17 +216,6 @@ struct OscQueue {
   static constexpr size_t kBytes = kCountOff + 32;  // count (int), next tile (long long)
 };
 
-// Behind the queue: one row-major (32, N) tile of u per warp, the SOURCE of the bulk copies (TMA, cp.async.bulk) that
-// carry a finished tile into every rank's gathered array (fused all-gather).  Unlike the pitch-33 staging tile it must
-// stay untouched until the copy engine has read it, so it is a buffer of its own (<= 1792 bytes per warp).
-#ifndef ABRB_GATHER_BULK
-#define ABRB_GATHER_BULK 1  // 0: build without the bulk-copy epilogue (A/B builds)
-#endif
-template <typename T, int N>
-struct OscBulk {
-  static constexpr size_t kPerWarp = ABRB_GATHER_BULK ? (size_t)32 * N * sizeof(T) : 0;  // a multiple of 16
-};
-
 // One pass over the batch, persistent CTAs (grid = resident CTAs, tiles round-robin).  The states whose task-space
 // inertia needs the truncating pseudo-inverse (3.8 % of uniformly random UR5 6-DOF states: 70 % of the warps hold one)
 // leave a record in the CTA's queue and are finished by the whole CTA cooperatively (abrb_coop.cuh) once 16 of them
@@ -294,7 +283,6 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
   T *qrec = reinterpret_cast<T *>(qbase);
   long long *qrow = reinterpret_cast<long long *>(qbase + Q::kRowOff);
   int *qcount = reinterpret_cast<int *>(qbase + Q::kCountOff);
-  T *bulk = reinterpret_cast<T *>(qbase + (Q::kBytes + 15) / 16 * 16 + warp * OscBulk<T, N>::kPerWarp);
   if (threadIdx.x == 0) *qcount = 0;
   __syncthreads();
 #ifdef ABRB_DBG_TIMING  // (timing experiments only) per-CTA cycle counts are written over the training-signal buffer
@@ -355,43 +343,16 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
     }
     coop.valid = lane < nvalid;
     coop.row = b;
-    coop.clear_qpos();
     osc_eval<T, N, KD, false>(P, O, q, dq, tg, a.tv != nullptr ? tv : nullptr, a.ierr != nullptr ? ie : nullptr, u, tr,
                               (T *)nullptr, K, coop);
-    const int qpos = coop.take_qpos();
-    if (qpos >= 0) {  // a deferred state: its row of u (without the task-space term) completes the record
-#pragma unroll
-      for (int k = 0; k < N; ++k) qrec[(size_t)qpos * CoopRecord<N, KD>::kLen + CoopRecord<N, KD>::kU + k] = u[k];
-    }
     if (a.u) store_records<T, N>(a.u, warp_b0, nvalid, u, stage, lane);
 #ifndef ABRB_DBG_TIMING
     if (a.train) store_records<T, N>(a.train, warp_b0, nvalid, tr, stage, lane);
 #endif
     if (a.ierr) store_records<T, 6>(a.ierr, warp_b0, nvalid, ie, stage, lane);
-    // fused all-gather: this tile's rows go to every rank's gathered array while the SM computes on.  The warp lays its
-    // (32, N) tile of u out row-major in its bulk buffer and one lane hands ONE bulk copy per rank to the copy engine
-    // (cp.async.bulk, 1.5 KB each for fp64): the NVLink traffic of a tile drains under the next tile's arithmetic
-    // instead of holding the warps at their stores.  (Ragged tails whose size or address is not a multiple of 16 bytes
-    // take ordinary stores.)
-    if (a.g.n_peer > 0 && nvalid > 0) {
-      const unsigned bytes = (unsigned)nvalid * N * (unsigned)sizeof(T);
-      const size_t off = (size_t)(a.g.row0 + warp_b0) * N * sizeof(T);
-      if (ABRB_GATHER_BULK && a.g.bulk != 0 && ((bytes | (unsigned)off) & 15u) == 0u) {
-        if (lane == 0) bulk_wait_read();  // the previous tile's copies have read the buffer
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < N; ++k) bulk[lane * N + k] = u[k];
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the copy engine
-        __syncwarp();
-        if (lane == 0) {
-          for (int p = 0; p < a.g.n_peer; ++p) bulk_store(static_cast<char *>(a.g.peer_u[p]) + off, bulk, bytes);
-          bulk_commit();
-        }
-      } else {
-        for (int p = 0; p < a.g.n_peer; ++p)
-          store_records<T, N>(static_cast<T *>(a.g.peer_u[p]), a.g.row0 + warp_b0, nvalid, u, stage, lane);
-      }
-    }
+    // fused all-gather: this tile's rows go to every rank's gathered array while the other warps still compute
+    for (int p = 0; p < a.g.n_peer; ++p)
+      store_records<T, N>(static_cast<T *>(a.g.peer_u[p]), a.g.row0 + warp_b0, nvalid, u, stage, lane);
     // deferred states: emptied once a full round of the CTA's groups has gathered, and after the last tile
 #ifdef ABRB_DBG_TIMING
     const long long dbg_w0 = clock64();
@@ -441,7 +402,6 @@ osc_kernel(const __grid_constant__ ChainK<T, N> P, const __grid_constant__ OscK<
   if (a.g.n_peer > 0) {
     // completion: once every CTA's peer stores are visible system-wide, the last CTA publishes this launch's epoch
     // in every rank's flag array; abrb_gather_wait() on the consumer side spins on those flags
-    if (lane == 0) bulk_wait_all();
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -811,8 +771,7 @@ int osc_go(const ChainHost &h, const abrb_osc_params &p, const OscCall &c) {
   constexpr bool KSMEM = sizeof(T) == 8 || ABRB_KSMEM_F32 || ABRB_ROLLED;  // rolled loops index the scratch at run time
   constexpr int kOscBlock = OscBlock<T, ORTHO>::value, kOscWarps = kOscBlock / 32;
   const size_t smem = ((size_t)kOscWarps * OscSmem<T, N, ORTHO, KD, KSMEM>::kElems * sizeof(T) + 15) / 16 * 16 +
-                      (OscQueue<T, N, KD, kCoopQueuePerWarp * kOscWarps>::kBytes + 15) / 16 * 16 +
-                      kOscWarps * OscBulk<T, N>::kPerWarp;
+                      OscQueue<T, N, KD, kCoopQueuePerWarp * kOscWarps>::kBytes;
   auto kern = osc_kernel<T, N, ORTHO, KD, KSMEM>;
   cudaError_t e = set_smem(kern, smem);
   if (e != cudaSuccess) return (int)e;

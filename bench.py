@@ -458,9 +458,6 @@ def run_ours(args):
             return pg.generate(ctrlr, q, dq, tg)
 
         t_fused = timed(step_fused, n_it, 20)
-        ctrlr.set_option("gather_bulk_copies", 0)  # the same epilogue with the warps' own stores instead of bulk copies
-        t_fused_st = timed(step_fused, n_it, 20)
-        ctrlr.set_option("gather_bulk_copies", 1)
         full = step_fused(0)  # parity of the fused gather: every rank's block equals an NCCL gather of the same step
         dist.all_gather_into_tensor(gbuf, step(0))
         torch.cuda.synchronize()
@@ -480,7 +477,6 @@ def run_ours(args):
             "kernel_only_us": t / args.steps * 1e6,
             "kernel_then_nccl_allgather_us": t_seq * 1e6,
             "kernel_with_fused_peer_store_us": t_fused * 1e6,
-            "kernel_with_fused_peer_store_plain_stores_us": t_fused_st * 1e6,
             "fused_nvlink_bytes_out_per_rank": payload * (world - 1),
             "fused_nvlink_GBps_out_per_rank": payload * (world - 1) / t_fused / 1e9,
             "fused_matches_nccl": same,
@@ -504,9 +500,6 @@ def run_ours(args):
         t5 = timed(lambda i: c5.generate_into(*s5[i % 12], u5), 40, 5)
         pg5 = parallel.PeerGather(world * B5, 6, torch.float32)
         t5g = timed(lambda i: pg5.generate(c5, *s5[i % 12]), 40, 5)
-        c5.set_option("gather_bulk_copies", 0)
-        t5gs = timed(lambda i: pg5.generate(c5, *s5[i % 12]), 40, 5)
-        c5.set_option("gather_bulk_copies", 1)
         g5 = torch.empty((world * B5, 6), dtype=torch.float32, device=dev)
 
         def step5_nccl(i):
@@ -517,8 +510,7 @@ def run_ours(args):
         pg5.close()
         multi["config5_jaco2_avoid_f32"] = {
             "states_per_gpu": B5, "global_states": world * B5, "us_per_step_no_gather": t5 * 1e6,
-            "us_per_step_fused_gather": t5g * 1e6, "us_per_step_fused_gather_plain_stores": t5gs * 1e6,
-            "us_per_step_nccl_gather": t5n * 1e6,
+            "us_per_step_fused_gather": t5g * 1e6, "us_per_step_nccl_gather": t5n * 1e6,
             "evals_per_s_fused_gather": world * B5 / t5g, "evals_per_s_no_gather": world * B5 / t5,
             "gather_payload_bytes_total": world * B5 * 6 * 4, "gather_ok": ok5}
     # ---- BASELINE config 4 at its stated scale: UR5 OSC(kp=10) closed-loop rollouts, 512 trajectories per GPU

@@ -160,8 +160,6 @@ int abrb_osc_destroy(abrb_osc *c);
  *                        (default: dq beside q) or 3 (per-state targets on a stream of their own as well); default from
  *                        ABRB_HOST_STREAMS.  Which is fastest depends on the host: one pinned host->device stream
  *                        reaches 18 to 54 GB/s on different B200 boxes of the same pool.
- *   "gather_bulk_copies" fused all-gather (abrb_osc_generate_gather_*): 1 (default) sends every finished tile to the
- *                        ranks as bulk asynchronous copies (cp.async.bulk), 0 as ordinary stores of the computing warps.
  * Returns ABRB_EINVAL for an unknown name.  Not thread safe against concurrent generate calls on the same handle. */
 int abrb_osc_set_option(abrb_osc *c, const char *name, double value);
 
