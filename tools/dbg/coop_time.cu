@@ -8,6 +8,7 @@
 using namespace abrb;
 
 struct Slot { static __device__ __forceinline__ int at(int r, int k) { return 12 + r * 6 + k; } };
+struct Layout { static constexpr int kY = 0, kZ = 6; };
 
 // one warp per CTA; `per_warp` waiting lanes per warp (1 .. 32); exchange area layout: [0,12) y z, [12,48) A
 __global__ void bench(const double *A, int n_states, int per_warp, long long *cycles, double *out) {
@@ -20,7 +21,7 @@ __global__ void bench(const double *A, int n_states, int per_warp, long long *cy
   __syncwarp();
   const unsigned mask = __ballot_sync(0xffffffffu, slow);
   const long long t0 = clock64();
-  coop_pinv_warp<double, 6, 6, Slot>(mask, xch, xch, lane, 1e-4, true);
+  coop_pinv_warp<double, 6, 6, Slot, Layout>(mask, xch, xch, lane, 1e-4, true);
   const long long t1 = clock64();
   __syncwarp();
   if (lane == 0) cycles[blockIdx.x] = t1 - t0;
@@ -42,7 +43,7 @@ int main(int argc, char **argv) {
   const int grid = 148;
   cudaMalloc(&dc, grid * 8);
   cudaMalloc(&dout, grid * 32 * 8);
-  for (int per_warp : {1, 4, 5, 8, 32}) {
+  for (int per_warp : {1, 4, 5, 6, 10, 32}) {  // five states per pass (six-lane groups)
     bench<<<grid, 32>>>(dA, n, per_warp, dc, dout);
     bench<<<grid, 32>>>(dA, n, per_warp, dc, dout);
     cudaDeviceSynchronize();
