@@ -547,6 +547,13 @@ def run_ours(args):
             u_host = ctrlr.generate(*host[i % n_host])
         sync_t.append(time.perf_counter() - t0)
     fence()
+    warm = [ctrlr.generate_async(*host[i % n_host], slot=i & 1) for i in range(2)]  # both slots' workspaces, untimed
+    for p_ in warm:
+        p_.wait()
+    warm = [ctrlr.generate_async(*host[i % n_host], slot=i & 1) for i in range(2)]
+    for p_ in warm:
+        p_.wait()
+    fence()
     for _ in range(blocks):
         t0 = time.perf_counter()
         pend = [None, None]
