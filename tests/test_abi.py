@@ -97,6 +97,11 @@ def test_model_handles_and_error_codes_without_compute():
     assert lib.abrb_osc_generate_host_async_f64(hc, 13, None, None, None, None, 6, None, 0, None, None, None, 8, 2) == _abi.EINVAL
     assert lib.abrb_osc_host_wait(hc, 0) == 0 and lib.abrb_osc_host_wait(hc, 5) == _abi.EINVAL
     assert lib.abrb_osc_set_option(hc, b"host_chunk_states", 32768.0) == 0
+    for k in (1.0, 2.0, 3.0):
+        assert lib.abrb_osc_set_option(hc, b"host_upload_streams", k) == 0
+    for k in (0.0, 4.0, float("nan")):
+        assert lib.abrb_osc_set_option(hc, b"host_upload_streams", k) == _abi.EINVAL
+        assert b"host_upload_streams" in lib.abrb_last_error()
     assert lib.abrb_osc_set_option(hc, b"no_such_option", 1.0) == _abi.EINVAL
     assert lib.abrb_osc_destroy(hk) == 0
     assert lib.abrb_osc_destroy(hc) == 0 and lib.abrb_model_destroy(h) == 0
