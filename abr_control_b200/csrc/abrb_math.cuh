@@ -1287,7 +1287,7 @@ ABRB_HD_NOINLINE void pinv_apply_sym(const T *Sin, unsigned active, T rcond, con
 // until all rows are mutually orthogonal, B = G A, B B^T = diag(s2), and then
 //   pinv(A A^T) y = sum_{i: s2_i > rcond * max s2} G_i^T (G y)_i / s2_i .
 // The pairs of one round (round-robin tournament schedule) are disjoint, so a round is ONE parallel step: on the GPU
-// each row lives in its own lane of an 8-lane group of the warp and the partners exchange rows with shuffles
+// each row lives in its own lane of a six- (eight-) lane group of the warp and the partners exchange rows with shuffles
 // (abrb_coop.cuh); the host instantiation (tests/hostsim) walks the same schedule sequentially.  Both use the
 // per-row step below, so the arithmetic is the same.
 template <int N, int KD>

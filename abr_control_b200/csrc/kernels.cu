@@ -216,10 +216,11 @@ struct OscQueue {
   static constexpr size_t kBytes = kCountOff + 32;  // count (int), next tile (long long)
 };
 
-// One pass over the batch, persistent CTAs (grid = resident CTAs, tiles round-robin).  The states whose task-space
-// inertia needs the truncating pseudo-inverse (3.8 % of uniformly random UR5 6-DOF states: 70 % of the warps hold one)
-// leave a record in the CTA's queue and are finished by the whole CTA cooperatively (abrb_coop.cuh) once 16 of them
-// have gathered or the CTA has run out of tiles; what does not fit the queue is finished by its warp in line.
+// One pass over the batch, persistent CTAs (grid = resident CTAs, tiles from a per-launch counter).  The states whose
+// task-space inertia needs the truncating pseudo-inverse (3.8 % of uniformly random UR5 6-DOF states: 70 % of the warps
+// hold one) leave a record in the CTA's queue and are finished by the whole CTA cooperatively (abrb_coop.cuh) once as
+// many as the CTA has groups (20 or 16) have gathered or the CTA has run out of tiles; what does not fit the queue is
+// finished by its warp in line.
 // CTA size of the OSC kernel.  Measured on B200 (UR5 6-DOF fp64, B = 65 536): 128 threads 60.4 us, 64 threads 65.7 us —
 // what ends the kernel is the CTA whose queue happens to hold more records than it has groups (a second Jacobi pass),
 // and smaller CTAs have fewer groups per queue; 256 threads do not fit the non-orthonormal fp64 scratch.
